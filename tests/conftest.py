@@ -1,0 +1,47 @@
+import importlib
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PKG_NAME = "genome-assembly-using-overlap-graphs_b200"
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "live_reference: needs the reference checkout (build container only)")
+
+
+def load_pkg(sub: str = ""):
+    return importlib.import_module(PKG_NAME + (("." + sub) if sub else ""))
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    return load_pkg()
+
+
+@pytest.fixture(scope="session")
+def golden_pairs():
+    with open(os.path.join(GOLDEN, "pairs.json")) as fh:
+        return json.load(fh)["cases"]
+
+
+@pytest.fixture(scope="session")
+def golden_graphs():
+    with open(os.path.join(GOLDEN, "graphs.json")) as fh:
+        return json.load(fh)["cases"]
+
+
+def has_cuda() -> bool:
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
