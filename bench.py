@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Benchmark of the overlap-detection hot path (BASELINE.json metric: overlap GCUPS).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--k K]
+    python bench.py --impl reference ...      # the CPU arm (oracle port on the host cores)
+
+A step = one pass of the hot path over the workload: pack -> k-mer keys -> prefix index ->
+candidate join -> overlap DP -> edge expansion (-> edge gather when N > 1).
+  value  GCUPS = sum over candidate pairs of len(a)*len(b) (cells as the reference fills them,
+         aligners.py:33-34) / step time, inputs resident in HBM.
+  e2e    the same through the host-buffer call (engine.overlap_edges): H2D of the reads and
+         D2H of the edge rows inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "genome-assembly-using-overlap-graphs_b200"
+
+METRIC = "overlap_gcups"
+UNIT = "GCUPS"
+OPS_PER_CELL = 7        # compare, select, 3 adds, 2 max
+
+
+def load_workload(name, seed):
+    synth = importlib.import_module(PKG + ".synth")
+    bases, offsets = synth.make_workload(name, seed)
+    ub, uo, counts, _ = synth.dedup(bases, offsets)           # host part of the builder (read_copies)
+    return ub, uo, counts, len(offsets) - 1
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu_index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_arm(ub, uo, pair_a, pair_b, target_s=12.0, nthreads=0):
+    """The oracle port of aligners.overlap_alignment (full matrices + traceback walk, like the
+    reference) over a bounded sample of the workload's candidate pairs, on all host threads."""
+    from oracle import overlap_oracle as orc
+    cores = orc.max_threads() if nthreads <= 0 else nthreads
+    lens = (uo[1:] - uo[:-1]).astype(np.int64)
+    rng = np.random.Generator(np.random.PCG64(99))
+    P = len(pair_a)
+    probe = min(P, 256 * cores)
+    sel = rng.choice(P, size=probe, replace=False) if P > probe else np.arange(P)
+    t0 = time.perf_counter()
+    orc.overlap_pairs(ub, uo, pair_a[sel], pair_b[sel], full=True, nthreads=cores)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    n = int(min(P, max(probe, probe * target_s / dt)))
+    sel = rng.choice(P, size=n, replace=False) if P > n else np.arange(P)
+    cells = int((lens[pair_a[sel]] * lens[pair_b[sel]]).sum())
+    t0 = time.perf_counter()
+    orc.overlap_pairs(ub, uo, pair_a[sel], pair_b[sel], full=True, nthreads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": cells / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} of {P} candidate pairs ({cells:.3e} cells) in {dt:.2f} s, oracle/overlap_oracle.c "
+                      f"ovo_overlap_pairs(full=1), OpenMP x{cores}",
+            "seconds": dt, "pairs": n, "cells": cells}
+
+
+def host_candidate_pairs(ub, uo, k):
+    """Candidate list on the host for the CPU arm (NumPy k-mer join, same rule as
+    overlapGraphs.py:30-52).  Not timed."""
+    lens = (uo[1:] - uo[:-1]).astype(np.int64)
+    U = len(lens)
+    code = np.zeros(256, np.uint64)
+    for i, ch in enumerate(b"ACGT"):
+        code[ch] = i
+    valid = np.nonzero(lens >= k)[0]
+    pk = np.zeros(len(valid), np.uint64)
+    sk = np.zeros(len(valid), np.uint64)
+    for i in range(k):
+        pk = pk * np.uint64(4) + code[ub[uo[valid] + i]]
+        sk = sk * np.uint64(4) + code[ub[uo[valid + 1] - k + i]]
+    order = np.argsort(pk, kind="stable")
+    spk = pk[order]
+    lo = np.searchsorted(spk, sk, "left")
+    hi = np.searchsorted(spk, sk, "right")
+    cnt = hi - lo
+    a = np.repeat(valid, cnt)
+    starts = np.repeat(lo, cnt)
+    within = np.arange(int(cnt.sum())) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+    b = valid[order][starts + within]
+    keep = a != b
+    return a[keep].astype(np.int32), b[keep].astype(np.int32)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ub, uo, counts, n_reads = load_workload(args.workload, args.seed)
+    pa, pb = host_candidate_pairs(ub, uo, args.k)
+    per_step = max(2.0, min(20.0, 60.0 / max(args.steps + args.warmup, 1)))
+    vals, secs = [], []
+    last = None
+    for it in range(args.warmup + args.steps):
+        last = cpu_arm(ub, uo, pa, pb, target_s=per_step)
+        if it >= args.warmup:
+            vals.append(last["value"]); secs.append(last["seconds"])
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": args.workload, "k": args.k, "seed": args.seed, "unique_reads": int(len(counts)),
+                       "candidate_pairs": int(len(pa))},
+            "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    line["cpu_baseline"]["value"] = v
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    engine_mod = importlib.import_module(PKG + ".engine")
+    par = importlib.import_module(PKG + ".parallel")
+    eng = engine_mod.get_engine(local_rank)
+    dev = eng.device
+
+    ub, uo, counts, n_reads = load_workload(args.workload, args.seed)
+    U = len(counts)
+    total_bases = int(uo[-1])
+    max_len = int((uo[1:] - uo[:-1]).max())
+    has_dups = bool(counts.max() > 1)
+
+    # pinned host buffers (the e2e leg copies from these every step)
+    h_bases = torch.from_numpy(ub[:total_bases].copy()).pin_memory()
+    h_off = torch.from_numpy(uo.copy()).pin_memory()
+    h_counts = torch.from_numpy(counts.copy()).pin_memory()
+    node_off_np = np.zeros(U + 1, np.int64)
+    np.cumsum(counts, out=node_off_np[1:])
+
+    # device-resident inputs for the `value` leg
+    d_ascii = torch.empty(total_bases + 64, dtype=torch.uint8, device=dev)
+    d_ascii[:total_bases].copy_(h_bases)
+    d_off = h_off.to(dev)
+    d_copies = h_counts.to(dev) if has_dups else None
+    d_node_off = torch.from_numpy(node_off_np).to(dev) if has_dups else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    shard = (rank, world)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def device_step(record=None):
+        rs = eng.pack_reads(d_ascii, d_off, U, max_len)
+        index = eng.kmer_index(rs, args.k) if args.k > 0 else None
+        pa, pb, _ = eng.candidate_pairs(rs, index, args.k, shard)
+        if record is not None:
+            record["dp0"].record()
+        score, end = eng.overlap_scores(rs, pa, pb)
+        if record is not None:
+            record["dp1"].record()
+        edges = eng.expand_edges(pa, pb, score, end, d_copies, d_node_off)
+        if world > 1:
+            edges_all = par.gather_edges(edges, 0)
+        else:
+            edges_all = edges
+        return rs, pa, pb, edges, edges_all
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- untimed: workload statistics (cells as the reference fills them)
+    rs, pa, pb, edges, edges_all = device_step()
+    torch.cuda.synchronize()
+    eng.check_alphabet(rs)
+    lens_d = rs.length[:U].to(torch.int64)
+    cells_local = int((lens_d[pa.long()] * lens_d[pb.long()]).sum().item()) if pa.numel() else 0
+    pairs_local = int(pa.shape[0])
+    edges_local = int(edges.shape[0])
+    stat = torch.tensor([cells_local, pairs_local, edges_local], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(stat)
+    cells, pairs, n_edges = (int(x) for x in stat.cpu().tolist())
+    checksum = int(edges_all.to(torch.int64).sum().item()) if (rank == 0 and edges_all is not None) else 0
+    plan = eng.dp_plan(max_len)
+    del rs, pa, pb, edges, edges_all
+
+    # ---- value leg: inputs resident in HBM
+    for _ in range(args.warmup):
+        device_step()
+        flush.zero_()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    step_ms, dp_ms = [], []
+    launches0 = eng.launches
+    for _ in range(args.steps):
+        flush.zero_()                                   # flush L2 between timed iterations
+        rec = {"dp0": ev(), "dp1": ev()}
+        e0, e1 = ev(), ev()
+        barrier()
+        e0.record()
+        device_step(rec)
+        e1.record()
+        barrier()
+        step_ms.append(e0.elapsed_time(e1))
+        dp_ms.append(rec["dp0"].elapsed_time(rec["dp1"]))
+    launches = eng.launches - launches0
+    clocks = sampler.stop()
+    t = torch.tensor([sum(step_ms), sum(dp_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)        # max over ranks
+    total_ms, dp_total_ms = (float(x) for x in t.cpu().tolist())
+    ms_per_step = total_ms / args.steps
+    value = cells / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e leg: host buffers in, host edge rows out, every step
+    def e2e_step():
+        out = eng.overlap_edges(h_bases, h_off, h_counts if has_dups else None, args.k, shard)
+        if world > 1:
+            g = par.gather_edges(torch.from_numpy(out).to(dev), 0)
+            if g is not None:
+                out = g.cpu().numpy()
+        return out
+
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    e2e_ms = []
+    d2h_bytes = 0
+    for _ in range(args.steps):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        out = e2e_step()
+        torch.cuda.synchronize()
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+        d2h_bytes = out.nbytes + 16
+    te = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_per_step = float(te.item()) / args.steps
+    h2d_bytes = total_bases + h_off.numel() * 8 + (h_counts.numel() * 4 + (U + 1) * 8 if has_dups else 0)
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (the DP): integer pipe, not HBM
+        probe = {}
+        names = {0: "iadd3", 1: "imad", 2: "vimnmx_s32", 3: "viaddmnmx_s16x2", 4: "dp_mix", 5: "prmt", 6: "lop3"}
+        import ctypes
+        nat = importlib.import_module(PKG + "._native")
+        for kind, nm in names.items():
+            g, ms = ctypes.c_double(), ctypes.c_double()
+            nat.check(nat.lib.ovl_int_peak_probe(eng._ctx, kind, 2000, ctypes.byref(g), ctypes.byref(ms)))
+            probe[nm] = round(g.value, 1)
+        dp_ms_avg = dp_total_ms / args.steps
+        cells_per_launch = cells / world                       # each rank launches the DP on its slice
+        achieved = cells_per_launch * OPS_PER_CELL / (dp_ms_avg * 1e-3) / 1e12
+        peak = probe["iadd3"] / 1e3
+        pk, pk_kind = peaks()
+        roofline = {"bound": "int32-alu", "kernel": f"overlap_dp_kernel<{plan['lanes']},{plan['cols']},{plan['mode']}>",
+                    "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak if peak else None,
+                    "traffic": None, "ops_per_cell": OPS_PER_CELL,
+                    "dp_gcups": cells_per_launch / (dp_ms_avg * 1e-3) / 1e9, "dp_ms": dp_ms_avg,
+                    "peak_source": "ovl_int_peak_probe kind 0 (IADD3 lane-ops/s), measured in this run",
+                    "int_probe_gops": probe, "hbm_peak_gbs": pk.get("hbm_gbs"), "hbm_peak_source": pk_kind}
+        # ---- CPU baseline on this box's host cores (bounded sample)
+        cpu = None
+        if not args.no_cpu_baseline:
+            pa_h, pb_h = host_candidate_pairs(ub, uo, args.k)
+            assert len(pa_h) == pairs, (len(pa_h), pairs)
+            cpu = cpu_arm(ub, uo, pa_h, pb_h, target_s=args.cpu_seconds)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "int16x2" if plan["mode"] == "packed16" else "int32",
+                "data": "synthetic",
+                "config": {"workload": args.workload, "k": args.k, "seed": args.seed, "reads": n_reads,
+                           "unique_reads": U, "max_read_len": max_len, "candidate_pairs": pairs, "edges": n_edges,
+                           "cells": cells, "edge_checksum": checksum, "sharding": f"pair-range x{world}",
+                           "l2": "flushed between timed iterations (256 MiB memset)",
+                           "scoring": "match 10, mismatch -1, indel -2^31 (reference defaults)"},
+                "pairs_per_s": pairs / (ms_per_step * 1e-3),
+                "e2e": {"value": cells / (e2e_per_step * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_per_step,
+                        "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="phix_n50000_l150")
+    ap.add_argument("--k", type=int, default=5)
+    ap.add_argument("--seed", type=int, default=12345)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,90 @@
+"""ctypes binding of libovl_b200.so (C ABI declared in include/ovl.h).
+
+There is no CPU fallback: if the shared library has not been built, importing this module
+raises, and if no CUDA device is present creating a context raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("OVL_B200_LIB", os.path.join(_HERE, "libovl_b200.so"))
+
+OVL_OK = 0
+OVL_E_CUDA = -1
+OVL_E_ARG = -2
+OVL_E_UNSUPPORTED = -3
+OVL_MAX_K = 32
+OVL_MAX_READ_LEN = 1216
+
+
+class OvlError(RuntimeError):
+    """A call into libovl_b200.so failed (message from ovl_last_error())."""
+
+
+class OvlUnsupported(OvlError, NotImplementedError):
+    """Valid input for the reference that the CUDA kernels do not cover."""
+
+
+if not os.path.isfile(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(nvcc, sm_100a). The overlap path has no CPU fallback.")
+
+lib = ctypes.CDLL(LIB_PATH)
+
+_vp = ctypes.c_void_p
+_i32 = ctypes.c_int32
+_i64 = ctypes.c_int64
+_sz = ctypes.c_size_t
+
+_SIGS = {
+    "ovl_last_error": (ctypes.c_char_p, []),
+    "ovl_version": (ctypes.c_int, []),
+    "ovl_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_vp)]),
+    "ovl_ctx_destroy": (ctypes.c_int, [_vp]),
+    "ovl_ctx_sm_count": (ctypes.c_int, [_vp]),
+    "ovl_row_words": (_i32, [_i32]),
+    "ovl_pack_reads": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "ovl_kmer_keys": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "ovl_index_workspace_bytes": (_sz, [_i64]),
+    "ovl_index_build": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ovl_join_workspace_bytes": (_sz, [_i64]),
+    "ovl_join_count": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ovl_join_fill": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "ovl_all_pairs_fill": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "ovl_overlap_dp": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _i64, _vp, _vp,
+                                      _i32, _i32, _i32, _vp]),
+    "ovl_overlap_dp_plan": (ctypes.c_int, [_i32, _i64, _i64, _i64, _i32, ctypes.POINTER(_i32 * 3)]),
+    "ovl_expand_workspace_bytes": (_sz, [_i64]),
+    "ovl_expand_count": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "ovl_expand_fill": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "ovl_expand_unit": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "ovl_align_pair_workspace_bytes": (_sz, [_i32, _i32]),
+    "ovl_align_pair": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp, _vp, _vp]),
+    "ovl_int_peak_probe": (ctypes.c_int, [_vp, _i32, _i32, ctypes.POINTER(ctypes.c_double),
+                                          ctypes.POINTER(ctypes.c_double)]),
+}
+
+EXPORTS = tuple(_SIGS)
+
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)      # AttributeError here == the .so does not match include/ovl.h
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error() -> str:
+    return lib.ovl_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc == OVL_OK:
+        return
+    msg = last_error()
+    if rc == OVL_E_UNSUPPORTED:
+        raise OvlUnsupported(msg)
+    if rc == OVL_E_ARG:
+        raise ValueError(msg)
+    raise OvlError(msg)

@@ -1,0 +1,67 @@
+"""Drop-in for the reference's ``aligners.overlap_alignment`` (aligners.py:6-82).
+
+Same name, same keyword arguments, same 5-tuple; the DP, the last-row arg-max and the
+traceback run on the GPU (kernel K7, csrc/align.cuh) -- there is no CPU fallback.
+Every other symbol of the reference's ``aligners`` module (local_alignment, ...) is outside
+the accelerated path and is forwarded to the reference module when its checkout is present
+(``OVL_REFERENCE_DIR``, default /root/reference).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+try:
+    from . import engine as _engine
+except ImportError:      # imported as a top-level module with the package directory on sys.path
+    import importlib as _il
+    import os as _os
+    import sys as _sys
+    _pkg_dir = _os.path.dirname(_os.path.abspath(__file__))
+    if _os.path.dirname(_pkg_dir) not in _sys.path:
+        _sys.path.append(_os.path.dirname(_pkg_dir))
+    _engine = _il.import_module(_os.path.basename(_pkg_dir) + ".engine")
+
+INDEL_DEFAULT = -2 ** 31
+
+
+def _codes(x: str) -> np.ndarray:
+    return np.frombuffer(x.encode("utf-32-le"), dtype=np.int32) if x else np.zeros(0, np.int32)
+
+
+def overlap_alignment(s, t, match_score=10, mismatch=-1, indel=-2 ** 31):
+    """Best suffix(s)/prefix(t) overlap alignment -- see aligners.py:6-26 for the contract.
+
+    Returns (alignment_to_print, align_s, align_t, best_score, alignment_end_position) with
+    ``best_score`` and ``alignment_end_position`` as Python ints.
+    """
+    if not isinstance(s, str) or not isinstance(t, str):
+        # the reference is @njit-compiled for unicode arguments and raises a TypingError here
+        raise TypeError("overlap_alignment expects str arguments (the reference raises a Numba TypingError)")
+    for name, v in (("match_score", match_score), ("mismatch", mismatch), ("indel", indel)):
+        if isinstance(v, bool) or not isinstance(v, (int, np.integer)):
+            raise TypeError(f"{name} must be an integer")
+        if not -2 ** 63 <= int(v) < 2 ** 63:
+            raise OverflowError(f"{name} does not fit int64")
+    eng = _engine.get_engine()
+    score, end, ops = eng.align_pair(_codes(s), _codes(t), int(match_score), int(mismatch), int(indel))
+    # rebuild the aligned strings from the device traceback (aligners.py:63-76)
+    i, j = len(s), end
+    a_s, a_t = [], []
+    for op in ops.tolist():
+        if op == 0:
+            a_s.append(s[i - 1]); a_t.append(t[j - 1]); i -= 1; j -= 1
+        elif op == 1:
+            a_s.append(s[i - 1]); a_t.append("-"); i -= 1
+        else:
+            a_s.append("-"); a_t.append(t[j - 1]); j -= 1
+    align_s = "".join(reversed(a_s))
+    align_t = "".join(reversed(a_t))
+    alignment_to_print = f"\nTarget:   {align_t}\n          {'|' * len(align_t)}\nQuery:    {align_s}"   # aligners.py:78
+    return alignment_to_print, align_s, align_t, int(score), int(end)
+
+
+def __getattr__(name):
+    ref = _engine.reference_module("aligners")
+    if ref is not None and hasattr(ref, name):
+        return getattr(ref, name)
+    raise AttributeError(f"module 'aligners' (B200 drop-in) has no attribute {name!r}")

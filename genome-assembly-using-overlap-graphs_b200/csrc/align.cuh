@@ -1,0 +1,67 @@
+// K7: one pair with traceback -- the whole of aligners.py:27-76 for the single-pair drop-in
+// (overlap_alignment returns the aligned strings as well as score/end).
+//
+// One CTA sweeps the anti-diagonals d = i + j; the cells of a diagonal are independent.
+// Arithmetic follows the reference exactly: candidates in int64 (Numba types indel as int64),
+// stored truncated to int32 (aligners.py:28, 35-48), tie order diag >= up >= left, first
+// strict maximum over the last row (aligners.py:50-57), traceback walk while i > 0 and j > 0
+// (aligners.py:63-76).  Sequences are int32 code points, so any alphabet works here.
+#pragma once
+#include "common.cuh"
+
+namespace ovl {
+
+constexpr int kAlignThreads = 1024;
+
+// workspace layout (int32 units): diag[3][n+1] | last_row[m+1] ; then tb[(n+1)*(m+1)] bytes
+__global__ void __launch_bounds__(kAlignThreads) align_pair_kernel(const int32_t* __restrict__ s, int n,
+                                                                   const int32_t* __restrict__ t, int m,
+                                                                   int64_t match, int64_t mismatch, int64_t indel,
+                                                                   int32_t* __restrict__ diag, int32_t* __restrict__ last_row,
+                                                                   int8_t* __restrict__ tb,
+                                                                   int32_t* __restrict__ result, uint8_t* __restrict__ ops) {
+    const int W = m + 1;
+    const int stride = n + 1;
+    for (int j = threadIdx.x; j <= m; j += blockDim.x) last_row[j] = 0;     // n == 0: row 0 is all zero
+    for (int i = threadIdx.x; i < 3 * stride; i += blockDim.x) diag[i] = 0;
+    __syncthreads();
+    for (int d = 2; d <= n + m; ++d) {
+        int32_t* cur = diag + (d % 3) * stride;
+        const int32_t* p1 = diag + ((d - 1) % 3) * stride;
+        const int32_t* p2 = diag + ((d - 2) % 3) * stride;
+        int ilo = max(1, d - m), ihi = min(n, d - 1);
+        for (int i = ilo + (int)threadIdx.x; i <= ihi; i += blockDim.x) {
+            int j = d - i;
+            int64_t dg = (int64_t)p2[i - 1] + (s[i - 1] == t[j - 1] ? match : mismatch);
+            int64_t up = (int64_t)p1[i - 1] + indel;
+            int64_t lf = (int64_t)p1[i] + indel;
+            int32_t v;
+            int8_t dir;
+            if (dg >= up && dg >= lf) { v = (int32_t)dg; dir = 0; }
+            else if (up >= lf)        { v = (int32_t)up; dir = 1; }
+            else                      { v = (int32_t)lf; dir = 2; }
+            cur[i] = v;
+            tb[(size_t)i * W + j] = dir;
+            if (i == n) last_row[j] = v;
+        }
+        // boundary cells of this diagonal: dp[0][d] and dp[d][0] are zero
+        if (threadIdx.x == 0) { cur[0] = 0; if (d <= n) cur[d] = 0; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int32_t best = last_row[0];          // j = 0 beats -inf (aligners.py:51-57)
+        int bj = 0;
+        for (int j = 1; j <= m; ++j) if (last_row[j] > best) { best = last_row[j]; bj = j; }
+        int i = n, j = bj, L = 0;
+        while (i > 0 && j > 0) {
+            int8_t dir = tb[(size_t)i * W + j];
+            ops[L++] = (uint8_t)dir;
+            if (dir == 0) { --i; --j; } else if (dir == 1) { --i; } else { --j; }
+        }
+        result[0] = best;
+        result[1] = bj;
+        result[2] = L;
+    }
+}
+
+}  // namespace ovl

@@ -1,0 +1,319 @@
+// k-mer stages of the overlap graph builder (replaces overlapGraphs.py:30-52, 55-60):
+//   K0 pack_reads      ASCII -> 2-bit packed rows (+ length, non-ACGT detection)
+//   K1 kmer_keys       prefix / suffix k-mer of every read as a 2k-bit integer
+//   K2 radix passes    stable LSD sort of (prefix_key, uid)  == the reference's prefix_index
+//   K3 join_count/fill suffix_key[a] == prefix_key[b], a != b  -> ordered candidate pairs
+//   K6 expand_*        (a, b, score, end) -> copy_a x copy_b edge rows
+// All of these are HBM-bound byte/integer work: coalesced, 128-bit where the layout allows.
+#pragma once
+#include "common.cuh"
+
+namespace ovl {
+
+// Base code: (c >> 1) & 3  ->  A=0, C=1, T=2, G=3.  Any bijection works: keys are only
+// compared for equality and the DP only tests s[i] == t[j].
+constexpr uint64_t kInvalidKey = ~0ull;
+
+// ------------------------------------------------------------------ K0 pack_reads
+// One thread per output word (16 bases).  The read's ASCII bytes start at an arbitrary byte
+// offset, so each thread loads the two aligned 16-byte segments that cover its 16 bytes and
+// funnel-shifts them into place (neighbouring threads share segments through L1, DRAM sees
+// each byte once).  Requires: ascii base 16-byte aligned and >= 32 bytes of slack after the
+// last read.
+__global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t* __restrict__ ascii,
+                                                         const int64_t* __restrict__ offsets,
+                                                         int64_t U, int row_words,
+                                                         uint32_t* __restrict__ packed,
+                                                         int32_t* __restrict__ len_out,
+                                                         int32_t* __restrict__ bad_count) {
+    int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = U * row_words;
+    if (slot >= total) return;
+    int64_t u = slot / row_words;
+    int w = (int)(slot - u * row_words);
+    int64_t o0 = offsets[u];
+    int len = (int)(offsets[u + 1] - o0);
+    if (w == 0) len_out[u] = len;
+    int nvalid = len - 16 * w;                       // bases this word holds
+    if (nvalid <= 0) { packed[slot] = 0u; return; }
+    if (nvalid > 16) nvalid = 16;
+
+    int64_t addr = o0 + 16 * (int64_t)w;             // byte index of the first base
+    const uint4* seg = reinterpret_cast<const uint4*>(ascii + (addr & ~(int64_t)15));
+    uint4 q0 = __ldg(seg), q1 = __ldg(seg + 1);
+    unsigned sh = (unsigned)(addr & 15);
+    uint32_t x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    // shift right by sh bytes: 8, 4, then 0..3 bytes
+    uint32_t y[6], z[5], r[4];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] = (sh & 8) ? x[i + 2] : x[i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) z[i] = (sh & 4) ? y[i + 1] : y[i];
+    unsigned bs = (sh & 3) * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = __funnelshift_r(z[i], z[i + 1], bs);
+
+    uint32_t out = 0, bad = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int nv = nvalid - 4 * i;                     // valid bytes in this word
+        uint32_t keep = nv >= 4 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u));
+        uint32_t c = (r[i] & keep) | (0x41414141u & ~keep);          // filler 'A' -> code 0
+        uint32_t t = (c >> 1) & 0x03030303u;
+        // exact check: rebuild the byte each code stands for and compare
+        uint32_t is_t = (t >> 1) & ~t & 0x01010101u;                 // code 2 == 'T'
+        uint32_t expect = 0x41414141u + 2u * t + 0x0fu * is_t;       // A 41, C 43, G 47, T 54
+        bad |= c ^ expect;
+        // gather the four 2-bit fields (at bits 0,8,16,24) into one byte with a multiply
+        uint32_t pk = (t * 0x01041040u) >> 24;
+        out |= pk << (8 * i);
+    }
+    packed[slot] = out;
+    if (bad) atomicAdd(bad_count, 1);
+}
+
+// ------------------------------------------------------------------ K1 kmer_keys
+// overlapGraphs.py:33-37 (prefix = read[:k]) and :44-47 (suffix = read[-k:]); reads shorter
+// than k can only ever match themselves: they get a placeholder key and are kept
+// out of the index and the lookups by their length (a 32-mer of all G is a real key ~0).
+__device__ __forceinline__ uint64_t extract_bits64(const uint32_t* __restrict__ row, int row_words, int bitpos) {
+    int w = bitpos >> 5, s = bitpos & 31;
+    uint32_t a = row[w];
+    uint32_t b = w + 1 < row_words ? row[w + 1] : 0u;
+    uint32_t c = w + 2 < row_words ? row[w + 2] : 0u;
+    uint32_t lo = __funnelshift_r(a, b, s);
+    uint32_t hi = __funnelshift_r(b, c, s);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+__global__ void __launch_bounds__(256) kmer_keys_kernel(const uint32_t* __restrict__ packed, int row_words,
+                                                        const int32_t* __restrict__ len, int64_t U, int k,
+                                                        uint64_t* __restrict__ prefix_key,
+                                                        uint64_t* __restrict__ suffix_key) {
+    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= U) return;
+    int n = len[u];
+    uint64_t pk = kInvalidKey, sk = kInvalidKey;
+    if (n >= k) {
+        const uint32_t* row = packed + u * row_words;
+        uint64_t mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+        pk = (((uint64_t)row[1] << 32) | row[0]) & mask;
+        sk = extract_bits64(row, row_words, 2 * (n - k)) & mask;
+    }
+    prefix_key[u] = pk;
+    suffix_key[u] = sk;
+}
+
+// ------------------------------------------------------------------ K2 radix sort (stable, LSD, 8-bit digits)
+// Each warp owns kSortChunk consecutive elements; a pass is: per-warp digit histogram ->
+// exclusive scan over (digit-major, warp-minor) -> per-warp stable scatter.  Stability keeps
+// uids ascending inside a bucket, which is the reference's bucket-append order
+// (overlapGraphs.py:38-40).  Pass 0 reads (prefix_key, uid = index) straight from K1's
+// output and drops reads shorter than k.
+constexpr int kSortChunk = 512;          // elements per warp
+constexpr int kSortWarps = 8;            // warps per CTA
+constexpr int kSortThreads = kSortWarps * 32;
+
+template <bool FIRST>
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint64_t* __restrict__ keys,
+                                                                  const int32_t* __restrict__ len, int k,
+                                                                  const int64_t* __restrict__ n_ptr, int64_t n_static,
+                                                                  int shift, int64_t W, int32_t* __restrict__ hist) {
+    __shared__ int32_t cnt[kSortWarps][256];
+    int wib = threadIdx.x >> 5;
+    int64_t warp = (int64_t)blockIdx.x * kSortWarps + wib;
+    for (int i = lane_id(); i < 256; i += 32) cnt[wib][i] = 0;
+    __syncwarp();
+    int64_t n = FIRST ? n_static : *n_ptr;
+    int64_t base = warp * kSortChunk;
+    if (warp < W) {
+        for (int it = 0; it < kSortChunk / 32; ++it) {
+            int64_t idx = base + it * 32 + lane_id();
+            if (idx < n) {
+                uint64_t key = keys[idx];
+                if (!FIRST || len[idx] >= k) atomicAdd(&cnt[wib][(int)((key >> shift) & 255u)], 1);
+            }
+        }
+        __syncwarp();
+        for (int d = lane_id(); d < 256; d += 32) hist[(int64_t)d * W + warp] = cnt[wib][d];
+    }
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint64_t* __restrict__ keys_in,
+                                                                     const uint32_t* __restrict__ uid_in,
+                                                                     const int32_t* __restrict__ len, int k,
+                                                                     const int64_t* __restrict__ n_ptr, int64_t n_static,
+                                                                     int shift, int64_t W,
+                                                                     const int32_t* __restrict__ hist_scanned,
+                                                                     uint64_t* __restrict__ keys_out,
+                                                                     uint32_t* __restrict__ uid_out,
+                                                                     int64_t* __restrict__ n_out) {
+    __shared__ int32_t off[kSortWarps][256];
+    int wib = threadIdx.x >> 5;
+    int64_t warp = (int64_t)blockIdx.x * kSortWarps + wib;
+    if (warp >= W) return;
+    for (int d = lane_id(); d < 256; d += 32) off[wib][d] = hist_scanned[(int64_t)d * W + warp];
+    __syncwarp();
+    int64_t n = FIRST ? n_static : *n_ptr;
+    int64_t base = warp * kSortChunk;
+    for (int it = 0; it < kSortChunk / 32; ++it) {
+        int64_t idx = base + it * 32 + lane_id();
+        bool live = idx < n;
+        uint64_t key = live ? keys_in[idx] : 0;
+        if (FIRST && live && len[idx] < k) live = false;
+        uint32_t uid = FIRST ? (uint32_t)idx : (live ? uid_in[idx] : 0u);
+        unsigned d = live ? (unsigned)((key >> shift) & 255u) : 256u + lane_id();  // dead lanes match nobody
+        unsigned peers = __match_any_sync(kFull, d);
+        int rank = __popc(peers & lanemask_lt());
+        int pos = 0;
+        if (live) pos = off[wib][d] + rank;
+        __syncwarp();
+        if (live && rank == 0) off[wib][d] += __popc(peers);
+        __syncwarp();
+        if (live) { keys_out[pos] = key; uid_out[pos] = uid; }
+    }
+    if (FIRST && n_out != nullptr && warp == W - 1 && lane_id() == 0) {
+        // after the last warp's chunk, digit 255's running offset is the number of survivors
+        *n_out = (int64_t)off[wib][255];
+    }
+}
+
+// ------------------------------------------------------------------ K3 join
+// One thread per source read a (overlapGraphs.py:43-52): equal range of suffix_key[a] in
+// the sorted prefix keys.  `self_rank` is a's own position inside its bucket (or -1): the
+// reference skips read_b == read_a (:52) and reads are unique, so that is the only skip.
+__global__ void __launch_bounds__(256) join_count_kernel(const uint64_t* __restrict__ suffix_key,
+                                                         const uint64_t* __restrict__ prefix_key,
+                                                         const int32_t* __restrict__ len, int k,
+                                                         int64_t a_begin, int64_t a_end,
+                                                         const uint64_t* __restrict__ sorted_key,
+                                                         const uint32_t* __restrict__ sorted_uid,
+                                                         const int64_t* __restrict__ n_indexed,
+                                                         int32_t* __restrict__ lo_out, int32_t* __restrict__ self_rank,
+                                                         int64_t* __restrict__ cnt_out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t a = a_begin + i;
+    if (a >= a_end) return;
+    uint64_t key = suffix_key[a];
+    int64_t cnt = 0;
+    int32_t lo32 = 0, sr = -1;
+    if (len[a] >= k) {
+        int64_t n = *n_indexed;
+        int64_t lo = lower_bound<uint64_t>(sorted_key, 0, n, key);
+        int64_t hi = upper_bound<uint64_t>(sorted_key, lo, n, key);
+        cnt = hi - lo;
+        lo32 = (int32_t)lo;
+        if (prefix_key[a] == key) {                 // a sits in its own bucket
+            int64_t p = lower_bound<uint32_t>(sorted_uid, lo, hi, (uint32_t)a);
+            sr = (int32_t)(p - lo);
+            cnt -= 1;
+        }
+    }
+    lo_out[i] = lo32;
+    self_rank[i] = sr;
+    cnt_out[i] = cnt;
+}
+
+// One thread per output pair; a CTA covers a contiguous tile of the output so both stores are
+// coalesced.  The owning source read is found by binary search over the scanned counts,
+// narrowed first to the tile's own [a_lo, a_hi] range (two searches per CTA).
+constexpr int kFillThreads = 256;
+constexpr int kFillItems = 8;
+constexpr int kFillTile = kFillThreads * kFillItems;
+
+__global__ void __launch_bounds__(kFillThreads) join_fill_kernel(const int64_t* __restrict__ pair_off,  // [nA+1]
+                                                                 int64_t nA, int64_t a_begin,
+                                                                 const int32_t* __restrict__ lo, const int32_t* __restrict__ self_rank,
+                                                                 const uint32_t* __restrict__ sorted_uid,
+                                                                 int64_t p_begin, int64_t p_count,
+                                                                 int32_t* __restrict__ pair_a, int32_t* __restrict__ pair_b) {
+    __shared__ int64_t range[2];
+    int64_t tile0 = (int64_t)blockIdx.x * kFillTile;
+    if (threadIdx.x == 0) {
+        int64_t first = p_begin + tile0;
+        int64_t last = p_begin + min(tile0 + kFillTile, p_count) - 1;
+        range[0] = upper_bound<int64_t>(pair_off, 0, nA + 1, first) - 1;
+        range[1] = upper_bound<int64_t>(pair_off, 0, nA + 1, last) - 1;
+    }
+    __syncthreads();
+    int64_t alo = range[0], ahi = range[1];
+#pragma unroll
+    for (int it = 0; it < kFillItems; ++it) {
+        int64_t q = tile0 + it * kFillThreads + threadIdx.x;
+        if (q >= p_count) break;
+        int64_t p = p_begin + q;
+        int64_t i = upper_bound<int64_t>(pair_off, alo, ahi + 1, p) - 1;
+        int32_t r = (int32_t)(p - pair_off[i]);
+        int32_t sr = self_rank[i];
+        if (sr >= 0 && r >= sr) r += 1;
+        pair_a[q] = (int32_t)(a_begin + i);
+        pair_b[q] = (int32_t)sorted_uid[lo[i] + r];
+    }
+}
+
+// k == 0: every ordered pair a != b (overlapGraphs.py:49), a in [a_begin, a_end).
+__global__ void __launch_bounds__(256) all_pairs_fill_kernel(int64_t U, int64_t a_begin, int64_t p_begin, int64_t p_count,
+                                                             int32_t* __restrict__ pair_a, int32_t* __restrict__ pair_b) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= p_count) return;
+    int64_t p = p_begin + q;
+    int64_t per = U - 1;
+    int64_t ai = p / per;
+    int64_t r = p - ai * per;
+    int64_t a = a_begin + ai;
+    pair_a[q] = (int32_t)a;
+    pair_b[q] = (int32_t)(r >= a ? r + 1 : r);
+}
+
+// ------------------------------------------------------------------ K6 expand edges
+// Edge row = (node_a, node_b, weight, end_position), node id = node_off[uid] + copy, emitted
+// in the reference's insertion order: pair order, then copy_a, then copy_b (overlapGraphs.py:55-60).
+__global__ void __launch_bounds__(256) expand_count_kernel(const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b,
+                                                           const int32_t* __restrict__ copies, int64_t P,
+                                                           int64_t* __restrict__ cnt) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    cnt[p] = (int64_t)copies[pair_a[p]] * (int64_t)copies[pair_b[p]];
+}
+
+__global__ void __launch_bounds__(kFillThreads) expand_fill_kernel(const int64_t* __restrict__ edge_off,  // [P+1]
+                                                                   int64_t P,
+                                                                   const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b,
+                                                                   const int32_t* __restrict__ score, const int32_t* __restrict__ end,
+                                                                   const int32_t* __restrict__ copies, const int64_t* __restrict__ node_off,
+                                                                   int64_t e_begin, int64_t e_count, int4* __restrict__ edges) {
+    __shared__ int64_t range[2];
+    int64_t tile0 = (int64_t)blockIdx.x * kFillTile;
+    if (threadIdx.x == 0) {
+        int64_t first = e_begin + tile0;
+        int64_t last = e_begin + min(tile0 + kFillTile, e_count) - 1;
+        range[0] = upper_bound<int64_t>(edge_off, 0, P + 1, first) - 1;
+        range[1] = upper_bound<int64_t>(edge_off, 0, P + 1, last) - 1;
+    }
+    __syncthreads();
+    int64_t plo = range[0], phi = range[1];
+#pragma unroll
+    for (int it = 0; it < kFillItems; ++it) {
+        int64_t q = tile0 + it * kFillThreads + threadIdx.x;
+        if (q >= e_count) break;
+        int64_t e = e_begin + q;
+        int64_t p = upper_bound<int64_t>(edge_off, plo, phi + 1, e) - 1;
+        int64_t r = e - edge_off[p];
+        int32_t a = pair_a[p], b = pair_b[p];
+        int32_t cb = copies[b];
+        int32_t ia = (int32_t)(r / cb), ib = (int32_t)(r - (int64_t)ia * cb);
+        edges[q] = make_int4((int32_t)(node_off[a] + ia), (int32_t)(node_off[b] + ib), score[p], end[p]);
+    }
+}
+
+// every read appears once: edge row == pair row, no scan needed
+__global__ void __launch_bounds__(256) expand_unit_kernel(const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b,
+                                                          const int32_t* __restrict__ score, const int32_t* __restrict__ end,
+                                                          int64_t P, int4* __restrict__ edges) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    edges[p] = make_int4(pair_a[p], pair_b[p], score[p], end[p]);
+}
+
+}  // namespace ovl

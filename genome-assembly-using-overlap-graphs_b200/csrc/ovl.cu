@@ -1,0 +1,465 @@
+// libovl_b200.so -- C ABI over the sm_100a overlap-detection kernels (see include/ovl.h).
+#include "../../include/ovl.h"
+
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+
+#include "common.cuh"
+#include "scan.cuh"
+#include "kmer.cuh"
+#include "dp.cuh"
+#include "probe.cuh"
+#include "align.cuh"
+
+using namespace ovl;
+
+struct ovl_ctx {
+    int device;
+    int sm_count;
+    uint32_t* probe_sink;
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e__ = (expr);                                                           \
+        if (e__ != cudaSuccess)                                                             \
+            return fail(OVL_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                \
+    } while (0)
+
+#define LAUNCH_CHECK(name)                                                                   \
+    do {                                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                                \
+        if (e__ != cudaSuccess)                                                              \
+            return fail(OVL_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+    } while (0)
+
+static inline unsigned grid_for(int64_t n, int per_block) {
+    int64_t g = (n + per_block - 1) / per_block;
+    return (unsigned)(g > 0 ? g : 1);
+}
+
+extern "C" {
+
+const char* ovl_last_error(void) { return g_err; }
+int ovl_version(void) { return 100; }
+
+int ovl_ctx_create(int device, ovl_ctx** out) {
+    if (!out) return fail(OVL_E_ARG, "ovl_ctx_create: out is null");
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(OVL_E_ARG, "ovl_ctx_create: no CUDA device %d (have %d)", device, count);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(OVL_E_UNSUPPORTED, "ovl_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+    ovl_ctx* c = new ovl_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->probe_sink = nullptr;
+    *out = c;
+    return OVL_OK;
+}
+
+int ovl_ctx_destroy(ovl_ctx* ctx) {
+    if (!ctx) return OVL_OK;
+    if (ctx->probe_sink) cudaFree(ctx->probe_sink);
+    delete ctx;
+    return OVL_OK;
+}
+
+int ovl_ctx_sm_count(const ovl_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+int32_t ovl_row_words(int32_t max_len) {
+    int32_t w = (max_len + 15) / 16;
+    if (w < 1) w = 1;
+    return (w + 3) & ~3;
+}
+
+// ---------------------------------------------------------------- K0 / K1
+int ovl_pack_reads(ovl_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int64_t U, int32_t row_words,
+                   uint32_t* packed, int32_t* len, int32_t* bad_count, void* stream) {
+    if (!ctx || !ascii || !offsets || !packed || !len || !bad_count) return fail(OVL_E_ARG, "ovl_pack_reads: null argument");
+    if (U <= 0) return OVL_OK;
+    if (row_words < 4 || (row_words & 3)) return fail(OVL_E_ARG, "ovl_pack_reads: row_words must be a positive multiple of 4");
+    if (((uintptr_t)ascii & 15) || ((uintptr_t)packed & 15)) return fail(OVL_E_ARG, "ovl_pack_reads: ascii and packed must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    pack_reads_kernel<<<grid_for(U * row_words, 256), 256, 0, st>>>(ascii, offsets, U, row_words, packed, len, bad_count);
+    LAUNCH_CHECK("pack_reads_kernel");
+    return OVL_OK;
+}
+
+int ovl_kmer_keys(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, int64_t U, int32_t k,
+                  uint64_t* prefix_key, uint64_t* suffix_key, void* stream) {
+    if (!ctx || !packed || !len || !prefix_key || !suffix_key) return fail(OVL_E_ARG, "ovl_kmer_keys: null argument");
+    if (k < 1 || k > OVL_MAX_K) return fail(OVL_E_UNSUPPORTED, "ovl_kmer_keys: k=%d outside 1..%d", k, OVL_MAX_K);
+    if (U <= 0) return OVL_OK;
+    kmer_keys_kernel<<<grid_for(U, 256), 256, 0, (cudaStream_t)stream>>>(packed, row_words, len, U, k, prefix_key, suffix_key);
+    LAUNCH_CHECK("kmer_keys_kernel");
+    return OVL_OK;
+}
+
+// ---------------------------------------------------------------- K2
+// workspace: [hist int32 256*W][scan sums][tmp keys u64 U][tmp uids u32 U]
+static inline int64_t sort_warps(int64_t U) { return (U + kSortChunk - 1) / kSortChunk; }
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t ovl_index_workspace_bytes(int64_t U) {
+    if (U < 1) U = 1;
+    int64_t W = sort_warps(U);
+    size_t hist = align256((size_t)(256 * W + 1) * sizeof(int32_t));
+    size_t sums = align256(scan_workspace_bytes(256 * W, sizeof(int32_t)));
+    size_t keys = align256((size_t)U * sizeof(uint64_t));
+    size_t uids = align256((size_t)U * sizeof(uint32_t));
+    return hist + sums + keys + uids + 256;
+}
+
+int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len, int64_t U, int32_t k, uint64_t* sorted_key,
+                    uint32_t* sorted_uid, int64_t* n_indexed, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!ctx || !prefix_key || !len || !sorted_key || !sorted_uid || !n_indexed || !workspace) return fail(OVL_E_ARG, "ovl_index_build: null argument");
+    if (k < 1 || k > OVL_MAX_K) return fail(OVL_E_UNSUPPORTED, "ovl_index_build: k=%d outside 1..%d", k, OVL_MAX_K);
+    if (workspace_bytes < ovl_index_workspace_bytes(U)) return fail(OVL_E_ARG, "ovl_index_build: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (U <= 0) { CUDA_TRY(cudaMemsetAsync(n_indexed, 0, sizeof(int64_t), st)); return OVL_OK; }
+    int64_t W = sort_warps(U);
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    int32_t* hist = (int32_t*)ws;                 ws += align256((size_t)(256 * W + 1) * sizeof(int32_t));
+    void* sums = ws;                              ws += align256(scan_workspace_bytes(256 * W, sizeof(int32_t)));
+    uint64_t* tmp_key = (uint64_t*)ws;            ws += align256((size_t)U * sizeof(uint64_t));
+    uint32_t* tmp_uid = (uint32_t*)ws;
+
+    int passes = (2 * k + 7) / 8;
+    // ping-pong so that the last pass lands in (sorted_key, sorted_uid)
+    uint64_t* kbuf[2] = {sorted_key, tmp_key};
+    uint32_t* ubuf[2] = {sorted_uid, tmp_uid};
+    int dst = (passes & 1) ? 0 : 1;
+    unsigned grid = grid_for(W, kSortWarps);
+    const uint64_t* src_key = prefix_key;
+    const uint32_t* src_uid = nullptr;
+    for (int p = 0; p < passes; ++p) {
+        int shift = 8 * p;
+        if (p == 0) {
+            radix_hist_kernel<true><<<grid, kSortThreads, 0, st>>>(src_key, len, k, nullptr, U, shift, W, hist);
+        } else {
+            radix_hist_kernel<false><<<grid, kSortThreads, 0, st>>>(src_key, len, k, n_indexed, 0, shift, W, hist);
+        }
+        LAUNCH_CHECK("radix_hist_kernel");
+        CUDA_TRY((exclusive_scan<int32_t, int32_t>(hist, hist, 256 * W, sums, st)));
+        if (p == 0) {
+            radix_scatter_kernel<true><<<grid, kSortThreads, 0, st>>>(src_key, nullptr, len, k, nullptr, U, shift, W, hist,
+                                                                       kbuf[dst], ubuf[dst], n_indexed);
+        } else {
+            radix_scatter_kernel<false><<<grid, kSortThreads, 0, st>>>(src_key, src_uid, len, k, n_indexed, 0, shift, W, hist,
+                                                                        kbuf[dst], ubuf[dst], nullptr);
+        }
+        LAUNCH_CHECK("radix_scatter_kernel");
+        src_key = kbuf[dst];
+        src_uid = ubuf[dst];
+        dst ^= 1;
+    }
+    return OVL_OK;
+}
+
+// ---------------------------------------------------------------- K3
+// workspace: [cnt int64 n][scan sums]
+size_t ovl_join_workspace_bytes(int64_t n_sources) {
+    if (n_sources < 1) n_sources = 1;
+    return align256((size_t)n_sources * sizeof(int64_t)) + align256(scan_workspace_bytes(n_sources, sizeof(int64_t))) + 256;
+}
+
+int ovl_join_count(ovl_ctx* ctx, const uint64_t* suffix_key, const uint64_t* prefix_key, const int32_t* len, int32_t k,
+                   int64_t a_begin, int64_t a_end,
+                   const uint64_t* sorted_key, const uint32_t* sorted_uid, const int64_t* n_indexed, int32_t* bucket_lo,
+                   int32_t* self_rank, int64_t* pair_off, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!ctx || !suffix_key || !prefix_key || !len || !sorted_key || !sorted_uid || !n_indexed || !bucket_lo || !self_rank || !pair_off || !workspace)
+        return fail(OVL_E_ARG, "ovl_join_count: null argument");
+    int64_t nA = a_end - a_begin;
+    if (nA < 0) return fail(OVL_E_ARG, "ovl_join_count: a_end < a_begin");
+    if (workspace_bytes < ovl_join_workspace_bytes(nA)) return fail(OVL_E_ARG, "ovl_join_count: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    int64_t* cnt = (int64_t*)ws;
+    void* sums = ws + align256((size_t)std::max<int64_t>(nA, 1) * sizeof(int64_t));
+    if (nA > 0) {
+        join_count_kernel<<<grid_for(nA, 256), 256, 0, st>>>(suffix_key, prefix_key, len, k, a_begin, a_end, sorted_key, sorted_uid,
+                                                              n_indexed, bucket_lo, self_rank, cnt);
+        LAUNCH_CHECK("join_count_kernel");
+    }
+    CUDA_TRY((exclusive_scan<int64_t, int64_t>(cnt, pair_off, nA, sums, st)));
+    return OVL_OK;
+}
+
+int ovl_join_fill(ovl_ctx* ctx, const int64_t* pair_off, int64_t a_begin, int64_t a_end, const int32_t* bucket_lo,
+                  const int32_t* self_rank, const uint32_t* sorted_uid, int64_t p_begin, int64_t p_count, int32_t* pair_a,
+                  int32_t* pair_b, void* stream) {
+    if (!ctx || !pair_off || !bucket_lo || !self_rank || !sorted_uid || !pair_a || !pair_b) return fail(OVL_E_ARG, "ovl_join_fill: null argument");
+    if (p_count <= 0) return OVL_OK;
+    join_fill_kernel<<<grid_for(p_count, kFillTile), kFillThreads, 0, (cudaStream_t)stream>>>(
+        pair_off, a_end - a_begin, a_begin, bucket_lo, self_rank, sorted_uid, p_begin, p_count, pair_a, pair_b);
+    LAUNCH_CHECK("join_fill_kernel");
+    return OVL_OK;
+}
+
+int ovl_all_pairs_fill(ovl_ctx* ctx, int64_t U, int64_t a_begin, int64_t p_begin, int64_t p_count, int32_t* pair_a,
+                       int32_t* pair_b, void* stream) {
+    if (!ctx || !pair_a || !pair_b) return fail(OVL_E_ARG, "ovl_all_pairs_fill: null argument");
+    if (p_count <= 0) return OVL_OK;
+    if (U < 2) return fail(OVL_E_ARG, "ovl_all_pairs_fill: need at least two reads");
+    all_pairs_fill_kernel<<<grid_for(p_count, 256), 256, 0, (cudaStream_t)stream>>>(U, a_begin, p_begin, p_count, pair_a, pair_b);
+    LAUNCH_CHECK("all_pairs_fill_kernel");
+    return OVL_OK;
+}
+
+// ---------------------------------------------------------------- K4 / K5
+}  // extern "C"
+
+namespace {
+
+struct DpPlan {
+    int mode;       // 1 packed16, 2 int32
+    int G, T;
+    DpParams prm;
+};
+
+const int kPackedT[] = {25, 32, 38};
+const int kScalarT[] = {32};
+const int kLanes[] = {1, 2, 4, 8, 16, 32};
+
+// Range analysis for the re-based recurrence (see dp.cuh).  N = longest s, M = G*T columns.
+bool dp_params(int64_t match, int64_t mismatch, int64_t indel, int64_t N, int64_t M, bool packed, DpParams* out) {
+    const int64_t limit = packed ? 32767 : (1ll << 30);
+    const int64_t big = 1ll << 40;
+    if (std::llabs(match) > big || std::llabs(mismatch) > big) return false;
+    int64_t base = std::min(match, mismatch);
+    int64_t eqv = match - base, nev = mismatch - base;
+    if (packed && (eqv > 127 || nev > 127)) return false;
+    if (eqv > limit || nev > limit) return false;
+    int64_t g = std::max<int64_t>(indel, -big);
+    g = std::min<int64_t>(g, big);
+    int64_t gain = std::max<int64_t>(std::max(match, mismatch), 0);
+    int64_t mn = std::min(N, M);
+    int64_t Hhi = g <= 0 ? gain * mn : std::max(gain, g) * (N + M);
+    int64_t absbase = base < 0 ? -base : base;
+    int64_t beta = std::max<int64_t>(base, 0) * N;
+    int64_t Ghi = Hhi + absbase * N;           // all G in [0, Ghi]
+    if (Ghi > limit) return false;
+    int64_t gl = g, gu = g - base;
+    if (Ghi + std::max(gu, gl) < 0) {
+        // a gap can never reach any true cell value (all >= 0): any always-negative constant is exact
+        gl = gu = -(Ghi + 1);
+    }
+    if (std::min(gu, gl) < -limit - 1) return false;
+    if (Ghi + std::max<int64_t>(std::max(gu, gl), 0) > limit) return false;
+    out->eqv = (int32_t)eqv; out->nev = (int32_t)nev; out->base = (int32_t)base; out->beta = (int32_t)beta;
+    out->gu = (int32_t)gu; out->gl = (int32_t)gl; out->one = 1u;
+    return true;
+}
+
+bool dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_t indel, int mode, int forceG, int forceT, DpPlan* plan) {
+    int64_t N = std::max(max_len, 1);
+    for (int m = 1; m <= 2; ++m) {
+        if (mode != 0 && mode != m) continue;
+        const int* Ts = m == 1 ? kPackedT : kScalarT;
+        int nT = m == 1 ? 3 : 1;
+        int64_t best = -1;
+        for (int gi = 0; gi < 6; ++gi) {
+            for (int ti = 0; ti < nT; ++ti) {
+                int G = kLanes[gi], T = Ts[ti];
+                if (forceG && G != forceG) continue;
+                if (forceT && T != forceT) continue;
+                if ((int64_t)G * T < N) continue;
+                DpParams prm;
+                if (!dp_params(match, mismatch, indel, N, (int64_t)G * T, m == 1, &prm)) continue;
+                int64_t cost = (int64_t)G * T * (N + G - 1);
+                if (best < 0 || cost < best) { best = cost; plan->mode = m; plan->G = G; plan->T = T; plan->prm = prm; }
+            }
+        }
+        if (best >= 0) return true;
+    }
+    return false;
+}
+
+template <int G, int T, bool PK>
+int launch_dp(const uint32_t* packed, int32_t row_words, const int32_t* len, const int32_t* pair_a, const int32_t* pair_b,
+              int64_t P, const DpParams& prm, int32_t* score, int32_t* end, cudaStream_t st) {
+    constexpr int PAIRS = PK ? 2 : 1;
+    constexpr int GROUPS_PER_CTA = (kDpThreads / 32) * (32 / G);
+    int64_t groups = (P + PAIRS - 1) / PAIRS;
+    int64_t grid = (groups + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA;
+    if (grid > 0x7fffffffll) return fail(OVL_E_ARG, "ovl_overlap_dp: too many pairs for one launch (%lld)", (long long)P);
+    size_t smem = (size_t)GROUPS_PER_CTA * 2 * PAIRS * row_words * sizeof(uint32_t);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(overlap_dp_kernel<G, T, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(OVL_E_CUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));
+    }
+    overlap_dp_kernel<G, T, PK><<<(unsigned)grid, kDpThreads, smem, st>>>(packed, row_words, len, pair_a, pair_b, P, prm, score, end);
+    LAUNCH_CHECK("overlap_dp_kernel");
+    return OVL_OK;
+}
+
+#define DP_CASE(G_, T_, PK_) \
+    if (plan.G == G_ && plan.T == T_) return launch_dp<G_, T_, PK_>(packed, row_words, len, pair_a, pair_b, P, plan.prm, score, end, st);
+#define DP_CASES_T(T_, PK_) \
+    DP_CASE(1, T_, PK_) DP_CASE(2, T_, PK_) DP_CASE(4, T_, PK_) DP_CASE(8, T_, PK_) DP_CASE(16, T_, PK_) DP_CASE(32, T_, PK_)
+
+}  // namespace
+
+extern "C" {
+
+int ovl_overlap_dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_t indel, int32_t mode, int32_t out[3]) {
+    if (max_len > OVL_MAX_READ_LEN)
+        return fail(OVL_E_UNSUPPORTED, "overlap DP: read length %d exceeds the supported maximum %d", max_len, OVL_MAX_READ_LEN);
+    DpPlan plan;
+    if (!dp_plan(max_len, match, mismatch, indel, mode, 0, 0, &plan))
+        return fail(OVL_E_UNSUPPORTED, "overlap DP: scores for (match=%lld, mismatch=%lld, indel=%lld, len=%d) do not fit the %s kernels",
+                    (long long)match, (long long)mismatch, (long long)indel, max_len, mode == 1 ? "16-bit" : "32-bit");
+    out[0] = plan.mode; out[1] = plan.G; out[2] = plan.T;
+    return OVL_OK;
+}
+
+int ovl_overlap_dp(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, const int32_t* pair_a,
+                   const int32_t* pair_b, int64_t P, int32_t max_len, int64_t match, int64_t mismatch, int64_t indel,
+                   int32_t* score, int32_t* end, int32_t mode, int32_t group_lanes, int32_t cols_per_lane, void* stream) {
+    if (!ctx || !packed || !len || !pair_a || !pair_b || !score || !end) return fail(OVL_E_ARG, "ovl_overlap_dp: null argument");
+    if (P <= 0) return OVL_OK;
+    if (row_words < 4 || (row_words & 3) || max_len > 16 * row_words) return fail(OVL_E_ARG, "ovl_overlap_dp: row_words=%d does not hold max_len=%d", row_words, max_len);
+    if (max_len > OVL_MAX_READ_LEN)
+        return fail(OVL_E_UNSUPPORTED, "ovl_overlap_dp: read length %d exceeds the supported maximum %d", max_len, OVL_MAX_READ_LEN);
+    DpPlan plan;
+    if (!dp_plan(max_len, match, mismatch, indel, mode, group_lanes, cols_per_lane, &plan))
+        return fail(OVL_E_UNSUPPORTED, "ovl_overlap_dp: no kernel for (match=%lld, mismatch=%lld, indel=%lld, len=%d, mode=%d, lanes=%d, cols=%d)",
+                    (long long)match, (long long)mismatch, (long long)indel, max_len, mode, group_lanes, cols_per_lane);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan.mode == 1) {
+        DP_CASES_T(25, true) DP_CASES_T(32, true) DP_CASES_T(38, true)
+    } else {
+        DP_CASES_T(32, false)
+    }
+    return fail(OVL_E_UNSUPPORTED, "ovl_overlap_dp: instantiation G=%d T=%d mode=%d missing", plan.G, plan.T, plan.mode);
+}
+
+// ---------------------------------------------------------------- K6
+size_t ovl_expand_workspace_bytes(int64_t P) {
+    if (P < 1) P = 1;
+    return align256((size_t)P * sizeof(int64_t)) + align256(scan_workspace_bytes(P, sizeof(int64_t))) + 256;
+}
+
+int ovl_expand_count(ovl_ctx* ctx, const int32_t* pair_a, const int32_t* pair_b, const int32_t* copies, int64_t P,
+                     int64_t* edge_off, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!ctx || !pair_a || !pair_b || !copies || !edge_off || !workspace) return fail(OVL_E_ARG, "ovl_expand_count: null argument");
+    if (workspace_bytes < ovl_expand_workspace_bytes(P)) return fail(OVL_E_ARG, "ovl_expand_count: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    int64_t* cnt = (int64_t*)ws;
+    void* sums = ws + align256((size_t)std::max<int64_t>(P, 1) * sizeof(int64_t));
+    if (P > 0) {
+        expand_count_kernel<<<grid_for(P, 256), 256, 0, st>>>(pair_a, pair_b, copies, P, cnt);
+        LAUNCH_CHECK("expand_count_kernel");
+    }
+    CUDA_TRY((exclusive_scan<int64_t, int64_t>(cnt, edge_off, P, sums, st)));
+    return OVL_OK;
+}
+
+int ovl_expand_fill(ovl_ctx* ctx, const int64_t* edge_off, int64_t P, const int32_t* pair_a, const int32_t* pair_b,
+                    const int32_t* score, const int32_t* end, const int32_t* copies, const int64_t* node_off,
+                    int64_t e_begin, int64_t e_count, int32_t* edges, void* stream) {
+    if (!ctx || !edge_off || !pair_a || !pair_b || !score || !end || !copies || !node_off || !edges) return fail(OVL_E_ARG, "ovl_expand_fill: null argument");
+    if (e_count <= 0) return OVL_OK;
+    if ((uintptr_t)edges & 15) return fail(OVL_E_ARG, "ovl_expand_fill: edges must be 16-byte aligned");
+    expand_fill_kernel<<<grid_for(e_count, kFillTile), kFillThreads, 0, (cudaStream_t)stream>>>(
+        edge_off, P, pair_a, pair_b, score, end, copies, node_off, e_begin, e_count, (int4*)edges);
+    LAUNCH_CHECK("expand_fill_kernel");
+    return OVL_OK;
+}
+
+int ovl_expand_unit(ovl_ctx* ctx, const int32_t* pair_a, const int32_t* pair_b, const int32_t* score, const int32_t* end,
+                    int64_t P, int32_t* edges, void* stream) {
+    if (!ctx || !pair_a || !pair_b || !score || !end || !edges) return fail(OVL_E_ARG, "ovl_expand_unit: null argument");
+    if (P <= 0) return OVL_OK;
+    if ((uintptr_t)edges & 15) return fail(OVL_E_ARG, "ovl_expand_unit: edges must be 16-byte aligned");
+    expand_unit_kernel<<<grid_for(P, 256), 256, 0, (cudaStream_t)stream>>>(pair_a, pair_b, score, end, P, (int4*)edges);
+    LAUNCH_CHECK("expand_unit_kernel");
+    return OVL_OK;
+}
+
+// ---------------------------------------------------------------- K7
+size_t ovl_align_pair_workspace_bytes(int32_t n, int32_t m) {
+    if (n < 0) n = 0;
+    if (m < 0) m = 0;
+    size_t ints = (size_t)3 * (n + 1) + (size_t)(m + 1);
+    return align256(ints * sizeof(int32_t)) + align256((size_t)(n + 1) * (m + 1)) + 256;
+}
+
+int ovl_align_pair(ovl_ctx* ctx, const int32_t* s, int32_t n, const int32_t* t, int32_t m, int64_t match, int64_t mismatch,
+                   int64_t indel, void* workspace, size_t workspace_bytes, int32_t* result, uint8_t* ops, void* stream) {
+    if (!ctx || !workspace || !result || !ops || (n > 0 && !s) || (m > 0 && !t)) return fail(OVL_E_ARG, "ovl_align_pair: null argument");
+    if (n < 0 || m < 0) return fail(OVL_E_ARG, "ovl_align_pair: negative length");
+    if (workspace_bytes < ovl_align_pair_workspace_bytes(n, m)) return fail(OVL_E_ARG, "ovl_align_pair: workspace too small");
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    int32_t* diag = (int32_t*)ws;
+    int32_t* last_row = diag + (size_t)3 * (n + 1);
+    int8_t* tb = (int8_t*)(ws + align256(((size_t)3 * (n + 1) + (size_t)(m + 1)) * sizeof(int32_t)));
+    align_pair_kernel<<<1, kAlignThreads, 0, (cudaStream_t)stream>>>(s, n, t, m, match, mismatch, indel, diag, last_row, tb, result, ops);
+    LAUNCH_CHECK("align_pair_kernel");
+    return OVL_OK;
+}
+
+// ---------------------------------------------------------------- probe
+}  // extern "C"
+
+template <int KIND>
+static int run_probe(ovl_ctx* ctx, int iters, double* gops, double* ms_out) {
+    if (!ctx->probe_sink) CUDA_TRY(cudaMalloc(&ctx->probe_sink, 256));
+    int blocks = ctx->sm_count * 8;     // 2048 threads per SM: every scheduler has 16 warps
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    int_probe_kernel<KIND><<<blocks, kProbeThreads>>>(ctx->probe_sink, 4, 0x00070003u, 0xfff5fff5u, 1u);   // warm-up
+    CUDA_TRY(cudaEventRecord(e0));
+    int_probe_kernel<KIND><<<blocks, kProbeThreads>>>(ctx->probe_sink, iters, 0x00070003u, 0xfff5fff5u, 1u);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    LAUNCH_CHECK("int_probe_kernel");
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    double ops = (double)blocks * kProbeThreads * (double)iters * kProbeUnroll * kProbeChains * probe_ops_per_iter(KIND);
+    *gops = ops / (ms * 1e-3) / 1e9;
+    if (ms_out) *ms_out = ms;
+    return OVL_OK;
+}
+
+extern "C" {
+
+int ovl_int_peak_probe(ovl_ctx* ctx, int32_t kind, int32_t iters, double* h_gops, double* h_ms) {
+    if (!ctx || !h_gops) return fail(OVL_E_ARG, "ovl_int_peak_probe: null argument");
+    if (iters < 1) iters = 1;
+    switch (kind) {
+        case 0: return run_probe<0>(ctx, iters, h_gops, h_ms);
+        case 1: return run_probe<1>(ctx, iters, h_gops, h_ms);
+        case 2: return run_probe<2>(ctx, iters, h_gops, h_ms);
+        case 3: return run_probe<3>(ctx, iters, h_gops, h_ms);
+        case 4: return run_probe<4>(ctx, iters, h_gops, h_ms);
+        case 5: return run_probe<5>(ctx, iters, h_gops, h_ms);
+        case 6: return run_probe<6>(ctx, iters, h_gops, h_ms);
+        default: return fail(OVL_E_ARG, "ovl_int_peak_probe: unknown kind %d", kind);
+    }
+}
+
+}  // extern "C"

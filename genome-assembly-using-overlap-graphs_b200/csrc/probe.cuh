@@ -1,0 +1,55 @@
+// Integer-pipe peak probes: the measured denominator of the DP roofline.
+// Each thread runs kChains independent dependency chains so the issue rate, not the latency,
+// is what is measured; one "lane-op" = one thread executing one instruction.
+#pragma once
+#include "common.cuh"
+
+namespace ovl {
+
+constexpr int kProbeChains = 8;
+constexpr int kProbeUnroll = 16;
+constexpr int kProbeThreads = 256;
+
+template <int KIND>
+__global__ void __launch_bounds__(kProbeThreads) int_probe_kernel(uint32_t* out, int iters, uint32_t a0, uint32_t b0, uint32_t one) {
+    uint32_t v[kProbeChains], w[kProbeChains];
+#pragma unroll
+    for (int c = 0; c < kProbeChains; ++c) { v[c] = a0 + threadIdx.x + c; w[c] = b0 ^ (c * 0x01010101u); }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < kProbeUnroll; ++u) {
+#pragma unroll
+            for (int c = 0; c < kProbeChains; ++c) {
+                if (KIND == 0) {            // IADD3
+                    asm volatile("add.u32 %0, %0, %1;" : "+r"(v[c]) : "r"(w[c]));
+                } else if (KIND == 1) {     // IMAD
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v[c]) : "r"(one), "r"(w[c]));
+                } else if (KIND == 2) {     // VIMNMX.S32
+                    asm volatile("max.s32 %0, %0, %1;" : "+r"(v[c]) : "r"(w[c]));
+                    w[c] += 0;              // keep operands live
+                } else if (KIND == 3) {     // VIADDMNMX.S16x2
+                    v[c] = __viaddmax_s16x2(v[c], b0, w[c]);
+                } else if (KIND == 4) {     // DP inner-loop mix: PRMT + IMAD + 2x VIADDMNMX.S16x2
+                    uint32_t sc;
+                    asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(sc) : "r"(a0), "r"(b0), "r"(w[c]));
+                    uint32_t d;
+                    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(sc), "r"(one), "r"(w[c]));
+                    uint32_t t1 = __viaddmax_s16x2(w[c], b0, d);
+                    v[c] = __viaddmax_s16x2(v[c], a0, t1);
+                } else if (KIND == 5) {     // PRMT
+                    asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(v[c]) : "r"(w[c]), "r"(b0));
+                } else {                    // LOP3
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[c]) : "r"(w[c]), "r"(b0));
+                }
+            }
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int c = 0; c < kProbeChains; ++c) acc ^= v[c] + w[c];
+    if (acc == 0x12345678u) out[0] = acc;    // practically never; keeps the chains alive
+}
+
+inline int probe_ops_per_iter(int kind) { return kind == 4 ? 4 : 1; }
+
+}  // namespace ovl

@@ -1,0 +1,363 @@
+"""Host orchestration of the overlap-detection pipeline on one B200.
+
+Stages (each a call into libovl_b200.so, kernels in csrc/):
+  K0 pack_reads -> K1 kmer_keys -> K2 index_build -> K3 join_count/fill -> K4/K5 overlap_dp
+  -> K6 expand_edges
+which together replace overlapGraphs.py:30-60 (index, candidate lookup, DP call, edge
+expansion).  PyTorch is used for device buffers, streams and host<->device copies only.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+INDEL_DEFAULT = -2 ** 31          # aligners.py:7
+
+
+@dataclass
+class ReadSet:
+    """Unique reads resident in HBM: 2-bit packed rows + lengths."""
+    packed: torch.Tensor          # uint8 view of uint32[U * row_words]
+    length: torch.Tensor          # int32[U]
+    bad: torch.Tensor             # int32[1]: words with a non-ACGT byte
+    row_words: int
+    n_reads: int
+    max_len: int
+
+
+@dataclass
+class KmerIndex:
+    k: int
+    prefix_key: torch.Tensor      # int64 view of uint64[U]
+    suffix_key: torch.Tensor
+    sorted_key: torch.Tensor
+    sorted_uid: torch.Tensor      # int32 view of uint32[U]
+    n_indexed: torch.Tensor       # int64[1]
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+class OverlapEngine:
+    def __init__(self, device: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device visible: the overlap path runs on sm_100a only (no CPU fallback)")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        ctx = ctypes.c_void_p()
+        nat.check(nat.lib.ovl_ctx_create(self.device_index, ctypes.byref(ctx)))
+        self._ctx = ctx
+        self.sm_count = int(nat.lib.ovl_ctx_sm_count(ctx))
+        self.launches = 0          # kernels launched through this engine (bench bookkeeping)
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            nat.lib.ovl_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> ctypes.c_void_p:
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _empty(self, n: int, dtype) -> torch.Tensor:
+        return torch.empty(max(int(n), 1), dtype=dtype, device=self.device)
+
+    def _to_device(self, x, dtype) -> torch.Tensor:
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        if x.dtype != dtype:
+            x = x.to(dtype)
+        return x.to(self.device, non_blocking=True)
+
+    # ------------------------------------------------------------------ K0
+    def upload_reads(self, bases, offsets, max_len: Optional[int] = None) -> ReadSet:
+        """bases: uint8[sum len] ASCII, offsets: int64[U+1] (NumPy or CPU/GPU torch tensors)."""
+        off_host = None
+        if isinstance(offsets, np.ndarray):
+            off_host = offsets
+        elif not offsets.is_cuda:
+            off_host = offsets.numpy()
+        U = int(offsets.shape[0]) - 1
+        if U < 0:
+            raise ValueError("offsets must have at least one entry")
+        if max_len is None:
+            if off_host is None:
+                off_host = offsets.cpu().numpy()
+            max_len = int(np.max(off_host[1:] - off_host[:-1])) if U > 0 else 0
+        total = int(bases.shape[0]) if U > 0 else 0
+        ascii_dev = torch.empty(total + 64, dtype=torch.uint8, device=self.device)   # 32 B slack for K0
+        if total:
+            src = torch.from_numpy(np.ascontiguousarray(bases)) if isinstance(bases, np.ndarray) else bases
+            ascii_dev[:total].copy_(src[:total], non_blocking=True)
+        off_dev = self._to_device(offsets, torch.int64)
+        return self.pack_reads(ascii_dev, off_dev, U, max_len)
+
+    def pack_reads(self, ascii_dev: torch.Tensor, off_dev: torch.Tensor, U: int, max_len: int) -> ReadSet:
+        if max_len > nat.OVL_MAX_READ_LEN:
+            raise nat.OvlUnsupported(f"read length {max_len} exceeds the supported maximum {nat.OVL_MAX_READ_LEN}")
+        row_words = int(nat.lib.ovl_row_words(max_len))
+        packed = self._empty(U * row_words * 4 + 16, torch.uint8)
+        length = self._empty(U, torch.int32)
+        bad = torch.zeros(1, dtype=torch.int32, device=self.device)
+        nat.check(nat.lib.ovl_pack_reads(self._ctx, _ptr(ascii_dev), _ptr(off_dev), U, row_words,
+                                         _ptr(packed), _ptr(length), _ptr(bad), self._stream()))
+        self.launches += 1 if U > 0 else 0
+        return ReadSet(packed, length, bad, row_words, U, max_len)
+
+    def check_alphabet(self, rs: ReadSet) -> None:
+        """The reference compares arbitrary characters; the 2-bit kernels cover A/C/G/T only
+        and refuse anything else instead of mis-scoring it (host sync)."""
+        if int(rs.bad.item()) != 0:
+            raise nat.OvlUnsupported("reads contain characters other than A, C, G, T; "
+                                     "the 2-bit CUDA path does not support them")
+
+    # ------------------------------------------------------------------ K1 + K2
+    def kmer_index(self, rs: ReadSet, k: int) -> KmerIndex:
+        if k < 1 or k > nat.OVL_MAX_K:
+            raise nat.OvlUnsupported(f"k={k}: the k-mer index covers 1 <= k <= {nat.OVL_MAX_K}")
+        U = rs.n_reads
+        pk = self._empty(U, torch.int64)
+        sk = self._empty(U, torch.int64)
+        nat.check(nat.lib.ovl_kmer_keys(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length), U, k,
+                                        _ptr(pk), _ptr(sk), self._stream()))
+        sorted_key = self._empty(U, torch.int64)
+        sorted_uid = self._empty(U, torch.int32)
+        n_indexed = torch.zeros(1, dtype=torch.int64, device=self.device)
+        ws_bytes = int(nat.lib.ovl_index_workspace_bytes(U))
+        ws = self._empty(ws_bytes, torch.uint8)
+        nat.check(nat.lib.ovl_index_build(self._ctx, _ptr(pk), _ptr(rs.length), U, k, _ptr(sorted_key), _ptr(sorted_uid),
+                                          _ptr(n_indexed), _ptr(ws), ws_bytes, self._stream()))
+        if U > 0:
+            self.launches += 1 + 5 * ((2 * k + 7) // 8)
+        return KmerIndex(k, pk, sk, sorted_key, sorted_uid, n_indexed)
+
+    # ------------------------------------------------------------------ K3
+    def candidate_pairs(self, rs: ReadSet, index: Optional[KmerIndex], k: int,
+                        shard: Tuple[int, int] = (0, 1)) -> Tuple[torch.Tensor, torch.Tensor, int]:
+        """Ordered candidate list (overlapGraphs.py:43-52).  ``shard=(rank, world)`` returns the
+        rank-th contiguous slice of the global (a, b)-ordered list, balanced by pair count.
+        Returns (pair_a, pair_b, first_pair_index)."""
+        U = rs.n_reads
+        rank, world = shard
+        st = self._stream()
+        if k == 0:
+            total = U * (U - 1) if U > 1 else 0
+            p_begin, p_end = total * rank // world, total * (rank + 1) // world
+            P = p_end - p_begin
+            pair_a = self._empty(P, torch.int32)
+            pair_b = self._empty(P, torch.int32)
+            if P:
+                nat.check(nat.lib.ovl_all_pairs_fill(self._ctx, U, 0, p_begin, P, _ptr(pair_a), _ptr(pair_b), st))
+                self.launches += 1
+            return pair_a[:P], pair_b[:P], p_begin
+        assert index is not None and index.k == k
+        lo = self._empty(U, torch.int32)
+        self_rank = self._empty(U, torch.int32)
+        pair_off = self._empty(U + 1, torch.int64)
+        ws_bytes = int(nat.lib.ovl_join_workspace_bytes(U))
+        ws = self._empty(ws_bytes, torch.uint8)
+        nat.check(nat.lib.ovl_join_count(self._ctx, _ptr(index.suffix_key), _ptr(index.prefix_key),
+                                         _ptr(rs.length), k, 0, U,
+                                         _ptr(index.sorted_key), _ptr(index.sorted_uid), _ptr(index.n_indexed),
+                                         _ptr(lo), _ptr(self_rank), _ptr(pair_off), _ptr(ws), ws_bytes, st))
+        self.launches += 4 if U > 0 else 0
+        total = int(pair_off[U].item())                      # host sync: the output size
+        p_begin, p_end = total * rank // world, total * (rank + 1) // world
+        P = p_end - p_begin
+        pair_a = self._empty(P, torch.int32)
+        pair_b = self._empty(P, torch.int32)
+        if P:
+            nat.check(nat.lib.ovl_join_fill(self._ctx, _ptr(pair_off), 0, U, _ptr(lo), _ptr(self_rank),
+                                            _ptr(index.sorted_uid), p_begin, P, _ptr(pair_a), _ptr(pair_b), st))
+            self.launches += 1
+        return pair_a[:P], pair_b[:P], p_begin
+
+    # ------------------------------------------------------------------ K4 / K5
+    def overlap_scores(self, rs: ReadSet, pair_a: torch.Tensor, pair_b: torch.Tensor,
+                       match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT,
+                       mode: int = 0, lanes: int = 0, cols: int = 0,
+                       out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+                       ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(score[p], end[p]) of overlap_alignment(read[a[p]], read[b[p]]) -- overlapGraphs.py:53."""
+        P = int(pair_a.shape[0])
+        if out is None:
+            score = self._empty(P, torch.int32)
+            end = self._empty(P, torch.int32)
+        else:
+            score, end = out
+        if P:
+            nat.check(nat.lib.ovl_overlap_dp(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length),
+                                             _ptr(pair_a), _ptr(pair_b), P, rs.max_len,
+                                             int(match_score), int(mismatch), int(indel),
+                                             _ptr(score), _ptr(end), mode, lanes, cols, self._stream()))
+            self.launches += 1
+        return score[:P], end[:P]
+
+    @staticmethod
+    def dp_plan(max_len: int, match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT, mode: int = 0):
+        out = (ctypes.c_int32 * 3)()
+        nat.check(nat.lib.ovl_overlap_dp_plan(max_len, int(match_score), int(mismatch), int(indel), mode,
+                                              ctypes.byref(out)))
+        return {"mode": "packed16" if out[0] == 1 else "int32", "lanes": int(out[1]), "cols": int(out[2])}
+
+    # ------------------------------------------------------------------ K7
+    def align_pair(self, s_codes: np.ndarray, t_codes: np.ndarray, match_score: int = 10, mismatch: int = -1,
+                   indel: int = INDEL_DEFAULT) -> Tuple[int, int, np.ndarray]:
+        """One pair with traceback (aligners.py:27-76).  s_codes / t_codes are int32 code
+        points.  Returns (best_score, end_position, ops) with ops the traceback from the end
+        backwards (0 diagonal, 1 up, 2 left)."""
+        n, m = int(s_codes.shape[0]), int(t_codes.shape[0])
+        both = np.concatenate([s_codes.astype(np.int32), t_codes.astype(np.int32), np.zeros(1, np.int32)])
+        dev = self._to_device(both, torch.int32)
+        ws_bytes = int(nat.lib.ovl_align_pair_workspace_bytes(n, m))
+        ws = self._empty(ws_bytes, torch.uint8)
+        result = torch.zeros(4, dtype=torch.int32, device=self.device)
+        ops = self._empty(n + m + 1, torch.uint8)
+        s_ptr = ctypes.c_void_p(dev.data_ptr())
+        t_ptr = ctypes.c_void_p(dev.data_ptr() + 4 * n)
+        nat.check(nat.lib.ovl_align_pair(self._ctx, s_ptr, n, t_ptr, m, int(match_score), int(mismatch), int(indel),
+                                         _ptr(ws), ws_bytes, _ptr(result), _ptr(ops), self._stream()))
+        self.launches += 1
+        res = result.cpu().numpy()
+        n_ops = int(res[2])
+        return int(res[0]), int(res[1]), ops[:n_ops].cpu().numpy()
+
+    # ------------------------------------------------------------------ K6
+    def expand_edges(self, pair_a, pair_b, score, end, copies: Optional[torch.Tensor] = None,
+                     node_off: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Edge rows int32[E, 4] = (node_a, node_b, weight, end_position), overlapGraphs.py:55-60.
+        copies=None means every read occurs once (node id == uid)."""
+        P = int(pair_a.shape[0])
+        st = self._stream()
+        if copies is None:
+            edges = self._empty(P * 4, torch.int32)
+            if P:
+                nat.check(nat.lib.ovl_expand_unit(self._ctx, _ptr(pair_a), _ptr(pair_b), _ptr(score), _ptr(end),
+                                                  P, _ptr(edges), st))
+                self.launches += 1
+            return edges[:P * 4].view(P, 4)
+        edge_off = self._empty(P + 1, torch.int64)
+        ws_bytes = int(nat.lib.ovl_expand_workspace_bytes(P))
+        ws = self._empty(ws_bytes, torch.uint8)
+        nat.check(nat.lib.ovl_expand_count(self._ctx, _ptr(pair_a), _ptr(pair_b), _ptr(copies), P,
+                                           _ptr(edge_off), _ptr(ws), ws_bytes, st))
+        self.launches += 4 if P > 0 else 0
+        E = int(edge_off[P].item())                           # host sync: the output size
+        edges = self._empty(E * 4, torch.int32)
+        if E:
+            nat.check(nat.lib.ovl_expand_fill(self._ctx, _ptr(edge_off), P, _ptr(pair_a), _ptr(pair_b),
+                                              _ptr(score), _ptr(end), _ptr(copies), _ptr(node_off), 0, E,
+                                              _ptr(edges), st))
+            self.launches += 1
+        return edges[:E * 4].view(E, 4)
+
+    # ------------------------------------------------------------------ whole path
+    def overlap_edges_device(self, rs: ReadSet, k: int, copies: Optional[torch.Tensor] = None,
+                             node_off: Optional[torch.Tensor] = None, shard: Tuple[int, int] = (0, 1),
+                             match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT,
+                             stats: Optional[dict] = None) -> torch.Tensor:
+        """Reads already packed in HBM -> device edge rows (this rank's shard)."""
+        index = self.kmer_index(rs, k) if k > 0 else None
+        pair_a, pair_b, _ = self.candidate_pairs(rs, index, k, shard)
+        score, end = self.overlap_scores(rs, pair_a, pair_b, match_score, mismatch, indel)
+        edges = self.expand_edges(pair_a, pair_b, score, end, copies, node_off)
+        if stats is not None:
+            stats["pairs"] = int(pair_a.shape[0])
+            stats["edges"] = int(edges.shape[0])
+            stats["pair_a"], stats["pair_b"] = pair_a, pair_b
+        return edges
+
+    def overlap_edges(self, bases, offsets, counts=None, k: int = 5, shard: Tuple[int, int] = (0, 1),
+                      match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT,
+                      stats: Optional[dict] = None) -> np.ndarray:
+        """HOST buffers in, HOST edge rows out: unique reads (ASCII bytes + offsets) and their
+        multiplicities -> int32[E, 4] (node_a, node_b, weight, end_position) in the reference's
+        insertion order.  This is the call the drop-in graph builder makes."""
+        if k < 0:
+            raise AssertionError("k-mer length must be non-negative")      # overlapGraphs.py:17
+        rs = self.upload_reads(bases, offsets)
+        copies = node_off = None
+        if counts is not None:
+            counts_np = counts if isinstance(counts, np.ndarray) else counts.numpy()
+            if counts_np.size and int(counts_np.max()) > 1:
+                no = np.zeros(counts_np.shape[0] + 1, dtype=np.int64)
+                np.cumsum(counts_np, out=no[1:])
+                copies = self._to_device(counts_np, torch.int32)
+                node_off = self._to_device(no, torch.int64)
+        edges = self.overlap_edges_device(rs, k, copies, node_off, shard, match_score, mismatch, indel, stats)
+        self.check_alphabet(rs)
+        return edges.cpu().numpy()
+
+
+_ENGINES = {}
+
+
+def get_engine(device: Optional[int] = None) -> OverlapEngine:
+    """Process-wide engine per device (created on first use)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device visible: the overlap path runs on sm_100a only (no CPU fallback)")
+    if device is None:
+        device = torch.cuda.current_device()
+    eng = _ENGINES.get(device)
+    if eng is None:
+        eng = _ENGINES[device] = OverlapEngine(device)
+    return eng
+
+
+_REF_MODULES = {}
+
+
+def reference_module(name: str):
+    """The reference's own module `name` (for the symbols outside the accelerated path), or
+    None when no checkout is available.  The reference's functions that call the builder look
+    it up in their module globals (overlapGraphs.py:167), so the forwarded module gets the
+    GPU builder / aligner patched in."""
+    import importlib.util
+    import os
+    import sys
+    from unittest.mock import MagicMock
+    if name in _REF_MODULES:
+        return _REF_MODULES[name]
+    ref_dir = os.environ.get("OVL_REFERENCE_DIR", "/root/reference")
+    path = os.path.join(ref_dir, name + ".py")
+    mod = None
+    if os.path.isfile(path):
+        for m in ("Bio", "Bio.Align", "matplotlib", "matplotlib.pyplot"):   # not on the hot path, may be absent
+            try:
+                __import__(m)
+            except Exception:
+                sys.modules.setdefault(m, MagicMock())
+        spec = importlib.util.spec_from_file_location(f"_ovl_reference_{name}", path)
+        mod = importlib.util.module_from_spec(spec)
+        saved_path = list(sys.path)
+        had = {m: m in sys.modules for m in ("aligners", "overlapGraphs")}
+        sys.path.insert(0, ref_dir)
+        try:
+            spec.loader.exec_module(mod)
+        finally:
+            sys.path[:] = saved_path
+            for m, was in had.items():          # do not leave the reference registered under
+                if not was:                     # the drop-in's module names
+                    sys.modules.pop(m, None)
+        if name == "overlapGraphs":
+            from . import overlapGraphs as dropin
+            from . import aligners as dropin_al
+            mod.construct_overlap_graph_nx_k = dropin.construct_overlap_graph_nx_k
+            mod.overlap_alignment = dropin_al.overlap_alignment
+    _REF_MODULES[name] = mod
+    return mod

@@ -1,0 +1,83 @@
+"""Drop-in for the reference's ``overlapGraphs.construct_overlap_graph_nx_k``
+(overlapGraphs.py:5-61): same signature, same ``(nx.DiGraph, read_copies)`` return value,
+same nodes, edges, attributes and iteration order.
+
+What stays on the host is what the return value itself is made of: the ``read_copies`` dict
+(overlapGraphs.py:18-20), the node-name strings and the NetworkX container.  The prefix
+index, the candidate lookup, the overlap DP and the copy x copy edge expansion
+(overlapGraphs.py:30-60) run on the GPU.  Other symbols of the reference module
+(assemble_contigs_using_overlap_graphs, ...) are forwarded to the reference checkout when it
+is present; they call this builder through the module global, as in overlapGraphs.py:167.
+"""
+from __future__ import annotations
+
+import networkx as nx
+import numpy as np
+
+try:
+    from . import engine as _engine
+except ImportError:      # imported as a top-level module with the package directory on sys.path
+    import importlib as _il
+    import os as _os
+    import sys as _sys
+    _pkg_dir = _os.path.dirname(_os.path.abspath(__file__))
+    if _os.path.dirname(_pkg_dir) not in _sys.path:
+        _sys.path.append(_os.path.dirname(_pkg_dir))
+    _engine = _il.import_module(_os.path.basename(_pkg_dir) + ".engine")
+
+
+def _flatten(uniq):
+    """Unique reads -> (ASCII bytes, int64 offsets)."""
+    lens = np.fromiter((len(r) for r in uniq), dtype=np.int64, count=len(uniq))
+    offsets = np.zeros(len(uniq) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    joined = "".join(uniq)
+    try:
+        raw = joined.encode("ascii")
+    except UnicodeEncodeError as exc:
+        raise _engine.nat.OvlUnsupported("reads contain non-ASCII characters; the 2-bit CUDA path "
+                                         "supports A, C, G, T only") from exc
+    bases = np.frombuffer(raw, dtype=np.uint8) if raw else np.zeros(0, np.uint8)
+    return bases, offsets
+
+
+def overlap_edge_rows(reads, k=5):
+    """The device part of the builder: returns (read_copies, uniq, counts, edges) where edges
+    is int32[E, 4] = (node_a, node_b, weight, end_position) in insertion order and node ids
+    number the copies in (uid, copy) order."""
+    assert k >= 0, "k-mer length must be non-negative"               # overlapGraphs.py:17
+    read_copies = {}
+    for read in reads:                                               # overlapGraphs.py:18-20
+        read_copies[read] = read_copies.get(read, 0) + 1
+    uniq = list(read_copies.keys())
+    for r in uniq:
+        if not isinstance(r, str):
+            raise TypeError("reads must be str")
+    counts = np.fromiter(read_copies.values(), dtype=np.int32, count=len(uniq))
+    if len(uniq) == 0:
+        return read_copies, uniq, counts, np.zeros((0, 4), np.int32)
+    bases, offsets = _flatten(uniq)
+    eng = _engine.get_engine()
+    edges = eng.overlap_edges(bases, offsets, counts, k)
+    return read_copies, uniq, counts, edges
+
+
+def construct_overlap_graph_nx_k(reads, k=5):
+    """Construct the overlap graph -- see overlapGraphs.py:5-16 for the contract."""
+    read_copies, uniq, counts, edges = overlap_edge_rows(reads, k)
+    overlap_graph = nx.DiGraph()
+    names = [f"{read}_{c}" for read, cnt in zip(uniq, counts.tolist()) for c in range(cnt)]   # :25-28
+    overlap_graph.add_nodes_from(names)
+    if edges.shape[0]:
+        cols = edges.T.tolist()               # Python ints, like the reference's edge attributes
+        overlap_graph.add_edges_from(
+            (names[u], names[v], {"weight": w, "end_position": e})
+            for u, v, w, e in zip(cols[0], cols[1], cols[2], cols[3]))
+    return overlap_graph, read_copies
+
+
+def __getattr__(name):
+    ref = _engine.reference_module("overlapGraphs")
+    if ref is not None and hasattr(ref, name):
+        return getattr(ref, name)
+    raise AttributeError(f"module 'overlapGraphs' (B200 drop-in) has no attribute {name!r}")

@@ -1,0 +1,145 @@
+/*
+ * ovl.h -- C ABI of libovl_b200.so: the B200 (sm_100a) overlap-detection hot path of
+ * roiteichman/Genome-Assembly-Using-Overlap-Graphs.
+ *
+ * The reference has no FFI layer: the boundary is two Python callables,
+ *   aligners.overlap_alignment(s, t, match_score=10, mismatch=-1, indel=-2**31)   aligners.py:6-82
+ *   overlapGraphs.construct_overlap_graph_nx_k(reads, k=5)                        overlapGraphs.py:5-61
+ * The Python drop-ins of those two functions (package genome-assembly-using-overlap-graphs_b200)
+ * bind the entry points below with ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, < 0 on error; ovl_last_error() gives the message
+ *     (thread local).  No exceptions cross the boundary, no ownership is transferred.
+ *   - every data pointer is a caller-owned DEVICE pointer unless its name starts with h_.
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous w.r.t. the host.
+ *   - scratch memory comes from the caller: query with the *_workspace_bytes() functions.
+ *   - one context per device; a context is not thread safe.
+ */
+#ifndef OVL_H
+#define OVL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OVL_OK 0
+#define OVL_E_CUDA (-1)      /* a CUDA runtime call or kernel launch failed */
+#define OVL_E_ARG (-2)       /* invalid argument */
+#define OVL_E_UNSUPPORTED (-3) /* valid for the reference, outside what the kernels implement */
+
+#define OVL_MAX_K 32          /* k-mer keys are 2k-bit integers in a uint64 */
+#define OVL_MAX_READ_LEN 1216 /* longest read the wavefront DP covers (32 lanes x 38 columns) */
+
+typedef struct ovl_ctx ovl_ctx;
+
+const char *ovl_last_error(void);
+int ovl_version(void);
+
+int ovl_ctx_create(int device, ovl_ctx **out);
+int ovl_ctx_destroy(ovl_ctx *ctx);
+int ovl_ctx_sm_count(const ovl_ctx *ctx);
+
+/* words per packed row for reads up to max_len bases: ceil(max_len/16) rounded up to a
+ * multiple of 4 so that every row is 16-byte aligned. */
+int32_t ovl_row_words(int32_t max_len);
+
+/* K0: ASCII reads -> 2-bit packed rows.  Stands in for the reference's Python str reads
+ * (the argument of overlapGraphs.py:5) in device form.
+ *   ascii      U reads concatenated; 16-byte aligned, >= 32 bytes of slack after the end
+ *   offsets    int64[U+1] byte offsets of the reads inside ascii
+ *   packed     uint32[U * row_words] out; base i of a read at bits 2*(i%16) of word i/16
+ *   len        int32[U] out
+ *   bad_count  int32[1] in/out (caller zeroes): number of 16-base words holding a byte
+ *              other than A, C, G, T.  The callers raise on bad_count != 0. */
+int ovl_pack_reads(ovl_ctx *ctx, const uint8_t *ascii, const int64_t *offsets, int64_t U,
+                   int32_t row_words, uint32_t *packed, int32_t *len, int32_t *bad_count,
+                   void *stream);
+
+/* K1: prefix / suffix k-mer keys, overlapGraphs.py:33-37 (read[:k]) and :44-47 (read[-k:]).
+ * Reads shorter than k can match nothing but themselves: their keys are placeholders and the
+ * index / join skip them by length. */
+int ovl_kmer_keys(ovl_ctx *ctx, const uint32_t *packed, int32_t row_words, const int32_t *len,
+                  int64_t U, int32_t k, uint64_t *prefix_key, uint64_t *suffix_key, void *stream);
+
+/* K2: the prefix index, overlapGraphs.py:30-40, as a stable sort of (prefix_key, uid):
+ * sorted_key / sorted_uid hold the *n_indexed reads with len >= k, keys ascending and uids
+ * ascending inside equal keys (the reference's bucket-append order). */
+size_t ovl_index_workspace_bytes(int64_t U);
+int ovl_index_build(ovl_ctx *ctx, const uint64_t *prefix_key, const int32_t *len, int64_t U, int32_t k,
+                    uint64_t *sorted_key, uint32_t *sorted_uid, int64_t *n_indexed,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* K3: candidate generation, overlapGraphs.py:43-52, for source reads a in [a_begin, a_end).
+ * ovl_join_count writes, per a, the bucket start, a's own rank inside the bucket (-1 if it
+ * is not in it) and the exclusive scan pair_off[(a_end-a_begin)+1] of the candidate counts;
+ * pair_off[last] is the number of pairs.  ovl_join_fill then writes pairs
+ * [p_begin, p_begin+p_count) of that range, ordered by (a, b) ascending. */
+size_t ovl_join_workspace_bytes(int64_t n_sources);
+int ovl_join_count(ovl_ctx *ctx, const uint64_t *suffix_key, const uint64_t *prefix_key,
+                   const int32_t *len, int32_t k, int64_t a_begin, int64_t a_end, const uint64_t *sorted_key,
+                   const uint32_t *sorted_uid, const int64_t *n_indexed, int32_t *bucket_lo,
+                   int32_t *self_rank, int64_t *pair_off, void *workspace, size_t workspace_bytes,
+                   void *stream);
+int ovl_join_fill(ovl_ctx *ctx, const int64_t *pair_off, int64_t a_begin, int64_t a_end,
+                  const int32_t *bucket_lo, const int32_t *self_rank, const uint32_t *sorted_uid,
+                  int64_t p_begin, int64_t p_count, int32_t *pair_a, int32_t *pair_b, void *stream);
+/* k == 0 (overlapGraphs.py:49): all ordered pairs a != b, a in [a_begin, ...); pair index p
+ * counts from a_begin: a = a_begin + p / (U-1). */
+int ovl_all_pairs_fill(ovl_ctx *ctx, int64_t U, int64_t a_begin, int64_t p_begin, int64_t p_count,
+                       int32_t *pair_a, int32_t *pair_b, void *stream);
+
+/* K4/K5: the DP call site overlapGraphs.py:53, i.e. aligners.py:27-57 for every pair:
+ *   score[p], end[p] = overlap_alignment(read[pair_a[p]], read[pair_b[p]], match, mismatch, indel)[3:5]
+ * indel is int64 like the reference's Numba-typed default (-2**31 never wraps).
+ * max_len = longest read in the batch (<= OVL_MAX_READ_LEN, <= 16*row_words).
+ * mode: 0 = choose, 1 = force the packed 16-bit kernel, 2 = force the 32-bit kernel.
+ * group_lanes / cols_per_lane: 0 = choose, else force that instantiation (tests). */
+int ovl_overlap_dp(ovl_ctx *ctx, const uint32_t *packed, int32_t row_words, const int32_t *len,
+                   const int32_t *pair_a, const int32_t *pair_b, int64_t P, int32_t max_len,
+                   int64_t match, int64_t mismatch, int64_t indel, int32_t *score, int32_t *end,
+                   int32_t mode, int32_t group_lanes, int32_t cols_per_lane, void *stream);
+/* which kernel ovl_overlap_dp would pick: out[0]=mode (1 packed, 2 int32), out[1]=lanes,
+ * out[2]=columns per lane.  Returns OVL_E_UNSUPPORTED when nothing fits. */
+int ovl_overlap_dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_t indel,
+                        int32_t mode, int32_t out[3]);
+
+/* K6: edge expansion, overlapGraphs.py:55-60.  Edge row = int32[4] (node_a, node_b, weight,
+ * end_position); node id = node_off[uid] + copy; order = pair order, copy_a, copy_b.
+ * ovl_expand_count writes the exclusive scan edge_off[P+1] of copies[a]*copies[b]. */
+size_t ovl_expand_workspace_bytes(int64_t P);
+int ovl_expand_count(ovl_ctx *ctx, const int32_t *pair_a, const int32_t *pair_b,
+                     const int32_t *copies, int64_t P, int64_t *edge_off, void *workspace,
+                     size_t workspace_bytes, void *stream);
+int ovl_expand_fill(ovl_ctx *ctx, const int64_t *edge_off, int64_t P, const int32_t *pair_a,
+                    const int32_t *pair_b, const int32_t *score, const int32_t *end,
+                    const int32_t *copies, const int64_t *node_off, int64_t e_begin,
+                    int64_t e_count, int32_t *edges, void *stream);
+/* every read occurs once (copies == 1 everywhere): edges[p] = (a, b, score, end) */
+int ovl_expand_unit(ovl_ctx *ctx, const int32_t *pair_a, const int32_t *pair_b,
+                    const int32_t *score, const int32_t *end, int64_t P, int32_t *edges,
+                    void *stream);
+
+/* K7: one pair with traceback: everything aligners.py:27-76 computes, for the single-pair
+ * drop-in.  s, t are int32 code points (any alphabet); arithmetic is the reference's (int64
+ * candidates, int32 storage).  result[0..2] = (best_score, alignment_end_position, n_ops);
+ * ops[0..n_ops) is the traceback from the end backwards: 0 diagonal, 1 up (gap in t),
+ * 2 left (gap in s); ops needs n+m bytes. */
+size_t ovl_align_pair_workspace_bytes(int32_t n, int32_t m);
+int ovl_align_pair(ovl_ctx *ctx, const int32_t *s, int32_t n, const int32_t *t, int32_t m,
+                   int64_t match, int64_t mismatch, int64_t indel, void *workspace,
+                   size_t workspace_bytes, int32_t *result, uint8_t *ops, void *stream);
+
+/* Roofline denominator for the DP: runs a dependency-free instruction stream on every SM and
+ * returns lane-operations per second (1e9/s).  kind: 0 IADD3, 1 IMAD, 2 VIMNMX.S32,
+ * 3 VIADDMNMX.S16x2, 4 the DP inner-loop mix (PRMT, IMAD, 2x VIADDMNMX.S16x2), 5 PRMT, 6 LOP3.
+ * Synchronises the device.  h_gops receives giga lane-instructions per second. */
+int ovl_int_peak_probe(ovl_ctx *ctx, int32_t kind, int32_t iters, double *h_gops, double *h_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OVL_H */

@@ -1,0 +1,96 @@
+"""CPU-side checks of the boundary: the library builds, loads and exports what include/ovl.h
+declares; host-side argument handling of the drop-ins (no GPU compute here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, load_pkg, has_cuda
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ovl.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ovl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    path = ge.build_library()
+    lib = ctypes.CDLL(path)
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ovl.h but not exported"
+    nat = load_pkg("_native")
+    assert sorted(nat.EXPORTS) == declared, "ctypes signature table and header disagree"
+
+
+def test_host_only_entry_points():
+    nat = load_pkg("_native")
+    assert nat.lib.ovl_version() >= 100
+    assert nat.lib.ovl_row_words(1) == 4
+    assert nat.lib.ovl_row_words(150) == 12
+    assert nat.lib.ovl_row_words(1000) == 64
+    assert nat.lib.ovl_index_workspace_bytes(1000) > 0
+    out = (ctypes.c_int32 * 3)()
+    # default scoring, l=150 -> packed 16-bit kernel, 4 lanes x 38 columns
+    assert nat.lib.ovl_overlap_dp_plan(150, 10, -1, -2 ** 31, 0, ctypes.byref(out)) == 0
+    assert list(out) == [1, 4, 38]
+    assert nat.lib.ovl_overlap_dp_plan(100, 10, -1, -2, 0, ctypes.byref(out)) == 0
+    assert list(out) == [1, 4, 25]
+    assert nat.lib.ovl_overlap_dp_plan(1000, 10, -1, -2 ** 31, 0, ctypes.byref(out)) == 0
+    assert list(out) == [1, 32, 32]
+    # scores that do not fit 16 bits fall to the int32 kernel
+    assert nat.lib.ovl_overlap_dp_plan(150, 10, -1000000, -2 ** 31, 0, ctypes.byref(out)) == 0
+    assert out[0] == 2
+    # too long for the wavefront kernels
+    assert nat.lib.ovl_overlap_dp_plan(5000, 10, -1, -2, 0, ctypes.byref(out)) == nat.OVL_E_UNSUPPORTED
+    assert b"5000" in nat.lib.ovl_last_error()
+
+
+@pytest.mark.skipif(has_cuda(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    pkg = load_pkg()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.construct_overlap_graph_nx_k(["ACGT", "CGTA"], k=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.overlap_alignment("ACGT", "CGTA")
+
+
+def test_argument_errors_match_reference():
+    pkg = load_pkg()
+    with pytest.raises(AssertionError):
+        pkg.construct_overlap_graph_nx_k(["ACGT"], k=-1)          # overlapGraphs.py:17
+    with pytest.raises(TypeError):
+        pkg.overlap_alignment(b"ACGT", "ACGT")                    # reference: Numba TypingError
+
+
+def test_drop_in_importable_as_top_level_modules():
+    """The reference's callers do `from aligners import overlap_alignment` (overlapGraphs.py:2)
+    and `from overlapGraphs import ...` (testAssembly.py:3)."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import overlapGraphs, aligners; "
+            "print(overlapGraphs.construct_overlap_graph_nx_k.__name__, aligners.overlap_alignment.__name__)"
+            % os.path.join(ROOT, "genome-assembly-using-overlap-graphs_b200"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True).stdout
+    assert out.split() == ["construct_overlap_graph_nx_k", "overlap_alignment"]
+
+
+def test_synth_generator_is_seeded_and_truncates():
+    synth = load_pkg("synth")
+    g = synth.phix_like_genome()
+    assert len(g) == 5386
+    b1, o1 = synth.simulate_reads(g, 500, 100, 0.01, seed=3)
+    b2, o2 = synth.simulate_reads(g, 500, 100, 0.01, seed=3)
+    assert (b1 == b2).all() and (o1 == o2).all()
+    lens = o1[1:] - o1[:-1]
+    assert lens.max() == 100 and lens.min() >= 1
+    ub, uo, counts, r2u = synth.dedup(b1, o1)
+    reads = synth.to_strings(b1, o1)
+    d = {}
+    for r in reads:
+        d[r] = d.get(r, 0) + 1
+    assert synth.to_strings(ub, uo) == list(d.keys()) and counts.tolist() == list(d.values())

@@ -1,0 +1,301 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden
+fixtures produced by the live reference.  Bit-exact: integer scores, end positions, edges."""
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+from conftest import load_pkg, has_cuda
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")]
+
+from oracle import overlap_oracle as orc  # noqa: E402  (the checker)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    return load_pkg("engine").get_engine()
+
+
+@pytest.fixture(scope="module")
+def nat():
+    return load_pkg("_native")
+
+
+def rand_reads(rng, n, lo, hi, alphabet="ACGT"):
+    return ["".join(rng.choice(alphabet) for _ in range(rng.randint(lo, hi))) for _ in range(n)]
+
+
+def overlapping_reads(rng, n, genome_len, read_len, p):
+    g = "".join(rng.choice("ACGT") for _ in range(genome_len))
+    out = []
+    for _ in range(n):
+        st = rng.randrange(genome_len)
+        r = g[st:st + read_len]
+        r = "".join(ch if rng.random() > p else rng.choice([c for c in "ACGT" if c != ch]) for ch in r)
+        out.append(r)
+    return out
+
+
+def upload(eng, reads):
+    bases, offsets = orc.concat_reads(reads)
+    return eng.upload_reads(bases[:int(offsets[-1])], offsets), bases, offsets
+
+
+# --------------------------------------------------------------------------- K7 single pair
+def test_single_pair_golden(golden_pairs):
+    al = load_pkg("aligners")
+    for c in golden_pairs:
+        got = al.overlap_alignment(c["s"], c["t"], c["match"], c["mismatch"], c["indel"])
+        want = (c["to_print"], c["align_s"], c["align_t"], c["score"], c["end"])
+        assert got == want, (c["s"], c["t"], c["match"], c["mismatch"], c["indel"])
+        assert type(got[3]) is int and type(got[4]) is int
+
+
+def test_single_pair_defaults_and_other_alphabets():
+    al = load_pkg("aligners")
+    assert al.overlap_alignment("ACGT", "TTACGTGG")[3:] == (40, 6)          # end > len(s)
+    assert al.overlap_alignment("", "") == ("\nTarget:   \n          \nQuery:    ", "", "", 0, 0)
+    # the single-pair kernel compares code points, so any alphabet works like in the reference
+    for s, t in [("hello world", "world peace"), ("NNNNACGT", "ACGTNNNN"), ("αβγδ", "γδεζ")]:
+        assert al.overlap_alignment(s, t) == orc_any(s, t)
+
+
+def orc_any(s, t, ma=10, mi=-1, ind=-2 ** 31):
+    """Pure-Python restatement of aligners.py:27-82 for non-latin-1 text (tiny inputs only)."""
+    n, m = len(s), len(t)
+    dp = [[0] * (m + 1) for _ in range(n + 1)]
+    tb = [[0] * (m + 1) for _ in range(n + 1)]
+    for i in range(1, n + 1):
+        for j in range(1, m + 1):
+            d = dp[i - 1][j - 1] + (ma if s[i - 1] == t[j - 1] else mi)
+            u = dp[i - 1][j] + ind
+            l = dp[i][j - 1] + ind
+            if d >= u and d >= l:
+                dp[i][j], tb[i][j] = d, 0
+            elif u >= l:
+                dp[i][j], tb[i][j] = u, 1
+            else:
+                dp[i][j], tb[i][j] = l, 2
+    best, bj = -float("inf"), 0
+    for j in range(m + 1):
+        if dp[n][j] > best:
+            best, bj = dp[n][j], j
+    i, j, a_s, a_t = n, bj, "", ""
+    while i > 0 and j > 0:
+        if tb[i][j] == 0:
+            a_s, a_t, i, j = s[i - 1] + a_s, t[j - 1] + a_t, i - 1, j - 1
+        elif tb[i][j] == 1:
+            a_s, a_t, i = s[i - 1] + a_s, "-" + a_t, i - 1
+        else:
+            a_s, a_t, j = "-" + a_s, t[j - 1] + a_t, j - 1
+    return f"\nTarget:   {a_t}\n          {'|' * len(a_t)}\nQuery:    {a_s}", a_s, a_t, int(best), bj
+
+
+# --------------------------------------------------------------------------- K0 / K1 / K2 / K3
+def np_pack(reads, row_words):
+    code = {"A": 0, "C": 1, "T": 2, "G": 3}
+    out = np.zeros((len(reads), row_words), dtype=np.uint32)
+    for u, r in enumerate(reads):
+        for i, ch in enumerate(r):
+            out[u, i // 16] |= np.uint32(code[ch] << (2 * (i % 16)))
+    return out
+
+
+def np_key(r, k, suffix):
+    code = {"A": 0, "C": 1, "T": 2, "G": 3}
+    seg = r[-k:] if suffix else r[:k]
+    v = 0
+    for i, ch in enumerate(seg):
+        v |= code[ch] << (2 * i)
+    return v
+
+
+@pytest.mark.parametrize("lo,hi,n", [(0, 40, 500), (1, 150, 700), (990, 1000, 40), (1, 1216, 30)])
+def test_pack_reads(eng, lo, hi, n):
+    import torch
+    rng = random.Random(lo * 1000 + hi)
+    reads = rand_reads(rng, n, lo, hi)
+    rs, _, offsets = upload(eng, reads)
+    eng.check_alphabet(rs)
+    got = rs.packed[:rs.n_reads * rs.row_words * 4].view(torch.int32).cpu().numpy().view(np.uint32)
+    got = got.reshape(rs.n_reads, rs.row_words)
+    assert np.array_equal(got, np_pack(reads, rs.row_words))
+    assert np.array_equal(rs.length[:n].cpu().numpy(), np.array([len(r) for r in reads], dtype=np.int32))
+
+
+def test_pack_rejects_non_acgt(eng, nat):
+    for bad in ["ACGTN", "acgt", "ACG-T", "ACGU", "ACGE"]:
+        rs, _, _ = upload(eng, ["ACGTACGTACGTACGTACGTA", bad, "TTTT"])
+        with pytest.raises(nat.OvlUnsupported):
+            eng.check_alphabet(rs)
+    g = load_pkg("overlapGraphs")
+    with pytest.raises(nat.OvlUnsupported):
+        g.construct_overlap_graph_nx_k(["ACGTN", "GTNAC"], k=2)
+
+
+@pytest.mark.parametrize("k", [1, 3, 5, 8, 15, 16, 17, 31, 32])
+def test_keys_index_and_join(eng, k):
+    import torch
+    rng = random.Random(k)
+    reads = list(dict.fromkeys(overlapping_reads(rng, 1500, 600, 48, 0.01) + rand_reads(rng, 60, 0, 40) +
+                               ["G" * 40, "G" * 33 + "A", "A" + "G" * 35]))
+    U = len(reads)
+    rs, _, _ = upload(eng, reads)
+    idx = eng.kmer_index(rs, k)
+    pk = idx.prefix_key[:U].cpu().numpy().view(np.uint64)
+    sk = idx.suffix_key[:U].cpu().numpy().view(np.uint64)
+    valid = np.array([len(r) >= k for r in reads])
+    want_pk = np.array([np_key(r, k, False) if len(r) >= k else 0 for r in reads], dtype=np.uint64)
+    want_sk = np.array([np_key(r, k, True) if len(r) >= k else 0 for r in reads], dtype=np.uint64)
+    assert np.array_equal(pk[valid], want_pk[valid]) and np.array_equal(sk[valid], want_sk[valid])
+    n_idx = int(idx.n_indexed.item())
+    assert n_idx == int(valid.sum())
+    order = np.argsort(want_pk[valid], kind="stable")
+    uids = np.nonzero(valid)[0][order]
+    assert np.array_equal(idx.sorted_uid[:n_idx].cpu().numpy().view(np.uint32), uids.astype(np.uint32))
+    assert np.array_equal(idx.sorted_key[:n_idx].cpu().numpy().view(np.uint64), want_pk[valid][order])
+    pa, pb, first = eng.candidate_pairs(rs, idx, k)
+    wa, wb = orc.candidate_pairs(reads, k)
+    assert first == 0
+    assert np.array_equal(pa.cpu().numpy(), wa) and np.array_equal(pb.cpu().numpy(), wb)
+    # sharded: concatenation of the rank slices is the global list
+    parts = [eng.candidate_pairs(rs, idx, k, (r, 3)) for r in range(3)]
+    assert [p[2] for p in parts] == [len(wa) * r // 3 for r in range(3)]
+    assert np.array_equal(torch.cat([p[0] for p in parts]).cpu().numpy(), wa)
+    assert np.array_equal(torch.cat([p[1] for p in parts]).cpu().numpy(), wb)
+
+
+def test_all_pairs_k0(eng):
+    reads = list(dict.fromkeys(rand_reads(random.Random(1), 40, 1, 12)))
+    rs, _, _ = upload(eng, reads)
+    pa, pb, _ = eng.candidate_pairs(rs, None, 0)
+    wa, wb = orc.candidate_pairs(reads, 0)
+    assert np.array_equal(pa.cpu().numpy(), wa) and np.array_equal(pb.cpu().numpy(), wb)
+
+
+# --------------------------------------------------------------------------- K4 / K5 batch DP
+PARAMS = [(10, -1, -2 ** 31), (10, -1, -2), (10, -1, -11), (1, -1, -1), (5, -4, -3), (2, -3, -2),
+          (10, -1, 0), (3, 0, -1), (-1, 10, -2), (7, 7, -3), (10, -1, -1000)]
+
+
+def run_dp(eng, reads, pa, pb, prm, **kw):
+    import torch
+    rs, bases, offsets = upload(eng, reads)
+    ta = torch.from_numpy(pa).to(eng.device)
+    tb = torch.from_numpy(pb).to(eng.device)
+    score, end = eng.overlap_scores(rs, ta, tb, *prm, **kw)
+    ws, we = orc.overlap_pairs(bases, offsets, pa, pb, *prm)
+    return score.cpu().numpy(), end.cpu().numpy(), ws, we
+
+
+@pytest.mark.parametrize("max_len", [1, 7, 25, 38, 64, 100, 150, 151, 300, 1000, 1216])
+def test_batch_dp_lengths(eng, max_len):
+    rng = random.Random(max_len)
+    n_reads = 60 if max_len > 300 else 300
+    reads = overlapping_reads(rng, n_reads, max(2 * max_len, 50), max_len, 0.03) + rand_reads(rng, 20, 0, max_len)
+    reads.append("")
+    P = 301 if max_len > 300 else 2001           # odd: exercises the half-empty last couple
+    pa = np.array([rng.randrange(len(reads)) for _ in range(P)], dtype=np.int32)
+    pb = np.array([rng.randrange(len(reads)) for _ in range(P)], dtype=np.int32)
+    for prm in PARAMS[:3] if max_len > 300 else PARAMS:
+        s, e, ws, we = run_dp(eng, reads, pa, pb, prm)
+        assert np.array_equal(s, ws) and np.array_equal(e, we), (max_len, prm)
+
+
+def test_batch_dp_every_instantiation(eng, nat):
+    """Force every (mode, lanes, columns) kernel that can hold the batch."""
+    rng = random.Random(99)
+    for max_len, n_pairs in [(24, 1500), (60, 1200), (150, 800), (400, 150), (1000, 40)]:
+        reads = overlapping_reads(rng, 120, 3 * max_len, max_len, 0.02) + rand_reads(rng, 10, 0, max_len)
+        pa = np.array([rng.randrange(len(reads)) for _ in range(n_pairs)], dtype=np.int32)
+        pb = np.array([rng.randrange(len(reads)) for _ in range(n_pairs)], dtype=np.int32)
+        tried = 0
+        for mode, cols_list in [(1, (25, 32, 38)), (2, (32,))]:
+            for lanes in (1, 2, 4, 8, 16, 32):
+                for cols in cols_list:
+                    if lanes * cols < max(len(r) for r in reads):
+                        continue
+                    for prm in [(10, -1, -2 ** 31), (10, -1, -2)]:
+                        s, e, ws, we = run_dp(eng, reads, pa, pb, prm, mode=mode, lanes=lanes, cols=cols)
+                        assert np.array_equal(s, ws) and np.array_equal(e, we), (max_len, mode, lanes, cols, prm)
+                        tried += 1
+        assert tried >= 6
+
+
+def test_batch_dp_wide_scores_use_int32_kernel(eng):
+    rng = random.Random(5)
+    reads = overlapping_reads(rng, 100, 400, 120, 0.05)
+    pa = np.array([rng.randrange(len(reads)) for _ in range(500)], dtype=np.int32)
+    pb = np.array([rng.randrange(len(reads)) for _ in range(500)], dtype=np.int32)
+    for prm in [(10, -1000000, -2 ** 31), (1000, -1, -5000), (300, -200, -7), (100000, -100000, -2 ** 31)]:
+        assert eng.dp_plan(120, *prm)["mode"] == "int32"
+        s, e, ws, we = run_dp(eng, reads, pa, pb, prm)
+        assert np.array_equal(s, ws) and np.array_equal(e, we), prm
+
+
+def test_batch_dp_unsupported_is_loud(eng, nat):
+    reads = ["ACGT" * 10, "CGTA" * 10]
+    pa, pb = np.array([0], np.int32), np.array([1], np.int32)
+    with pytest.raises(nat.OvlUnsupported):
+        run_dp(eng, reads, pa, pb, (2 ** 40, -1, -2))            # would overflow int32 storage
+    with pytest.raises(nat.OvlUnsupported):
+        upload(eng, ["A" * 1300])                                # longer than the wavefront covers
+
+
+# --------------------------------------------------------------------------- whole builder
+def test_graph_builder_golden(golden_graphs, nat):
+    g = load_pkg("overlapGraphs")
+    for c in golden_graphs:
+        if c["k"] > nat.OVL_MAX_K:
+            with pytest.raises(nat.OvlUnsupported):
+                g.construct_overlap_graph_nx_k(c["reads"], k=c["k"])
+            continue
+        G, read_copies = g.construct_overlap_graph_nx_k(c["reads"], k=c["k"])
+        assert [[r, n] for r, n in read_copies.items()] == c["read_copies"], c["name"]
+        nodes = list(G.nodes)
+        assert len(nodes) == c["n_nodes"]
+        assert hashlib.sha256("\n".join(nodes).encode()).hexdigest() == c["nodes_sha256"], c["name"]
+        idx = {n: i for i, n in enumerate(nodes)}
+        got = [[idx[u], idx[v], d["weight"], d["end_position"]] for u, v, d in G.edges(data=True)]
+        assert got == c["edges"], c["name"]
+        for _, _, d in list(G.edges(data=True))[:5]:
+            assert type(d["weight"]) is int and type(d["end_position"]) is int
+
+
+def test_graph_builder_vs_oracle_with_duplicates(eng):
+    g = load_pkg("overlapGraphs")
+    rng = random.Random(2024)
+    reads = overlapping_reads(rng, 3000, 500, 60, 0.005)       # tiny genome: many duplicate reads
+    assert len(set(reads)) < len(reads)
+    for k in (4, 9):
+        G, rc = g.construct_overlap_graph_nx_k(reads, k=k)
+        nodes, edges, rc2 = orc.construct_overlap_graph(reads, k)
+        assert list(rc.items()) == list(rc2.items())
+        G2 = orc.to_networkx(nodes, edges)
+        assert list(G.nodes) == list(G2.nodes)
+        assert list(G.edges(data=True)) == list(G2.edges(data=True))
+        assert [list(G.pred[n]) for n in G.nodes] == [list(G2.pred[n]) for n in G2.nodes]
+
+
+def test_edge_rows_insertion_order(eng):
+    """Device edge rows come in the reference's insertion order (a, b, copy_a, copy_b)."""
+    g = load_pkg("overlapGraphs")
+    rng = random.Random(11)
+    reads = overlapping_reads(rng, 800, 200, 30, 0.0)
+    rc, uniq, counts, edges = g.overlap_edge_rows(reads, k=6)
+    nodes, oedges, _ = orc.construct_overlap_graph(reads, 6)
+    idx = {n: i for i, n in enumerate(nodes)}
+    want = np.array([[idx[u], idx[v], w, e] for u, v, w, e in oedges], dtype=np.int32).reshape(-1, 4)
+    assert np.array_equal(edges, want)
+
+
+def test_sharded_edges_concatenate(eng):
+    """Rank slices of the pair list produce edge slices whose concatenation is the 1-GPU list."""
+    synth = load_pkg("synth")
+    bases, offsets = synth.simulate_reads(synth.phix_like_genome(), 4000, 100, 0.01, seed=5)
+    ub, uo, counts, _ = synth.dedup(bases, offsets)
+    whole = eng.overlap_edges(ub, uo, counts, k=6)
+    parts = [eng.overlap_edges(ub, uo, counts, k=6, shard=(r, 4)) for r in range(4)]
+    assert np.array_equal(np.concatenate(parts), whole)
