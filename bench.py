@@ -316,7 +316,8 @@ def run_ours(args):
     if rank == 0:
         # ---- roofline of the dominant kernel (the DP): integer pipe, not HBM
         probe = {}
-        names = {0: "iadd3", 1: "imad", 2: "vimnmx_s32", 3: "viaddmnmx_s16x2", 4: "dp_mix", 5: "prmt", 6: "lop3"}
+        names = {0: "iadd3", 1: "imad", 2: "vimnmx_s32", 3: "viaddmnmx_s16x2", 4: "dp_mix", 5: "prmt", 6: "lop3",
+                 7: "lop3_imad_pair"}
         import ctypes
         nat = importlib.import_module(PKG + "._native")
         for kind, nm in names.items():

@@ -361,7 +361,7 @@ size_t ovl_expand_workspace_bytes(int64_t P) {
 
 int ovl_expand_count(ovl_ctx* ctx, const int32_t* pair_a, const int32_t* pair_b, const int32_t* copies, int64_t P,
                      int64_t* edge_off, void* workspace, size_t workspace_bytes, void* stream) {
-    if (!ctx || !pair_a || !pair_b || !copies || !edge_off || !workspace) return fail(OVL_E_ARG, "ovl_expand_count: null argument");
+    if (!ctx || !edge_off || !workspace || (P > 0 && (!pair_a || !pair_b || !copies))) return fail(OVL_E_ARG, "ovl_expand_count: null argument");
     if (workspace_bytes < ovl_expand_workspace_bytes(P)) return fail(OVL_E_ARG, "ovl_expand_count: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
@@ -458,6 +458,7 @@ int ovl_int_peak_probe(ovl_ctx* ctx, int32_t kind, int32_t iters, double* h_gops
         case 4: return run_probe<4>(ctx, iters, h_gops, h_ms);
         case 5: return run_probe<5>(ctx, iters, h_gops, h_ms);
         case 6: return run_probe<6>(ctx, iters, h_gops, h_ms);
+        case 7: return run_probe<7>(ctx, iters, h_gops, h_ms);
         default: return fail(OVL_E_ARG, "ovl_int_peak_probe: unknown kind %d", kind);
     }
 }

@@ -30,12 +30,16 @@ __global__ void __launch_bounds__(kProbeThreads) int_probe_kernel(uint32_t* out,
                 } else if (KIND == 3) {     // VIADDMNMX.S16x2
                     v[c] = __viaddmax_s16x2(v[c], b0, w[c]);
                 } else if (KIND == 4) {     // DP inner-loop mix: PRMT + IMAD + 2x VIADDMNMX.S16x2
+                    // every op depends on the chain value so ptxas cannot hoist any of them
                     uint32_t sc;
-                    asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(sc) : "r"(a0), "r"(b0), "r"(w[c]));
+                    asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(sc) : "r"(a0), "r"(b0), "r"(v[c]));
                     uint32_t d;
                     asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(sc), "r"(one), "r"(w[c]));
                     uint32_t t1 = __viaddmax_s16x2(w[c], b0, d);
                     v[c] = __viaddmax_s16x2(v[c], a0, t1);
+                } else if (KIND == 7) {     // LOP3 and IMAD on independent chains: do ALU and FMA pipes co-issue?
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[c]) : "r"(a0), "r"(b0));
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(w[c]) : "r"(one), "r"(b0));
                 } else if (KIND == 5) {     // PRMT
                     asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(v[c]) : "r"(w[c]), "r"(b0));
                 } else {                    // LOP3
@@ -50,6 +54,6 @@ __global__ void __launch_bounds__(kProbeThreads) int_probe_kernel(uint32_t* out,
     if (acc == 0x12345678u) out[0] = acc;    // practically never; keeps the chains alive
 }
 
-inline int probe_ops_per_iter(int kind) { return kind == 4 ? 4 : 1; }
+inline int probe_ops_per_iter(int kind) { return kind == 4 ? 4 : (kind == 7 ? 2 : 1); }
 
 }  // namespace ovl

@@ -244,6 +244,8 @@ class OverlapEngine:
         copies=None means every read occurs once (node id == uid)."""
         P = int(pair_a.shape[0])
         st = self._stream()
+        if P == 0:
+            return torch.empty((0, 4), dtype=torch.int32, device=self.device)
         if copies is None:
             edges = self._empty(P * 4, torch.int32)
             if P:

@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--max-pairs", type=int, default=4_000_000)
     ap.add_argument("--indel", type=int, default=-2 ** 31)
     ap.add_argument("--modes", default="1,2")
+    ap.add_argument("--only", default="", help="LANESxCOLS, e.g. 4x38")
+    ap.add_argument("--no-probe", action="store_true")
     args = ap.parse_args()
     import torch
     synth = importlib.import_module(PKG + ".synth")
@@ -47,6 +49,8 @@ def main():
             for cols in ((25, 32, 38) if mode == 1 else (32,)):
                 if lanes * cols < rs.max_len or lanes * cols > 4 * max(rs.max_len, 38):
                     continue
+                if args.only and args.only != f"{lanes}x{cols}":
+                    continue
                 try:
                     s, e = eng.overlap_scores(rs, pa, pb, 10, -1, args.indel, mode=mode, lanes=lanes, cols=cols)
                 except nat.OvlError as exc:
@@ -66,7 +70,10 @@ def main():
                     best = min(best, e0.elapsed_time(e1))
                 print(json.dumps({"mode": mode, "lanes": lanes, "cols": cols, "ms": round(best, 3),
                                   "gcups": round(cells / best / 1e6, 1), "same_as_first": ok}), flush=True)
-    names = {0: "iadd3", 1: "imad", 2: "vimnmx_s32", 3: "viaddmnmx_s16x2", 4: "dp_mix", 5: "prmt", 6: "lop3"}
+    if args.no_probe:
+        return
+    names = {0: "iadd3", 1: "imad", 2: "vimnmx_s32", 3: "viaddmnmx_s16x2", 4: "dp_mix", 5: "prmt", 6: "lop3",
+                 7: "lop3_imad_pair"}
     probe = {}
     for kind, nm in names.items():
         g, ms = ctypes.c_double(), ctypes.c_double()
