@@ -9,43 +9,56 @@
 // sweeps the rows as a wavefront: at step k lane r computes row k-r, taking its left
 // neighbour's last column from the previous step with one __shfl_up_sync.  G*T >= longest t.
 //
-// Packed arithmetic.  The two pairs of a couple live in the two 16-bit halves of every
-// register and are advanced together by the DPX instructions VIADDMNMX.S16x2
-// (__viaddmax_s16x2): per 32-bit lane op two DP cells.  To keep the per-cell instruction
-// count at four the recurrence is re-based:
-//     G[i][j] = H[i][j] - i*base + beta,   base = min(match, mismatch)
-//   diag:  G[i-1][j-1] + sc,  sc = score - base  in {0, |match - mismatch|}   (>= 0)
-//   up:    G[i-1][j]   + (indel - base)
-//   left:  G[i][j-1]   + indel
-// sc for both halves comes from ONE byte permute: per row the two query bases select two
-// 4-entry byte tables (lutA, lutB); per column the selector register holds the two target
-// bases (PRMT picks lutA[tA] into the low half, lutB[tB] into the high half, zero bytes via
-// the sign-replicate selector on a non-negative byte).  Because every G is in [0, 32767] the
-// diagonal add is a plain 32-bit add with no carry between halves; it is issued as IMAD so
-// it runs on the FMA pipe while PRMT and the two VIADDMNMX run on the ALU pipe.
-// indel = -2^31 (the reference default: gapless) and any indel too negative to ever win are
-// clamped to -(range+1), which is exact (see ovl_overlap_dp in ovl.cu for the bounds).
+// Cost space.  The recurrence is evaluated on  C[i][j] = beta + i*maxs - H[i][j]  with
+// maxs = max(match, mismatch):
+//     diag:  C[i-1][j-1] + dc,   dc = maxs - score  in {0, |match - mismatch|}
+//     up:    C[i-1][j]   + gu,   gu = maxs - indel
+//     left:  C[i][j-1]   + gl,   gl = -indel
+//     C[i][j] = min of the three;  C[0][j] = beta,  C[i][0] = beta + i*maxs
+// For gap penalties (indel <= 0) every addend is NON-NEGATIVE and every C is in [0, Cmax], so
+//   * two pairs are packed in the two 16-bit halves of each register (unsigned), and all three
+//     adds are plain 32-bit adds with no carry between the halves -- they can be issued as
+//     IMAD on the FMA pipe, next to the ALU pipe that does the DPX min (VIMNMX3.U16x2 /
+//     VIADDMNMX.U16x2).  Measured on B200: ALU and FMA pipes each issue 64 lanes/clk/SM and
+//     co-issue (probe kinds 5,6,7 in probe.cuh), so the per-column work is split over both.
+//   * indel = -2^31 (the reference default: gapless) or any indel too negative to ever win is
+//     replaced by Cmax+1, which is exact: such a candidate exceeds every true cell value.
+// dc for both halves comes from ONE byte permute: the two query bases of a row select two
+// 4-entry byte tables (lutA, lutB), precomputed per row in shared memory; the per-column
+// selector register holds the two target bases (PRMT puts lutA[tA] in the low half,
+// lutB[tB] in the high half; the zero bytes come from the sign-replicate selector applied to
+// a byte < 128).
+// Per column (2 cells) the kernel issues either
+//     form 1:  PRMT, IMAD, VIADDMNMX, VIADDMNMX          (3 ALU + 1 FMA)
+//     form 2:  PRMT, IMAD, IMAD, IMAD, VIMNMX3           (2 ALU + 3 FMA)
+// mixed OVL_DP_F2_NUM : OVL_DP_F2_DEN to balance the two pipes.
 //
-// A 32-bit variant (one pair per group, VIADDMNMX on s32, compare+select for sc) covers
-// scoring schemes or read lengths whose range does not fit 16 bits.
+// A 32-bit variant (one pair per group, s32 DPX ops, compare+select for dc) covers scoring
+// schemes or read lengths whose range does not fit 16 bits.
 #pragma once
 #include "common.cuh"
 
 namespace ovl {
 
 struct DpParams {
-    int32_t eqv;        // match - base      (>= 0)
-    int32_t nev;        // mismatch - base   (>= 0), one of eqv/nev is 0
-    int32_t base;       // min(match, mismatch)
-    int32_t beta;       // bias so that every G >= 0
-    int32_t gu;         // effective (indel - base), clamped
-    int32_t gl;         // effective indel, clamped
-    uint32_t one;       // == 1, a runtime value so the diagonal add stays an IMAD
+    int32_t eqc;        // maxs - match      (>= 0)   diagonal cost on equal bases
+    int32_t nec;        // maxs - mismatch   (>= 0)   diagonal cost on different bases
+    int32_t maxs;       // max(match, mismatch): per-row drift
+    int32_t beta;       // bias so that every C >= 0
+    int32_t gu;         // effective cost of an up move   (maxs - indel), clamped
+    int32_t gl;         // effective cost of a left move  (-indel), clamped
+    uint32_t one;       // == 1, a runtime value so the adds stay IMADs
 };
 
 constexpr int kDpThreads = 128;
 #ifndef OVL_DP_MINB
 #define OVL_DP_MINB 4          // resident CTAs per SM the register allocator must allow
+#endif
+#ifndef OVL_DP_F2_NUM
+#define OVL_DP_F2_NUM 1        // columns using form 2 (FMA-heavy): NUM out of every DEN
+#endif
+#ifndef OVL_DP_F2_DEN
+#define OVL_DP_F2_DEN 2
 #endif
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -53,31 +66,36 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
-__device__ __forceinline__ uint32_t imad_add(uint32_t a, uint32_t one, uint32_t c) {
+// a + c as IMAD (a * 1 + c): runs on the FMA pipe instead of the ALU pipe
+__device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t one, uint32_t c) {
     uint32_t d;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(c));
     return d;
 }
-__device__ __forceinline__ uint32_t base_code(const uint32_t* row, int i) {
+__device__ __forceinline__ uint32_t base_code(const uint32_t* __restrict__ row, int i) {
     return (row[i >> 4] >> ((i & 15) * 2)) & 3u;
 }
 __device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; }
-__device__ __forceinline__ int half_lo(uint32_t x) { return (int)(int16_t)(x & 0xffffu); }
-__device__ __forceinline__ int half_hi(uint32_t x) { return (int)x >> 16; }
+__device__ __forceinline__ constexpr bool dp_form2(int c) {
+    return OVL_DP_F2_NUM > 0 && (c * OVL_DP_F2_NUM) % OVL_DP_F2_DEN < OVL_DP_F2_NUM;
+}
 
-// PK = true : two pairs per group (16-bit halves).  PK = false: one pair per group (32 bit).
+// rows of the per-couple LUT array, padded so that consecutive couples start 8 banks apart
+__host__ __device__ inline int dp_lut_rows(int max_len) {
+    int r = max_len < 1 ? 1 : max_len;
+    return ((r + 11) / 16) * 16 + 4;       // == 4 (mod 16), >= r
+}
+
+// PK = true : two pairs per group (unsigned 16-bit halves).  PK = false: one pair per group (s32).
 template <int G, int T, bool PK>
-__global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(const uint32_t* __restrict__ packed, int row_words,
-                                                                const int32_t* __restrict__ len,
-                                                                const int32_t* __restrict__ pair_a,
-                                                                const int32_t* __restrict__ pair_b, int64_t P,
-                                                                DpParams prm,
-                                                                int32_t* __restrict__ score_out,
-                                                                int32_t* __restrict__ end_out) {
+__global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(
+    const uint32_t* __restrict__ packed, int row_words, const int32_t* __restrict__ len,
+    const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b, int64_t P, int lut_rows,
+    DpParams prm, int32_t* __restrict__ score_out, int32_t* __restrict__ end_out) {
     constexpr int PAIRS = PK ? 2 : 1;
     constexpr int GROUPS_PER_WARP = 32 / G;
     constexpr int GROUPS_PER_CTA = (kDpThreads / 32) * GROUPS_PER_WARP;
-    extern __shared__ uint32_t smem[];                 // [GROUPS_PER_CTA][2*PAIRS][row_words]
+    extern __shared__ uint2 smem_lut[];                // [GROUPS_PER_CTA][lut_rows] (lutA, lutB)
 
     const unsigned lane = lane_id();
     const int r = lane % G;                            // lane within the group
@@ -85,10 +103,9 @@ __global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(con
     const int64_t grp = (int64_t)blockIdx.x * GROUPS_PER_CTA + gib;
     const int64_t p0 = grp * PAIRS;
 
-    // ---- stage the packed reads of this group's pairs in shared memory (128-bit copies)
     int32_t n[PAIRS], m[PAIRS];
-    uint32_t* rows = smem + (size_t)gib * (2 * PAIRS) * row_words;
-    const int rw4 = row_words >> 2;
+    const uint32_t* srow[PAIRS];
+    const uint32_t* trow[PAIRS];
 #pragma unroll
     for (int h = 0; h < PAIRS; ++h) {
         int64_t p = p0 + h;
@@ -96,32 +113,35 @@ __global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(con
         int32_t a = live ? pair_a[p] : 0, b = live ? pair_b[p] : 0;
         n[h] = live ? len[a] : 0;
         m[h] = live ? len[b] : 0;
-        const uint4* sa = reinterpret_cast<const uint4*>(packed + (size_t)a * row_words);
-        const uint4* sb = reinterpret_cast<const uint4*>(packed + (size_t)b * row_words);
-        uint4* ds = reinterpret_cast<uint4*>(rows + (size_t)(2 * h) * row_words);
-        uint4* dt = reinterpret_cast<uint4*>(rows + (size_t)(2 * h + 1) * row_words);
-        for (int i = r; i < rw4; i += G) { ds[i] = __ldg(sa + i); dt[i] = __ldg(sb + i); }
+        srow[h] = packed + (size_t)a * row_words;
+        trow[h] = packed + (size_t)b * row_words;
     }
-    __syncwarp();
-    const uint32_t* sA = rows;
-    const uint32_t* tA = rows + row_words;
-    const uint32_t* sB = rows + (PK ? 2 : 0) * row_words;
-    const uint32_t* tB = rows + (PK ? 3 : 1) * row_words;
-
     const int nmax = PK ? max(n[0], n[PAIRS - 1]) : n[0];
-    const int steps = __reduce_max_sync(kFull, nmax) + G - 1;      // warp-uniform trip count
     const int max_col = row_words * 16 - 1;
 
+    // ---- per-row tables: lut.x / lut.y = bytes {cost of s[i] vs code 0..3} for pair 0 / 1
+    uint2* lut = smem_lut + (size_t)gib * lut_rows;
+    {
+        const uint32_t nec4 = (uint32_t)prm.nec * 0x01010101u;
+        const uint32_t flip = (uint32_t)(prm.eqc ^ prm.nec);
+        for (int i = r; i < nmax; i += G) {
+            uint32_t ca = base_code(srow[0], min(i, max_col));
+            uint32_t cb = base_code(srow[PAIRS - 1], min(i, max_col));
+            lut[i] = PK ? make_uint2(nec4 ^ (flip << (8 * ca)), nec4 ^ (flip << (8 * cb))) : make_uint2(ca, 0u);
+        }
+    }
+    __syncwarp();
+
     // ---- per-column state
-    uint32_t up[T];        // G[i-1][j] for my columns (row 0: beta)
+    uint32_t up[T];        // C[i-1][j] for my columns (row 0: beta)
     uint32_t sel[T];       // PK: PRMT selector holding (tA[j], tB[j]);  else: t code
     const uint32_t beta2 = PK ? pack2(prm.beta) : (uint32_t)prm.beta;
 #pragma unroll
     for (int c = 0; c < T; ++c) {
         int j = min(r * T + c, max_col);
-        uint32_t ca = base_code(tA, j);
+        uint32_t ca = base_code(trow[0], j);
         if (PK) {
-            uint32_t cb = base_code(tB, j);
+            uint32_t cb = base_code(trow[PAIRS - 1], j);
             sel[c] = ca | 0x80u | ((4u + cb) << 8) | 0x8000u;
         } else {
             sel[c] = ca;
@@ -130,85 +150,83 @@ __global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(con
     }
     const uint32_t gu2 = PK ? pack2(prm.gu) : (uint32_t)prm.gu;
     const uint32_t gl2 = PK ? pack2(prm.gl) : (uint32_t)prm.gl;
-    const uint32_t nbase2 = PK ? (uint32_t)(-prm.base) * 0x10001u : (uint32_t)(-prm.base);
-    const uint32_t nev4 = (uint32_t)prm.nev * 0x01010101u;
-    const uint32_t flip = (uint32_t)(prm.eqv ^ prm.nev);
+    const uint32_t maxs2 = PK ? (uint32_t)prm.maxs * 0x10001u : (uint32_t)prm.maxs;
+    const uint32_t one = prm.one;
 
-    // running best of the last row, per half: value in G space, column j
+    // running best of the last row, per pair: cost (smaller is better), column j
     int bestv[PAIRS], bestj[PAIRS];
 #pragma unroll
     for (int h = 0; h < PAIRS; ++h) {
-        bestv[h] = (r == 0) ? prm.beta - n[h] * prm.base : INT_MIN;   // G[n][0]  (j = 0 floor, aligners.py:51-57)
+        bestv[h] = (r == 0) ? prm.beta + n[h] * prm.maxs : INT_MAX;   // C[n][0]  (j = 0, aligners.py:51-57)
         bestj[h] = 0;
     }
 
     uint32_t out = beta2;        // my last column of the row just finished (goes to lane r+1)
-    uint32_t diag_in = beta2;    // G[i-1][rT-1] for the row about to be computed
-    uint32_t col0 = beta2;       // lane 0: G[i][0] = beta - i*base
+    uint32_t diag_in = beta2;    // C[i-1][rT-1] for the row about to be computed
+    uint32_t col0 = beta2;       // lane 0: C[i][0] = beta + i*maxs
+    const int steps = __reduce_max_sync(kFull, nmax) + G - 1;      // warp-uniform trip count
 
     for (int k = 0; k < steps; ++k) {
         const int i = k - r;                               // 0-based row of s handled this step
         uint32_t recv = __shfl_up_sync(kFull, out, 1, G);
-        col0 += nbase2;                                    // lane 0 at step k: G[k+1][0]
+        col0 += maxs2;                                     // lane 0 at step k: C[k+1][0]
         if (r == 0) recv = col0;
         if (i >= 0 && i < nmax) {
             uint32_t left = recv, diag = diag_in;
-            if (PK) {
-                uint32_t ca = base_code(sA, i), cb = base_code(sB, i);
-                uint32_t lutA = nev4 ^ (flip << (8 * ca));
-                uint32_t lutB = nev4 ^ (flip << (8 * cb));
+            const uint2 lu = lut[i];
 #pragma unroll
-                for (int c = 0; c < T; ++c) {
-                    uint32_t sc = prmt(lutA, lutB, sel[c]);
-                    uint32_t d = imad_add(sc, prm.one, diag);
-                    uint32_t t1 = __viaddmax_s16x2(up[c], gu2, d);
-                    uint32_t g = __viaddmax_s16x2(left, gl2, t1);
-                    diag = up[c];
-                    up[c] = g;
-                    left = g;
+            for (int c = 0; c < T; ++c) {
+                uint32_t g;
+                if (PK) {
+                    uint32_t dc = prmt(lu.x, lu.y, sel[c]);
+                    uint32_t a1 = fma_add(dc, one, diag);
+                    if (dp_form2(c)) {
+                        uint32_t a2 = fma_add(up[c], one, gu2);
+                        uint32_t a3 = fma_add(left, one, gl2);
+                        g = __vimin3_u16x2(a1, a2, a3);
+                    } else {
+                        uint32_t t1 = __viaddmin_u16x2(up[c], gu2, a1);
+                        g = __viaddmin_u16x2(left, gl2, t1);
+                    }
+                } else {
+                    int dc = (sel[c] == lu.x) ? prm.eqc : prm.nec;
+                    int a1 = (int)diag + dc;
+                    int t1 = __viaddmin_s32((int)up[c], (int)gu2, a1);
+                    g = (uint32_t)__viaddmin_s32((int)left, (int)gl2, t1);
                 }
-            } else {
-                uint32_t ca = base_code(sA, i);
-#pragma unroll
-                for (int c = 0; c < T; ++c) {
-                    int sc = (sel[c] == ca) ? prm.eqv : prm.nev;
-                    int d = (int)diag + sc;
-                    int t1 = __viaddmax_s32((int)up[c], (int)gu2, d);
-                    int g = __viaddmax_s32((int)left, (int)gl2, t1);
-                    diag = up[c];
-                    up[c] = (uint32_t)g;
-                    left = (uint32_t)g;
-                }
+                diag = up[c];
+                up[c] = g;
+                left = g;
             }
             out = left;
             diag_in = recv;
-            // last row of a pair reached: fold my columns into its running (first) maximum
+            // last row of a pair reached: fold my columns into its running (first) minimum
 #pragma unroll
             for (int h = 0; h < PAIRS; ++h) {
                 if (i + 1 == n[h]) {
 #pragma unroll
                     for (int c = 0; c < T; ++c) {
                         int j = r * T + c + 1;
-                        int v = PK ? (h == 0 ? half_lo(up[c]) : half_hi(up[c])) : (int)up[c];
-                        if (j <= m[h] && v > bestv[h]) { bestv[h] = v; bestj[h] = j; }
+                        int v = PK ? (int)(h == 0 ? (up[c] & 0xffffu) : (up[c] >> 16)) : (int)up[c];
+                        if (j <= m[h] && v < bestv[h]) { bestv[h] = v; bestj[h] = j; }
                     }
                 }
             }
         }
     }
 
-    // ---- group arg-max: higher value wins, ties go to the smaller j (first maximum)
+    // ---- group arg-min: lower cost wins, ties go to the smaller j (first maximum of H)
 #pragma unroll
     for (int h = 0; h < PAIRS; ++h) {
 #pragma unroll
         for (int d = 1; d < G; d <<= 1) {
             int ov = __shfl_xor_sync(kFull, bestv[h], d, G);
             int oj = __shfl_xor_sync(kFull, bestj[h], d, G);
-            if (ov > bestv[h] || (ov == bestv[h] && oj < bestj[h])) { bestv[h] = ov; bestj[h] = oj; }
+            if (ov < bestv[h] || (ov == bestv[h] && oj < bestj[h])) { bestv[h] = ov; bestj[h] = oj; }
         }
         int64_t p = p0 + h;
         if (r == 0 && p < P) {
-            score_out[p] = bestv[h] - prm.beta + n[h] * prm.base;
+            score_out[p] = prm.beta + n[h] * prm.maxs - bestv[h];
             end_out[p] = bestj[h];
         }
     }

@@ -240,32 +240,41 @@ const int kPackedT[] = {25, 32, 38};
 const int kScalarT[] = {32};
 const int kLanes[] = {1, 2, 4, 8, 16, 32};
 
-// Range analysis for the re-based recurrence (see dp.cuh).  N = longest s, M = G*T columns.
+// Range analysis for the cost-space recurrence (see dp.cuh).  N = longest s (rows), M = G*T
+// columns.  C[i][j] = beta + i*maxs - H[i][j].  With indel <= 0:
+//   max(maxs,0)*min(i,j) >= H[i][j] >= min(base,0)*min(i,j)      (base = min(match, mismatch))
+// so 0 <= C <= Cmax = beta + max(maxs,0)*N + |min(base,0)|*min(N,M), beta = max(-maxs,0)*N, and
+// the diagonal candidate obeys the same bound.  A gap cost above Cmax can never win and is
+// replaced by Cmax+1 (exact).  The packed kernel needs every addend >= 0 and no carry out of a
+// 16-bit half: Cmax + max(gu, gl) <= 65535.
 bool dp_params(int64_t match, int64_t mismatch, int64_t indel, int64_t N, int64_t M, bool packed, DpParams* out) {
-    const int64_t limit = packed ? 32767 : (1ll << 30);
     const int64_t big = 1ll << 40;
     if (std::llabs(match) > big || std::llabs(mismatch) > big) return false;
-    int64_t base = std::min(match, mismatch);
-    int64_t eqv = match - base, nev = mismatch - base;
-    if (packed && (eqv > 127 || nev > 127)) return false;
-    if (eqv > limit || nev > limit) return false;
-    int64_t g = std::max<int64_t>(indel, -big);
-    g = std::min<int64_t>(g, big);
-    int64_t gain = std::max<int64_t>(std::max(match, mismatch), 0);
+    int64_t g = std::min<int64_t>(std::max<int64_t>(indel, -big), big);
+    int64_t maxs = std::max(match, mismatch), base = std::min(match, mismatch);
+    int64_t eqc = maxs - match, nec = maxs - mismatch;
     int64_t mn = std::min(N, M);
-    int64_t Hhi = g <= 0 ? gain * mn : std::max(gain, g) * (N + M);
-    int64_t absbase = base < 0 ? -base : base;
-    int64_t beta = std::max<int64_t>(base, 0) * N;
-    int64_t Ghi = Hhi + absbase * N;           // all G in [0, Ghi]
-    if (Ghi > limit) return false;
-    int64_t gl = g, gu = g - base;
-    if (Ghi + std::max(gu, gl) < 0) {
-        // a gap can never reach any true cell value (all >= 0): any always-negative constant is exact
-        gl = gu = -(Ghi + 1);
+    int64_t gu = maxs - g, gl = -g, beta, hi;
+    if (g <= 0) {
+        beta = std::max<int64_t>(-maxs, 0) * N;
+        int64_t cmax = beta + std::max<int64_t>(maxs, 0) * N + std::max<int64_t>(-base, 0) * mn;
+        if (gu > cmax) gu = cmax + 1;
+        if (gl > cmax) gl = cmax + 1;
+        hi = cmax + std::max<int64_t>(std::max(gu, gl), 0);
+        if (packed) {
+            if (eqc > 127 || nec > 127 || gu < 0 || gl < 0 || hi > 65535 || cmax > 32767) return false;
+        } else if (hi >= (1ll << 30) || std::min(gu, gl) <= -(1ll << 30)) {
+            return false;
+        }
+    } else {
+        // gaps are rewarded (nothing the assembler uses, but the signature allows it): int32 only
+        if (packed) return false;
+        beta = 0;
+        int64_t mag = (int64_t)std::llabs(maxs) * N + std::max<int64_t>(std::max<int64_t>(std::llabs(match), std::llabs(mismatch)), g) * (N + M);
+        if (mag >= (1ll << 30)) return false;
     }
-    if (std::min(gu, gl) < -limit - 1) return false;
-    if (Ghi + std::max<int64_t>(std::max(gu, gl), 0) > limit) return false;
-    out->eqv = (int32_t)eqv; out->nev = (int32_t)nev; out->base = (int32_t)base; out->beta = (int32_t)beta;
+    if (eqc >= (1ll << 30) || nec >= (1ll << 30)) return false;
+    out->eqc = (int32_t)eqc; out->nec = (int32_t)nec; out->maxs = (int32_t)maxs; out->beta = (int32_t)beta;
     out->gu = (int32_t)gu; out->gl = (int32_t)gl; out->one = 1u;
     return true;
 }
@@ -296,24 +305,25 @@ bool dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_t indel, in
 
 template <int G, int T, bool PK>
 int launch_dp(const uint32_t* packed, int32_t row_words, const int32_t* len, const int32_t* pair_a, const int32_t* pair_b,
-              int64_t P, const DpParams& prm, int32_t* score, int32_t* end, cudaStream_t st) {
+              int64_t P, int32_t max_len, const DpParams& prm, int32_t* score, int32_t* end, cudaStream_t st) {
     constexpr int PAIRS = PK ? 2 : 1;
     constexpr int GROUPS_PER_CTA = (kDpThreads / 32) * (32 / G);
     int64_t groups = (P + PAIRS - 1) / PAIRS;
     int64_t grid = (groups + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA;
     if (grid > 0x7fffffffll) return fail(OVL_E_ARG, "ovl_overlap_dp: too many pairs for one launch (%lld)", (long long)P);
-    size_t smem = (size_t)GROUPS_PER_CTA * 2 * PAIRS * row_words * sizeof(uint32_t);
+    int lut_rows = dp_lut_rows(max_len);
+    size_t smem = (size_t)GROUPS_PER_CTA * lut_rows * sizeof(uint2);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(overlap_dp_kernel<G, T, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(OVL_E_CUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));
     }
-    overlap_dp_kernel<G, T, PK><<<(unsigned)grid, kDpThreads, smem, st>>>(packed, row_words, len, pair_a, pair_b, P, prm, score, end);
+    overlap_dp_kernel<G, T, PK><<<(unsigned)grid, kDpThreads, smem, st>>>(packed, row_words, len, pair_a, pair_b, P, lut_rows, prm, score, end);
     LAUNCH_CHECK("overlap_dp_kernel");
     return OVL_OK;
 }
 
 #define DP_CASE(G_, T_, PK_) \
-    if (plan.G == G_ && plan.T == T_) return launch_dp<G_, T_, PK_>(packed, row_words, len, pair_a, pair_b, P, plan.prm, score, end, st);
+    if (plan.G == G_ && plan.T == T_) return launch_dp<G_, T_, PK_>(packed, row_words, len, pair_a, pair_b, P, max_len, plan.prm, score, end, st);
 #define DP_CASES_T(T_, PK_) \
     DP_CASE(1, T_, PK_) DP_CASE(2, T_, PK_) DP_CASE(4, T_, PK_) DP_CASE(8, T_, PK_) DP_CASE(16, T_, PK_) DP_CASE(32, T_, PK_)
 
