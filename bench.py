@@ -52,52 +52,76 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML from a
+    thread every 5 ms (nvidia-smi -lms cannot sample a region of a few tens of ms)."""
 
     def __init__(self, gpu_index):
-        self.rows = []
-        self.proc = None
+        self.rows = []          # (t, sm_mhz, max_mhz, power_w, reasons bitmask)
         self.gpu_index = gpu_index
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.err = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x for x in vis.split(",") if x.strip() != ""]
+            try:
+                return int(ids[self.gpu_index])
+            except Exception:
+                return self.gpu_index
+        return self.gpu_index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu_index), "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as exc:          # noqa: BLE001
+            self.err = f"NVML unavailable: {exc}"
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 9:
-                continue
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
             try:
-                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                except Exception:
+                    pw = None
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.time(), sm, self.max_mhz, pw, rs))
+            except Exception as exc:      # noqa: BLE001
+                self.err = str(exc)
+                return
+            time.sleep(0.005)
+
+    def stop(self, t_begin=None, t_end=None):
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no samples"]}
+        rows = [r for r in self.rows if (t_begin is None or r[0] >= t_begin) and (t_end is None or r[0] <= t_end)]
+        if len(rows) < 3:
+            rows = self.rows
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted(n for n, bit in names.items() if any(r[4] & bit for r in rows))
+        power = [r[3] for r in rows if r[3] is not None]
+        return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": rows[0][2],
+                "power_w_max": max(power) if power else None, "samples": len(rows), "reasons": reasons}
 
 
 # --------------------------------------------------------------------------------------- CPU arm
@@ -225,7 +249,7 @@ def run_ours(args):
         index = eng.kmer_index(rs, args.k) if args.k > 0 else None
         pa, pb, _ = eng.candidate_pairs(rs, index, args.k, shard)
         if record is not None:
-            record["dp0"].record()
+            record["dp0"].record()          # end of the k-mer stages (K0-K3) == start of the DP
         score, end = eng.overlap_scores(rs, pa, pb)
         if record is not None:
             record["dp1"].record()
@@ -258,13 +282,14 @@ def run_ours(args):
     del rs, pa, pb, edges, edges_all
 
     # ---- value leg: inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         device_step()
         flush.zero_()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
-    step_ms, dp_ms = [], []
+    t_begin = time.time()
+    step_ms, dp_ms, kmer_ms = [], [], []
     launches0 = eng.launches
     for _ in range(args.steps):
         flush.zero_()                                   # flush L2 between timed iterations
@@ -277,12 +302,13 @@ def run_ours(args):
         barrier()
         step_ms.append(e0.elapsed_time(e1))
         dp_ms.append(rec["dp0"].elapsed_time(rec["dp1"]))
+        kmer_ms.append(e0.elapsed_time(rec["dp0"]))
     launches = eng.launches - launches0
-    clocks = sampler.stop()
-    t = torch.tensor([sum(step_ms), sum(dp_ms)], dtype=torch.float64, device=dev)
+    clocks = sampler.stop(t_begin, time.time())
+    t = torch.tensor([sum(step_ms), sum(dp_ms), sum(kmer_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)        # max over ranks
-    total_ms, dp_total_ms = (float(x) for x in t.cpu().tolist())
+    total_ms, dp_total_ms, kmer_total_ms = (float(x) for x in t.cpu().tolist())
     ms_per_step = total_ms / args.steps
     value = cells / (ms_per_step * 1e-3) / 1e9
 
@@ -327,14 +353,32 @@ def run_ours(args):
         dp_ms_avg = dp_total_ms / args.steps
         cells_per_launch = cells / world                       # each rank launches the DP on its slice
         achieved = cells_per_launch * OPS_PER_CELL / (dp_ms_avg * 1e-3) / 1e12
-        peak = probe["iadd3"] / 1e3
+        # Peak of the integer pipes for this op class, measured in this run: the ALU pipe issues
+        # VIADDMNMX.U16x2 at `viaddmnmx_s16x2` G lane-instr/s, each doing 4 algorithmic 16-bit ops
+        # (2 halves x (add + min)); the FMA pipe co-issues IMAD at `imad` G lane-instr/s, each a
+        # packed add = 2 algorithmic ops.
+        peak = (probe["viaddmnmx_s16x2"] * 4 + probe["imad"] * 2) / 1e3 if plan["mode"] == "packed16" \
+            else (probe["viaddmnmx_s16x2"] * 2 + probe["imad"]) / 1e3
+        peak_int32 = probe["lop3"] / 1e3            # int32 lanes x clock (one op per lane-instr)
         pk, pk_kind = peaks()
-        roofline = {"bound": "int32-alu", "kernel": f"overlap_dp_kernel<{plan['lanes']},{plan['cols']},{plan['mode']}>",
+        roofline = {"bound": "int-pipe (ALU DPX + FMA IMAD)",
+                    "kernel": f"overlap_dp_kernel<{plan['lanes']},{plan['cols']},{plan['mode']}>",
                     "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak if peak else None,
                     "traffic": None, "ops_per_cell": OPS_PER_CELL,
                     "dp_gcups": cells_per_launch / (dp_ms_avg * 1e-3) / 1e9, "dp_ms": dp_ms_avg,
-                    "peak_source": "ovl_int_peak_probe kind 0 (IADD3 lane-ops/s), measured in this run",
+                    "peak_source": "ovl_int_peak_probe in this run: 4 ops x VIADDMNMX.16x2 rate + 2 ops x IMAD rate",
+                    "frac_vs_int32_lanes": achieved / peak_int32, "peak_int32_lanes": peak_int32,
                     "int_probe_gops": probe, "hbm_peak_gbs": pk.get("hbm_gbs"), "hbm_peak_source": pk_kind}
+        # ---- the k-mer stages (K0-K3) and edge expansion (K6): HBM-bound; algorithmic bytes per SURVEY 8(d)
+        passes = (2 * args.k + 7) // 8
+        kb = (total_bases + total_bases / 4) + 48 * U + 12 * (1 + 2 * passes) * U + 16 * U + 12 * pairs
+        eb = 16 * pairs + 16 * n_edges
+        k_ms = kmer_total_ms / args.steps
+        x_ms = ms_per_step - (kmer_total_ms + dp_total_ms) / args.steps
+        kmer = {"algorithmic_bytes": {"k0_k3": int(kb), "k6": int(eb)},
+                "k0_k3_gbs": kb / (k_ms * 1e-3) / 1e9, "k6_gbs": eb / (max(x_ms, 1e-6) * 1e-3) / 1e9,
+                "hbm_peak_gbs": pk.get("hbm_gbs"), "k0_k3_frac": kb / (k_ms * 1e-3) / 1e9 / pk.get("hbm_gbs"),
+                "note": "includes two host round trips for the output sizes; at this size launch-latency bound"}
         # ---- CPU baseline on this box's host cores (bounded sample)
         cpu = None
         if not args.no_cpu_baseline:
@@ -351,7 +395,10 @@ def run_ours(args):
                            "cells": cells, "edge_checksum": checksum, "sharding": f"pair-range x{world}",
                            "l2": "flushed between timed iterations (256 MiB memset)",
                            "scoring": "match 10, mismatch -1, indel -2^31 (reference defaults)"},
-                "pairs_per_s": pairs / (ms_per_step * 1e-3),
+                "pairs_per_s": pairs / (kmer_total_ms / args.steps * 1e-3),
+                "stage_ms": {"kmer_index_join": kmer_total_ms / args.steps, "overlap_dp": dp_total_ms / args.steps,
+                             "expand_gather": ms_per_step - (kmer_total_ms + dp_total_ms) / args.steps},
+                "kmer_stages": kmer,
                 "e2e": {"value": cells / (e2e_per_step * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_per_step,
                         "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}

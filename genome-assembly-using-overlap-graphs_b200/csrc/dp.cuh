@@ -58,7 +58,7 @@ constexpr int kDpThreads = 128;
 #define OVL_DP_F2_NUM 1        // columns using form 2 (FMA-heavy): NUM out of every DEN
 #endif
 #ifndef OVL_DP_F2_DEN
-#define OVL_DP_F2_DEN 2
+#define OVL_DP_F2_DEN 3
 #endif
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {

@@ -236,7 +236,7 @@ struct DpPlan {
     DpParams prm;
 };
 
-const int kPackedT[] = {25, 32, 38};
+const int kPackedT[] = {19, 25, 32, 38};
 const int kScalarT[] = {32};
 const int kLanes[] = {1, 2, 4, 8, 16, 32};
 
@@ -284,7 +284,7 @@ bool dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_t indel, in
     for (int m = 1; m <= 2; ++m) {
         if (mode != 0 && mode != m) continue;
         const int* Ts = m == 1 ? kPackedT : kScalarT;
-        int nT = m == 1 ? 3 : 1;
+        int nT = m == 1 ? 4 : 1;
         int64_t best = -1;
         for (int gi = 0; gi < 6; ++gi) {
             for (int ti = 0; ti < nT; ++ti) {
@@ -356,7 +356,7 @@ int ovl_overlap_dp(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, cons
                     (long long)match, (long long)mismatch, (long long)indel, max_len, mode, group_lanes, cols_per_lane);
     cudaStream_t st = (cudaStream_t)stream;
     if (plan.mode == 1) {
-        DP_CASES_T(25, true) DP_CASES_T(32, true) DP_CASES_T(38, true)
+        DP_CASES_T(19, true) DP_CASES_T(25, true) DP_CASES_T(32, true) DP_CASES_T(38, true)
     } else {
         DP_CASES_T(32, false)
     }

@@ -46,7 +46,7 @@ def main():
     ref = None
     for mode in [int(x) for x in args.modes.split(",")]:
         for lanes in (1, 2, 4, 8, 16, 32):
-            for cols in ((25, 32, 38) if mode == 1 else (32,)):
+            for cols in ((19, 25, 32, 38) if mode == 1 else (32,)):
                 if lanes * cols < rs.max_len or lanes * cols > 4 * max(rs.max_len, 38):
                     continue
                 if args.only and args.only != f"{lanes}x{cols}":
