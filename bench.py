@@ -129,7 +129,7 @@ def cpu_arm(ub, uo, pair_a, pair_b, target_s=12.0, nthreads=0):
     """The oracle port of aligners.overlap_alignment (full matrices + traceback walk, like the
     reference) over a bounded sample of the workload's candidate pairs, on all host threads."""
     from oracle import overlap_oracle as orc
-    cores = orc.max_threads() if nthreads <= 0 else nthreads
+    cores = (os.cpu_count() or 1) if nthreads <= 0 else nthreads     # torchrun exports OMP_NUM_THREADS=1: be explicit
     lens = (uo[1:] - uo[:-1]).astype(np.int64)
     rng = np.random.Generator(np.random.PCG64(99))
     P = len(pair_a)
@@ -150,9 +150,11 @@ def cpu_arm(ub, uo, pair_a, pair_b, target_s=12.0, nthreads=0):
             "seconds": dt, "pairs": n, "cells": cells}
 
 
-def host_candidate_pairs(ub, uo, k):
+def host_candidate_pairs(ub, uo, k, max_pairs=None):
     """Candidate list on the host for the CPU arm (NumPy k-mer join, same rule as
-    overlapGraphs.py:30-52).  Not timed."""
+    overlapGraphs.py:30-52).  Not timed.  With max_pairs, only a random subset of the source
+    reads is expanded (all their candidates), so memory stays bounded on the big workloads.
+    Returns (pair_a, pair_b, total_pairs)."""
     lens = (uo[1:] - uo[:-1]).astype(np.int64)
     U = len(lens)
     code = np.zeros(256, np.uint64)
@@ -169,12 +171,20 @@ def host_candidate_pairs(ub, uo, k):
     lo = np.searchsorted(spk, sk, "left")
     hi = np.searchsorted(spk, sk, "right")
     cnt = hi - lo
-    a = np.repeat(valid, cnt)
-    starts = np.repeat(lo, cnt)
-    within = np.arange(int(cnt.sum())) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+    total = int(cnt.sum() - (pk == sk).sum())            # a read sits in its own bucket iff prefix == suffix key
+    src = np.arange(len(valid))
+    if max_pairs is not None and int(cnt.sum()) > max_pairs:
+        rng = np.random.Generator(np.random.PCG64(7))
+        perm = rng.permutation(len(valid))
+        take = np.searchsorted(np.cumsum(cnt[perm]), max_pairs) + 1
+        src = np.sort(perm[:take])
+    c = cnt[src]
+    a = np.repeat(valid[src], c)
+    starts = np.repeat(lo[src], c)
+    within = np.arange(int(c.sum())) - np.repeat(np.cumsum(c) - c, c)
     b = valid[order][starts + within]
     keep = a != b
-    return a[keep].astype(np.int32), b[keep].astype(np.int32)
+    return a[keep].astype(np.int32), b[keep].astype(np.int32), total
 
 
 def run_reference(args):
@@ -182,7 +192,7 @@ def run_reference(args):
     if rank != 0:
         return
     ub, uo, counts, n_reads = load_workload(args.workload, args.seed)
-    pa, pb = host_candidate_pairs(ub, uo, args.k)
+    pa, pb, total_pairs = host_candidate_pairs(ub, uo, args.k, max_pairs=8_000_000)
     per_step = max(2.0, min(20.0, 60.0 / max(args.steps + args.warmup, 1)))
     vals, secs = [], []
     last = None
@@ -195,7 +205,7 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": args.workload, "k": args.k, "seed": args.seed, "unique_reads": int(len(counts)),
-                       "candidate_pairs": int(len(pa))},
+                       "candidate_pairs": int(total_pairs)},
             "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -314,12 +324,11 @@ def run_ours(args):
 
     # ---- e2e leg: host buffers in, host edge rows out, every step
     def e2e_step():
-        out = eng.overlap_edges(h_bases, h_off, h_counts if has_dups else None, args.k, shard)
-        if world > 1:
-            g = par.gather_edges(torch.from_numpy(out).to(dev), 0)
-            if g is not None:
-                out = g.cpu().numpy()
-        return out
+        if world == 1:
+            return eng.overlap_edges(h_bases, h_off, h_counts if has_dups else None, args.k, shard, reuse_host_buffer=True)
+        dev_edges = eng.overlap_edges(h_bases, h_off, h_counts if has_dups else None, args.k, shard, to_host=False)
+        g = par.gather_edges(dev_edges, 0)
+        return eng.to_pinned_host(g) if g is not None else np.zeros((0, 4), np.int32)
 
     for _ in range(min(args.warmup, 2)):
         e2e_step()
@@ -381,9 +390,13 @@ def run_ours(args):
                 "note": "includes two host round trips for the output sizes; at this size launch-latency bound"}
         # ---- CPU baseline on this box's host cores (bounded sample)
         cpu = None
-        if not args.no_cpu_baseline:
-            pa_h, pb_h = host_candidate_pairs(ub, uo, args.k)
-            assert len(pa_h) == pairs, (len(pa_h), pairs)
+        if not args.no_cpu_baseline and world == 1:
+            # a bounded random sample of the SAME candidate list the GPU just processed
+            rs_, pa_, pb_, _, _ = device_step()
+            n_s = min(pairs, 4_000_000)
+            idx = torch.randperm(pairs, device=dev)[:n_s] if pairs > n_s else torch.arange(pairs, device=dev)
+            pa_h, pb_h = pa_[idx].cpu().numpy(), pb_[idx].cpu().numpy()
+            del rs_, pa_, pb_, idx
             cpu = cpu_arm(ub, uo, pa_h, pb_h, target_s=args.cpu_seconds)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -52,7 +52,7 @@ _SIGS = {
     "ovl_index_build": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ovl_join_workspace_bytes": (_sz, [_i64]),
     "ovl_join_count": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "ovl_join_fill": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "ovl_join_fill": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "ovl_all_pairs_fill": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "ovl_overlap_dp": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _i64, _vp, _vp,
                                       _i32, _i32, _i32, _vp]),

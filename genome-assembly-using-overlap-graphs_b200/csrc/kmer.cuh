@@ -15,45 +15,13 @@ namespace ovl {
 constexpr uint64_t kInvalidKey = ~0ull;
 
 // ------------------------------------------------------------------ K0 pack_reads
-// One thread per output word (16 bases).  The read's ASCII bytes start at an arbitrary byte
-// offset, so each thread loads the two aligned 16-byte segments that cover its 16 bytes and
-// funnel-shifts them into place (neighbouring threads share segments through L1, DRAM sees
-// each byte once).  Requires: ascii base 16-byte aligned and >= 32 bytes of slack after the
-// last read.
-__global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t* __restrict__ ascii,
-                                                         const int64_t* __restrict__ offsets,
-                                                         int64_t U, int row_words,
-                                                         uint32_t* __restrict__ packed,
-                                                         int32_t* __restrict__ len_out,
-                                                         int32_t* __restrict__ bad_count) {
-    int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t total = U * row_words;
-    if (slot >= total) return;
-    int64_t u = slot / row_words;
-    int w = (int)(slot - u * row_words);
-    int64_t o0 = offsets[u];
-    int len = (int)(offsets[u + 1] - o0);
-    if (w == 0) len_out[u] = len;
-    int nvalid = len - 16 * w;                       // bases this word holds
-    if (nvalid <= 0) { packed[slot] = 0u; return; }
-    if (nvalid > 16) nvalid = 16;
-
-    int64_t addr = o0 + 16 * (int64_t)w;             // byte index of the first base
-    const uint4* seg = reinterpret_cast<const uint4*>(ascii + (addr & ~(int64_t)15));
-    uint4 q0 = __ldg(seg), q1 = __ldg(seg + 1);
-    unsigned sh = (unsigned)(addr & 15);
-    uint32_t x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-    // shift right by sh bytes: 8, 4, then 0..3 bytes
-    uint32_t y[6], z[5], r[4];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) y[i] = (sh & 8) ? x[i + 2] : x[i];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) z[i] = (sh & 4) ? y[i + 1] : y[i];
-    unsigned bs = (sh & 3) * 8;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) r[i] = __funnelshift_r(z[i], z[i + 1], bs);
-
-    uint32_t out = 0, bad = 0;
+// One thread per 4 output words (64 bases, one 16-byte store).  The read's ASCII bytes start at
+// an arbitrary byte offset, so the thread loads the five aligned 16-byte segments that cover
+// its 64 bytes (all issued up front) and funnel-shifts them into place; the segment shared with
+// the neighbouring thread comes from L1, DRAM sees each byte once.  Requires: ascii base 16-byte
+// aligned and >= 32 bytes of slack after the last read.
+__device__ __forceinline__ uint32_t pack16(const uint32_t r[4], int nvalid, uint32_t& bad) {
+    uint32_t out = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int nv = nvalid - 4 * i;                     // valid bytes in this word
@@ -68,8 +36,53 @@ __global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t* __restri
         uint32_t pk = (t * 0x01041040u) >> 24;
         out |= pk << (8 * i);
     }
-    packed[slot] = out;
-    if (bad) atomicAdd(bad_count, 1);
+    return out;
+}
+
+__global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t* __restrict__ ascii,
+                                                         const int64_t* __restrict__ offsets,
+                                                         int64_t U, int row_words,
+                                                         uint32_t* __restrict__ packed,
+                                                         int32_t* __restrict__ len_out,
+                                                         int32_t* __restrict__ bad_count) {
+    const int quads = row_words >> 2;                // 16-byte groups per row
+    int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= U * quads) return;
+    int64_t u = slot / quads;
+    int q = (int)(slot - u * quads);
+    int64_t o0 = offsets[u];
+    int len = (int)(offsets[u + 1] - o0);
+    if (q == 0) len_out[u] = len;
+    int nvalid = len - 64 * q;                       // bases this thread holds
+    uint4 outv = make_uint4(0u, 0u, 0u, 0u);
+    if (nvalid > 0) {
+        int64_t addr = o0 + 64 * (int64_t)q;         // byte index of the first base
+        const uint4* seg = reinterpret_cast<const uint4*>(ascii + (addr & ~(int64_t)15));
+        int nseg = min(5, (int)(((addr & 15) + min(nvalid, 64) + 15) >> 4));
+        uint4 sv[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) sv[i] = i < nseg ? __ldg(seg + i) : make_uint4(0u, 0u, 0u, 0u);
+        uint32_t x[20];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { x[4 * i] = sv[i].x; x[4 * i + 1] = sv[i].y; x[4 * i + 2] = sv[i].z; x[4 * i + 3] = sv[i].w; }
+        unsigned sh = (unsigned)(addr & 15);
+        // shift right by sh bytes: 8, 4, then 0..3 bytes
+        uint32_t y[18], z[17], r[16];
+#pragma unroll
+        for (int i = 0; i < 18; ++i) y[i] = (sh & 8) ? x[i + 2] : x[i];
+#pragma unroll
+        for (int i = 0; i < 17; ++i) z[i] = (sh & 4) ? y[i + 1] : y[i];
+        unsigned bs = (sh & 3) * 8;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __funnelshift_r(z[i], z[i + 1], bs);
+        uint32_t bad = 0;
+        outv.x = pack16(r, nvalid, bad);
+        outv.y = pack16(r + 4, nvalid - 16, bad);
+        outv.z = pack16(r + 8, nvalid - 32, bad);
+        outv.w = pack16(r + 12, nvalid - 48, bad);
+        if (bad) atomicAdd(bad_count, 1);
+    }
+    reinterpret_cast<uint4*>(packed)[slot] = outv;
 }
 
 // ------------------------------------------------------------------ K1 kmer_keys
@@ -127,13 +140,20 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint64_t
     int64_t n = FIRST ? n_static : *n_ptr;
     int64_t base = warp * kSortChunk;
     if (warp < W) {
-        for (int it = 0; it < kSortChunk / 32; ++it) {
+        // all loads of the chunk are issued before the first atomic (16 independent requests per lane)
+        constexpr int R = kSortChunk / 32;
+        uint64_t key[R];
+        bool live[R];
+#pragma unroll
+        for (int it = 0; it < R; ++it) {
             int64_t idx = base + it * 32 + lane_id();
-            if (idx < n) {
-                uint64_t key = keys[idx];
-                if (!FIRST || len[idx] >= k) atomicAdd(&cnt[wib][(int)((key >> shift) & 255u)], 1);
-            }
+            live[it] = idx < n;
+            key[it] = live[it] ? keys[idx] : 0;
+            if (FIRST && live[it]) live[it] = len[idx] >= k;
         }
+#pragma unroll
+        for (int it = 0; it < R; ++it)
+            if (live[it]) atomicAdd(&cnt[wib][(int)((key[it] >> shift) & 255u)], 1);
         __syncwarp();
         for (int d = lane_id(); d < 256; d += 32) hist[(int64_t)d * W + warp] = cnt[wib][d];
     }
@@ -157,21 +177,29 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
     __syncwarp();
     int64_t n = FIRST ? n_static : *n_ptr;
     int64_t base = warp * kSortChunk;
-    for (int it = 0; it < kSortChunk / 32; ++it) {
+    constexpr int R = kSortChunk / 32;
+    uint64_t key[R];
+    uint32_t uid[R];
+    bool live[R];
+#pragma unroll
+    for (int it = 0; it < R; ++it) {                 // issue every load of the chunk up front
         int64_t idx = base + it * 32 + lane_id();
-        bool live = idx < n;
-        uint64_t key = live ? keys_in[idx] : 0;
-        if (FIRST && live && len[idx] < k) live = false;
-        uint32_t uid = FIRST ? (uint32_t)idx : (live ? uid_in[idx] : 0u);
-        unsigned d = live ? (unsigned)((key >> shift) & 255u) : 256u + lane_id();  // dead lanes match nobody
+        live[it] = idx < n;
+        key[it] = live[it] ? keys_in[idx] : 0;
+        uid[it] = FIRST ? (uint32_t)idx : (live[it] ? uid_in[idx] : 0u);
+        if (FIRST && live[it]) live[it] = len[idx] >= k;
+    }
+#pragma unroll
+    for (int it = 0; it < R; ++it) {
+        unsigned d = live[it] ? (unsigned)((key[it] >> shift) & 255u) : 256u + lane_id();  // dead lanes match nobody
         unsigned peers = __match_any_sync(kFull, d);
         int rank = __popc(peers & lanemask_lt());
         int pos = 0;
-        if (live) pos = off[wib][d] + rank;
+        if (live[it]) pos = off[wib][d] + rank;
         __syncwarp();
-        if (live && rank == 0) off[wib][d] += __popc(peers);
+        if (live[it] && rank == 0) off[wib][d] += __popc(peers);
         __syncwarp();
-        if (live) { keys_out[pos] = key; uid_out[pos] = uid; }
+        if (live[it]) { keys_out[pos] = key[it]; uid_out[pos] = uid[it]; }
     }
     if (FIRST && n_out != nullptr && warp == W - 1 && lane_id() == 0) {
         // after the last warp's chunk, digit 255's running offset is the number of survivors
@@ -252,6 +280,30 @@ __global__ void __launch_bounds__(kFillThreads) join_fill_kernel(const int64_t* 
     }
 }
 
+// Same output, one warp per source read: used when buckets are large (mean >= 32 candidates per
+// read), where every lane streams consecutive candidates -- no search, fully coalesced stores.
+__global__ void __launch_bounds__(256) join_fill_warp_kernel(const int64_t* __restrict__ pair_off, int64_t nA, int64_t a_begin,
+                                                             const int32_t* __restrict__ lo, const int32_t* __restrict__ self_rank,
+                                                             const uint32_t* __restrict__ sorted_uid,
+                                                             int64_t p_begin, int64_t p_count,
+                                                             int32_t* __restrict__ pair_a, int32_t* __restrict__ pair_b) {
+    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nA) return;
+    int64_t first = pair_off[i], last = pair_off[i + 1];
+    int64_t from = max(first, p_begin), to = min(last, p_begin + p_count);
+    if (from >= to) return;
+    int32_t sr = self_rank[i];
+    int64_t base = lo[i];
+    int32_t a = (int32_t)(a_begin + i);
+    for (int64_t p = from + lane_id(); p < to; p += 32) {
+        int32_t r = (int32_t)(p - first);
+        if (sr >= 0 && r >= sr) r += 1;
+        int64_t q = p - p_begin;
+        pair_a[q] = a;
+        pair_b[q] = (int32_t)sorted_uid[base + r];
+    }
+}
+
 // k == 0: every ordered pair a != b (overlapGraphs.py:49), a in [a_begin, a_end).
 __global__ void __launch_bounds__(256) all_pairs_fill_kernel(int64_t U, int64_t a_begin, int64_t p_begin, int64_t p_count,
                                                              int32_t* __restrict__ pair_a, int32_t* __restrict__ pair_b) {
@@ -269,14 +321,6 @@ __global__ void __launch_bounds__(256) all_pairs_fill_kernel(int64_t U, int64_t 
 // ------------------------------------------------------------------ K6 expand edges
 // Edge row = (node_a, node_b, weight, end_position), node id = node_off[uid] + copy, emitted
 // in the reference's insertion order: pair order, then copy_a, then copy_b (overlapGraphs.py:55-60).
-__global__ void __launch_bounds__(256) expand_count_kernel(const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b,
-                                                           const int32_t* __restrict__ copies, int64_t P,
-                                                           int64_t* __restrict__ cnt) {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
-    cnt[p] = (int64_t)copies[pair_a[p]] * (int64_t)copies[pair_b[p]];
-}
-
 __global__ void __launch_bounds__(kFillThreads) expand_fill_kernel(const int64_t* __restrict__ edge_off,  // [P+1]
                                                                    int64_t P,
                                                                    const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b,

@@ -99,7 +99,7 @@ int ovl_pack_reads(ovl_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, i
     if (row_words < 4 || (row_words & 3)) return fail(OVL_E_ARG, "ovl_pack_reads: row_words must be a positive multiple of 4");
     if (((uintptr_t)ascii & 15) || ((uintptr_t)packed & 15)) return fail(OVL_E_ARG, "ovl_pack_reads: ascii and packed must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    pack_reads_kernel<<<grid_for(U * row_words, 256), 256, 0, st>>>(ascii, offsets, U, row_words, packed, len, bad_count);
+    pack_reads_kernel<<<grid_for(U * (row_words / 4), 256), 256, 0, st>>>(ascii, offsets, U, row_words, packed, len, bad_count);
     LAUNCH_CHECK("pack_reads_kernel");
     return OVL_OK;
 }
@@ -159,7 +159,7 @@ int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len
             radix_hist_kernel<false><<<grid, kSortThreads, 0, st>>>(src_key, len, k, n_indexed, 0, shift, W, hist);
         }
         LAUNCH_CHECK("radix_hist_kernel");
-        CUDA_TRY((exclusive_scan<int32_t, int32_t>(hist, hist, 256 * W, sums, st)));
+        CUDA_TRY((exclusive_scan<LoadArray<int32_t>, int32_t>(LoadArray<int32_t>{hist}, hist, 256 * W, sums, st)));
         if (p == 0) {
             radix_scatter_kernel<true><<<grid, kSortThreads, 0, st>>>(src_key, nullptr, len, k, nullptr, U, shift, W, hist,
                                                                        kbuf[dst], ubuf[dst], n_indexed);
@@ -200,18 +200,26 @@ int ovl_join_count(ovl_ctx* ctx, const uint64_t* suffix_key, const uint64_t* pre
                                                               n_indexed, bucket_lo, self_rank, cnt);
         LAUNCH_CHECK("join_count_kernel");
     }
-    CUDA_TRY((exclusive_scan<int64_t, int64_t>(cnt, pair_off, nA, sums, st)));
+    CUDA_TRY((exclusive_scan<LoadArray<int64_t>, int64_t>(LoadArray<int64_t>{cnt}, pair_off, nA, sums, st)));
     return OVL_OK;
 }
 
 int ovl_join_fill(ovl_ctx* ctx, const int64_t* pair_off, int64_t a_begin, int64_t a_end, const int32_t* bucket_lo,
-                  const int32_t* self_rank, const uint32_t* sorted_uid, int64_t p_begin, int64_t p_count, int32_t* pair_a,
-                  int32_t* pair_b, void* stream) {
+                  const int32_t* self_rank, const uint32_t* sorted_uid, int64_t p_begin, int64_t p_count, int64_t total_hint,
+                  int32_t* pair_a, int32_t* pair_b, void* stream) {
     if (!ctx || !pair_off || !bucket_lo || !self_rank || !sorted_uid || !pair_a || !pair_b) return fail(OVL_E_ARG, "ovl_join_fill: null argument");
     if (p_count <= 0) return OVL_OK;
-    join_fill_kernel<<<grid_for(p_count, kFillTile), kFillThreads, 0, (cudaStream_t)stream>>>(
-        pair_off, a_end - a_begin, a_begin, bucket_lo, self_rank, sorted_uid, p_begin, p_count, pair_a, pair_b);
-    LAUNCH_CHECK("join_fill_kernel");
+    int64_t nA = a_end - a_begin;
+    if (total_hint >= 32 * nA) {
+        // large buckets: one warp per source read streams its candidates
+        join_fill_warp_kernel<<<grid_for(nA * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+            pair_off, nA, a_begin, bucket_lo, self_rank, sorted_uid, p_begin, p_count, pair_a, pair_b);
+        LAUNCH_CHECK("join_fill_warp_kernel");
+    } else {
+        join_fill_kernel<<<grid_for(p_count, kFillTile), kFillThreads, 0, (cudaStream_t)stream>>>(
+            pair_off, nA, a_begin, bucket_lo, self_rank, sorted_uid, p_begin, p_count, pair_a, pair_b);
+        LAUNCH_CHECK("join_fill_kernel");
+    }
     return OVL_OK;
 }
 
@@ -366,7 +374,7 @@ int ovl_overlap_dp(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, cons
 // ---------------------------------------------------------------- K6
 size_t ovl_expand_workspace_bytes(int64_t P) {
     if (P < 1) P = 1;
-    return align256((size_t)P * sizeof(int64_t)) + align256(scan_workspace_bytes(P, sizeof(int64_t))) + 256;
+    return align256(scan_workspace_bytes(P, sizeof(int64_t))) + 256;
 }
 
 int ovl_expand_count(ovl_ctx* ctx, const int32_t* pair_a, const int32_t* pair_b, const int32_t* copies, int64_t P,
@@ -374,14 +382,9 @@ int ovl_expand_count(ovl_ctx* ctx, const int32_t* pair_a, const int32_t* pair_b,
     if (!ctx || !edge_off || !workspace || (P > 0 && (!pair_a || !pair_b || !copies))) return fail(OVL_E_ARG, "ovl_expand_count: null argument");
     if (workspace_bytes < ovl_expand_workspace_bytes(P)) return fail(OVL_E_ARG, "ovl_expand_count: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    int64_t* cnt = (int64_t*)ws;
-    void* sums = ws + align256((size_t)std::max<int64_t>(P, 1) * sizeof(int64_t));
-    if (P > 0) {
-        expand_count_kernel<<<grid_for(P, 256), 256, 0, st>>>(pair_a, pair_b, copies, P, cnt);
-        LAUNCH_CHECK("expand_count_kernel");
-    }
-    CUDA_TRY((exclusive_scan<int64_t, int64_t>(cnt, edge_off, P, sums, st)));
+    void* sums = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    // the per-pair edge count copies[a]*copies[b] is computed inside the scan: no count array
+    CUDA_TRY((exclusive_scan<CopyProduct, int64_t>(CopyProduct{pair_a, pair_b, copies}, edge_off, P, sums, st)));
     return OVL_OK;
 }
 

@@ -184,7 +184,7 @@ class OverlapEngine:
         pair_b = self._empty(P, torch.int32)
         if P:
             nat.check(nat.lib.ovl_join_fill(self._ctx, _ptr(pair_off), 0, U, _ptr(lo), _ptr(self_rank),
-                                            _ptr(index.sorted_uid), p_begin, P, _ptr(pair_a), _ptr(pair_b), st))
+                                            _ptr(index.sorted_uid), p_begin, P, total, _ptr(pair_a), _ptr(pair_b), st))
             self.launches += 1
         return pair_a[:P], pair_b[:P], p_begin
 
@@ -285,9 +285,20 @@ class OverlapEngine:
             stats["pair_a"], stats["pair_b"] = pair_a, pair_b
         return edges
 
+    def to_pinned_host(self, edges: torch.Tensor) -> np.ndarray:
+        """Device edge rows -> NumPy view of the engine's reusable pinned buffer (valid until the
+        next call)."""
+        E = int(edges.shape[0])
+        if self._pinned_out is None or self._pinned_out.shape[0] < max(E, 1):
+            self._pinned_out = torch.empty((max(E, 1) * 5 // 4 + 16, 4), dtype=torch.int32).pin_memory()
+        host = self._pinned_out[:E]
+        host.copy_(edges, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host.numpy()
+
     def overlap_edges(self, bases, offsets, counts=None, k: int = 5, shard: Tuple[int, int] = (0, 1),
                       match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT,
-                      stats: Optional[dict] = None) -> np.ndarray:
+                      stats: Optional[dict] = None, to_host: bool = True, reuse_host_buffer: bool = False):
         """HOST buffers in, HOST edge rows out: unique reads (ASCII bytes + offsets) and their
         multiplicities -> int32[E, 4] (node_a, node_b, weight, end_position) in the reference's
         insertion order.  This is the call the drop-in graph builder makes."""
@@ -303,15 +314,12 @@ class OverlapEngine:
                 copies = self._to_device(counts_np, torch.int32)
                 node_off = self._to_device(no, torch.int64)
         edges = self.overlap_edges_device(rs, k, copies, node_off, shard, match_score, mismatch, indel, stats)
-        E = int(edges.shape[0])
-        if self._pinned_out is None or self._pinned_out.shape[0] < max(E, 1):
-            self._pinned_out = torch.empty((max(E, 1) * 5 // 4 + 16, 4), dtype=torch.int32).pin_memory()
-        host = self._pinned_out[:E]
-        host.copy_(edges, non_blocking=True)
-        self.check_alphabet(rs)            # .item(): also completes the async copy above
-        torch.cuda.current_stream(self.device).synchronize()
-        # a view of the engine's pinned buffer: valid until the next overlap_edges() call
-        return host.numpy()
+        self.check_alphabet(rs)
+        if not to_host:
+            return edges
+        host = self.to_pinned_host(edges)
+        # reuse_host_buffer: hand out the engine's pinned buffer itself (valid until the next call)
+        return host if reuse_host_buffer else host.copy()
 
 
 _ENGINES = {}

@@ -41,7 +41,7 @@ def _flatten(uniq):
     return bases, offsets
 
 
-def overlap_edge_rows(reads, k=5):
+def overlap_edge_rows(reads, k=5, _reuse_host_buffer=False):
     """The device part of the builder: returns (read_copies, uniq, counts, edges) where edges
     is int32[E, 4] = (node_a, node_b, weight, end_position) in insertion order and node ids
     number the copies in (uid, copy) order."""
@@ -58,13 +58,13 @@ def overlap_edge_rows(reads, k=5):
         return read_copies, uniq, counts, np.zeros((0, 4), np.int32)
     bases, offsets = _flatten(uniq)
     eng = _engine.get_engine()
-    edges = eng.overlap_edges(bases, offsets, counts, k)
+    edges = eng.overlap_edges(bases, offsets, counts, k, reuse_host_buffer=_reuse_host_buffer)
     return read_copies, uniq, counts, edges
 
 
 def construct_overlap_graph_nx_k(reads, k=5):
     """Construct the overlap graph -- see overlapGraphs.py:5-16 for the contract."""
-    read_copies, uniq, counts, edges = overlap_edge_rows(reads, k)
+    read_copies, uniq, counts, edges = overlap_edge_rows(reads, k, _reuse_host_buffer=True)   # consumed right below
     overlap_graph = nx.DiGraph()
     names = [f"{read}_{c}" for read, cnt in zip(uniq, counts.tolist()) for c in range(cnt)]   # :25-28
     overlap_graph.add_nodes_from(names)

@@ -77,7 +77,9 @@ int ovl_index_build(ovl_ctx *ctx, const uint64_t *prefix_key, const int32_t *len
  * ovl_join_count writes, per a, the bucket start, a's own rank inside the bucket (-1 if it
  * is not in it) and the exclusive scan pair_off[(a_end-a_begin)+1] of the candidate counts;
  * pair_off[last] is the number of pairs.  ovl_join_fill then writes pairs
- * [p_begin, p_begin+p_count) of that range, ordered by (a, b) ascending. */
+ * [p_begin, p_begin+p_count) of that range, ordered by (a, b) ascending.  total_hint = the
+ * total number of pairs of the range (pair_off[last], which the host has read anyway): it
+ * only selects between the thread-per-pair and the warp-per-source fill kernels. */
 size_t ovl_join_workspace_bytes(int64_t n_sources);
 int ovl_join_count(ovl_ctx *ctx, const uint64_t *suffix_key, const uint64_t *prefix_key,
                    const int32_t *len, int32_t k, int64_t a_begin, int64_t a_end, const uint64_t *sorted_key,
@@ -86,7 +88,8 @@ int ovl_join_count(ovl_ctx *ctx, const uint64_t *suffix_key, const uint64_t *pre
                    void *stream);
 int ovl_join_fill(ovl_ctx *ctx, const int64_t *pair_off, int64_t a_begin, int64_t a_end,
                   const int32_t *bucket_lo, const int32_t *self_rank, const uint32_t *sorted_uid,
-                  int64_t p_begin, int64_t p_count, int32_t *pair_a, int32_t *pair_b, void *stream);
+                  int64_t p_begin, int64_t p_count, int64_t total_hint, int32_t *pair_a,
+                  int32_t *pair_b, void *stream);
 /* k == 0 (overlapGraphs.py:49): all ordered pairs a != b, a in [a_begin, ...); pair index p
  * counts from a_begin: a = a_begin + p / (U-1). */
 int ovl_all_pairs_fill(ovl_ctx *ctx, int64_t U, int64_t a_begin, int64_t p_begin, int64_t p_count,
