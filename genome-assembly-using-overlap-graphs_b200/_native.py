@@ -56,6 +56,8 @@ _SIGS = {
     "ovl_all_pairs_fill": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "ovl_overlap_dp": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _i64, _vp, _vp,
                                       _i32, _i32, _i32, _vp]),
+    "ovl_overlap_dp_edges": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _i64, _vp, _vp, _vp,
+                                            _vp, _vp]),
     "ovl_overlap_dp_plan": (ctypes.c_int, [_i32, _i64, _i64, _i64, _i32, ctypes.POINTER(_i32 * 3)]),
     "ovl_expand_workspace_bytes": (_sz, [_i64]),
     "ovl_expand_count": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),

@@ -50,6 +50,14 @@ struct DpParams {
     uint32_t one;       // == 1, a runtime value so the adds stay IMADs
 };
 
+// optional fused edge expansion in the DP epilogue (all null: plain score/end output)
+struct DpEdgeOut {
+    int4* edges;                 // int32[E][4] rows, or null
+    const int32_t* copies;       // multiplicity per unique read, or null when every read occurs once
+    const int64_t* node_off;     // exclusive scan of copies
+    const int64_t* edge_off;     // exclusive scan of copies[a]*copies[b] over the pair list
+};
+
 constexpr int kDpThreads = 128;
 #ifndef OVL_DP_MINB
 #define OVL_DP_MINB 4          // resident CTAs per SM the register allocator must allow
@@ -57,9 +65,14 @@ constexpr int kDpThreads = 128;
 #ifndef OVL_DP_F2_NUM
 #define OVL_DP_F2_NUM 1        // columns using form 2 (FMA-heavy): NUM out of every DEN
 #endif
+#ifndef OVL_DP_KUNROLL
+#define OVL_DP_KUNROLL 1       // unroll factor of the row loop
+#endif
 #ifndef OVL_DP_F2_DEN
 #define OVL_DP_F2_DEN 3
 #endif
+
+constexpr int kDpKUnroll = OVL_DP_KUNROLL;
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t d;
@@ -91,7 +104,7 @@ template <int G, int T, bool PK>
 __global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(
     const uint32_t* __restrict__ packed, int row_words, const int32_t* __restrict__ len,
     const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b, int64_t P, int lut_rows,
-    DpParams prm, int32_t* __restrict__ score_out, int32_t* __restrict__ end_out) {
+    DpParams prm, int32_t* __restrict__ score_out, int32_t* __restrict__ end_out, DpEdgeOut eo) {
     constexpr int PAIRS = PK ? 2 : 1;
     constexpr int GROUPS_PER_WARP = 32 / G;
     constexpr int GROUPS_PER_CTA = (kDpThreads / 32) * GROUPS_PER_WARP;
@@ -161,11 +174,17 @@ __global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(
         bestj[h] = 0;
     }
 
+    // the shorter pair of the couple (if any), folded inside the loop
+    const int hshort = (PK && n[PAIRS - 1] < n[0]) ? PAIRS - 1 : 0;
+    const int nshort = n[hshort], mshort = m[hshort];
+    int bests = bestv[hshort], bestjs = 0;
+
     uint32_t out = beta2;        // my last column of the row just finished (goes to lane r+1)
     uint32_t diag_in = beta2;    // C[i-1][rT-1] for the row about to be computed
     uint32_t col0 = beta2;       // lane 0: C[i][0] = beta + i*maxs
     const int steps = __reduce_max_sync(kFull, nmax) + G - 1;      // warp-uniform trip count
 
+#pragma unroll kDpKUnroll
     for (int k = 0; k < steps; ++k) {
         const int i = k - r;                               // 0-based row of s handled this step
         uint32_t recv = __shfl_up_sync(kFull, out, 1, G);
@@ -200,18 +219,31 @@ __global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(
             }
             out = left;
             diag_in = recv;
-            // last row of a pair reached: fold my columns into its running (first) minimum
+            // a pair shorter than its partner reaches its last row inside the loop: fold my columns
+            // into its running (first) minimum now, its half keeps computing an ignored padded DP
+            if (PK && i + 1 == nshort && nshort < nmax) {
 #pragma unroll
-            for (int h = 0; h < PAIRS; ++h) {
-                if (i + 1 == n[h]) {
-#pragma unroll
-                    for (int c = 0; c < T; ++c) {
-                        int j = r * T + c + 1;
-                        int v = PK ? (int)(h == 0 ? (up[c] & 0xffffu) : (up[c] >> 16)) : (int)up[c];
-                        if (j <= m[h] && v < bestv[h]) { bestv[h] = v; bestj[h] = j; }
-                    }
+                for (int c = 0; c < T; ++c) {
+                    int j = r * T + c + 1;
+                    int v = (int)(hshort == 0 ? (up[c] & 0xffffu) : (up[c] >> 16));
+                    if (j <= mshort && v < bests) { bests = v; bestjs = j; }
                 }
             }
+        }
+    }
+    // the pair(s) with n == nmax: after the loop every lane still holds its columns of the last row
+#pragma unroll
+    for (int h = 0; h < PAIRS; ++h) {
+        if (n[h] == nmax && nmax > 0) {
+#pragma unroll
+            for (int c = 0; c < T; ++c) {
+                int j = r * T + c + 1;
+                int v = PK ? (int)(h == 0 ? (up[c] & 0xffffu) : (up[c] >> 16)) : (int)up[c];
+                if (j <= m[h] && v < bestv[h]) { bestv[h] = v; bestj[h] = j; }
+            }
+        } else if (PK) {
+            bestv[h] = bests;
+            bestj[h] = bestjs;
         }
     }
 
@@ -226,8 +258,23 @@ __global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(
         }
         int64_t p = p0 + h;
         if (r == 0 && p < P) {
-            score_out[p] = prm.beta + n[h] * prm.maxs - bestv[h];
-            end_out[p] = bestj[h];
+            const int32_t score = prm.beta + n[h] * prm.maxs - bestv[h];
+            if (eo.edges == nullptr) {
+                score_out[p] = score;
+                end_out[p] = bestj[h];
+            } else {
+                // fused K6 (overlapGraphs.py:55-60): emit the pair's copy_a x copy_b edge rows directly
+                const int32_t a = pair_a[p], b = pair_b[p];
+                if (eo.copies == nullptr) {
+                    eo.edges[p] = make_int4(a, b, score, bestj[h]);
+                } else {
+                    const int32_t ca = eo.copies[a], cb = eo.copies[b];
+                    const int32_t na = (int32_t)eo.node_off[a], nb = (int32_t)eo.node_off[b];
+                    int4* dst = eo.edges + eo.edge_off[p];
+                    for (int32_t ia = 0; ia < ca; ++ia)
+                        for (int32_t ib = 0; ib < cb; ++ib) *dst++ = make_int4(na + ia, nb + ib, score, bestj[h]);
+                }
+            }
         }
     }
 }

@@ -313,7 +313,7 @@ bool dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_t indel, in
 
 template <int G, int T, bool PK>
 int launch_dp(const uint32_t* packed, int32_t row_words, const int32_t* len, const int32_t* pair_a, const int32_t* pair_b,
-              int64_t P, int32_t max_len, const DpParams& prm, int32_t* score, int32_t* end, cudaStream_t st) {
+              int64_t P, int32_t max_len, const DpParams& prm, int32_t* score, int32_t* end, const DpEdgeOut& eo, cudaStream_t st) {
     constexpr int PAIRS = PK ? 2 : 1;
     constexpr int GROUPS_PER_CTA = (kDpThreads / 32) * (32 / G);
     int64_t groups = (P + PAIRS - 1) / PAIRS;
@@ -325,13 +325,13 @@ int launch_dp(const uint32_t* packed, int32_t row_words, const int32_t* len, con
         cudaError_t e = cudaFuncSetAttribute(overlap_dp_kernel<G, T, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(OVL_E_CUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));
     }
-    overlap_dp_kernel<G, T, PK><<<(unsigned)grid, kDpThreads, smem, st>>>(packed, row_words, len, pair_a, pair_b, P, lut_rows, prm, score, end);
+    overlap_dp_kernel<G, T, PK><<<(unsigned)grid, kDpThreads, smem, st>>>(packed, row_words, len, pair_a, pair_b, P, lut_rows, prm, score, end, eo);
     LAUNCH_CHECK("overlap_dp_kernel");
     return OVL_OK;
 }
 
 #define DP_CASE(G_, T_, PK_) \
-    if (plan.G == G_ && plan.T == T_) return launch_dp<G_, T_, PK_>(packed, row_words, len, pair_a, pair_b, P, max_len, plan.prm, score, end, st);
+    if (plan.G == G_ && plan.T == T_) return launch_dp<G_, T_, PK_>(packed, row_words, len, pair_a, pair_b, P, max_len, plan.prm, score, end, eo, st);
 #define DP_CASES_T(T_, PK_) \
     DP_CASE(1, T_, PK_) DP_CASE(2, T_, PK_) DP_CASE(4, T_, PK_) DP_CASE(8, T_, PK_) DP_CASE(16, T_, PK_) DP_CASE(32, T_, PK_)
 
@@ -350,25 +350,51 @@ int ovl_overlap_dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_
     return OVL_OK;
 }
 
-int ovl_overlap_dp(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, const int32_t* pair_a,
-                   const int32_t* pair_b, int64_t P, int32_t max_len, int64_t match, int64_t mismatch, int64_t indel,
-                   int32_t* score, int32_t* end, int32_t mode, int32_t group_lanes, int32_t cols_per_lane, void* stream) {
-    if (!ctx || !packed || !len || !pair_a || !pair_b || !score || !end) return fail(OVL_E_ARG, "ovl_overlap_dp: null argument");
+}  // extern "C"
+
+static int dp_dispatch(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, const int32_t* pair_a,
+                       const int32_t* pair_b, int64_t P, int32_t max_len, int64_t match, int64_t mismatch, int64_t indel,
+                       int32_t* score, int32_t* end, const DpEdgeOut& eo, int32_t mode, int32_t group_lanes,
+                       int32_t cols_per_lane, void* stream, const char* who) {
+    if (!ctx || !packed || !len || !pair_a || !pair_b) return fail(OVL_E_ARG, "%s: null argument", who);
     if (P <= 0) return OVL_OK;
-    if (row_words < 4 || (row_words & 3) || max_len > 16 * row_words) return fail(OVL_E_ARG, "ovl_overlap_dp: row_words=%d does not hold max_len=%d", row_words, max_len);
+    if (row_words < 4 || (row_words & 3) || max_len > 16 * row_words) return fail(OVL_E_ARG, "%s: row_words=%d does not hold max_len=%d", who, row_words, max_len);
     if (max_len > OVL_MAX_READ_LEN)
-        return fail(OVL_E_UNSUPPORTED, "ovl_overlap_dp: read length %d exceeds the supported maximum %d", max_len, OVL_MAX_READ_LEN);
+        return fail(OVL_E_UNSUPPORTED, "%s: read length %d exceeds the supported maximum %d", who, max_len, OVL_MAX_READ_LEN);
     DpPlan plan;
     if (!dp_plan(max_len, match, mismatch, indel, mode, group_lanes, cols_per_lane, &plan))
-        return fail(OVL_E_UNSUPPORTED, "ovl_overlap_dp: no kernel for (match=%lld, mismatch=%lld, indel=%lld, len=%d, mode=%d, lanes=%d, cols=%d)",
-                    (long long)match, (long long)mismatch, (long long)indel, max_len, mode, group_lanes, cols_per_lane);
+        return fail(OVL_E_UNSUPPORTED, "%s: no kernel for (match=%lld, mismatch=%lld, indel=%lld, len=%d, mode=%d, lanes=%d, cols=%d)",
+                    who, (long long)match, (long long)mismatch, (long long)indel, max_len, mode, group_lanes, cols_per_lane);
     cudaStream_t st = (cudaStream_t)stream;
     if (plan.mode == 1) {
         DP_CASES_T(19, true) DP_CASES_T(25, true) DP_CASES_T(32, true) DP_CASES_T(38, true)
     } else {
         DP_CASES_T(32, false)
     }
-    return fail(OVL_E_UNSUPPORTED, "ovl_overlap_dp: instantiation G=%d T=%d mode=%d missing", plan.G, plan.T, plan.mode);
+    return fail(OVL_E_UNSUPPORTED, "%s: instantiation G=%d T=%d mode=%d missing", who, plan.G, plan.T, plan.mode);
+}
+
+extern "C" {
+
+int ovl_overlap_dp(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, const int32_t* pair_a,
+                   const int32_t* pair_b, int64_t P, int32_t max_len, int64_t match, int64_t mismatch, int64_t indel,
+                   int32_t* score, int32_t* end, int32_t mode, int32_t group_lanes, int32_t cols_per_lane, void* stream) {
+    if (P > 0 && (!score || !end)) return fail(OVL_E_ARG, "ovl_overlap_dp: null output");
+    DpEdgeOut eo{nullptr, nullptr, nullptr, nullptr};
+    return dp_dispatch(ctx, packed, row_words, len, pair_a, pair_b, P, max_len, match, mismatch, indel, score, end, eo,
+                       mode, group_lanes, cols_per_lane, stream, "ovl_overlap_dp");
+}
+
+int ovl_overlap_dp_edges(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, const int32_t* pair_a,
+                         const int32_t* pair_b, int64_t P, int32_t max_len, int64_t match, int64_t mismatch, int64_t indel,
+                         const int32_t* copies, const int64_t* node_off, const int64_t* edge_off, int32_t* edges,
+                         void* stream) {
+    if (P > 0 && !edges) return fail(OVL_E_ARG, "ovl_overlap_dp_edges: null output");
+    if ((uintptr_t)edges & 15) return fail(OVL_E_ARG, "ovl_overlap_dp_edges: edges must be 16-byte aligned");
+    if (copies && (!node_off || !edge_off)) return fail(OVL_E_ARG, "ovl_overlap_dp_edges: copies given without node_off / edge_off");
+    DpEdgeOut eo{(int4*)edges, copies, node_off, edge_off};
+    return dp_dispatch(ctx, packed, row_words, len, pair_a, pair_b, P, max_len, match, mismatch, indel, nullptr, nullptr, eo,
+                       0, 0, 0, stream, "ovl_overlap_dp_edges");
 }
 
 // ---------------------------------------------------------------- K6

@@ -209,6 +209,38 @@ class OverlapEngine:
             self.launches += 1
         return score[:P], end[:P]
 
+    def overlap_edges_fused(self, rs: ReadSet, pair_a: torch.Tensor, pair_b: torch.Tensor,
+                            copies: Optional[torch.Tensor] = None, node_off: Optional[torch.Tensor] = None,
+                            match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT,
+                            events=None) -> torch.Tensor:
+        """DP + edge expansion in one kernel (overlapGraphs.py:53-60): the DP epilogue writes the
+        copy_a x copy_b edge rows, so score/end never travel through HBM."""
+        P = int(pair_a.shape[0])
+        st = self._stream()
+        if P == 0:
+            return torch.empty((0, 4), dtype=torch.int32, device=self.device)
+        edge_off = None
+        E = P
+        if copies is not None:
+            edge_off = self._empty(P + 1, torch.int64)
+            ws_bytes = int(nat.lib.ovl_expand_workspace_bytes(P))
+            ws = self._empty(ws_bytes, torch.uint8)
+            nat.check(nat.lib.ovl_expand_count(self._ctx, _ptr(pair_a), _ptr(pair_b), _ptr(copies), P,
+                                               _ptr(edge_off), _ptr(ws), ws_bytes, st))
+            self.launches += 1 if P <= 16384 else 3
+            E = int(edge_off[P].item())                       # host sync: the output size
+        edges = self._empty(E * 4, torch.int32)
+        if events is not None:
+            events[0].record()
+        nat.check(nat.lib.ovl_overlap_dp_edges(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length),
+                                               _ptr(pair_a), _ptr(pair_b), P, rs.max_len,
+                                               int(match_score), int(mismatch), int(indel),
+                                               _ptr(copies), _ptr(node_off), _ptr(edge_off), _ptr(edges), st))
+        if events is not None:
+            events[1].record()
+        self.launches += 1
+        return edges[:E * 4].view(E, 4)
+
     @staticmethod
     def dp_plan(max_len: int, match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT, mode: int = 0):
         out = (ctypes.c_int32 * 3)()
@@ -259,7 +291,7 @@ class OverlapEngine:
         ws = self._empty(ws_bytes, torch.uint8)
         nat.check(nat.lib.ovl_expand_count(self._ctx, _ptr(pair_a), _ptr(pair_b), _ptr(copies), P,
                                            _ptr(edge_off), _ptr(ws), ws_bytes, st))
-        self.launches += 4 if P > 0 else 0
+        self.launches += 1 if P <= 16384 else 3
         E = int(edge_off[P].item())                           # host sync: the output size
         edges = self._empty(E * 4, torch.int32)
         if E:
@@ -277,8 +309,7 @@ class OverlapEngine:
         """Reads already packed in HBM -> device edge rows (this rank's shard)."""
         index = self.kmer_index(rs, k) if k > 0 else None
         pair_a, pair_b, _ = self.candidate_pairs(rs, index, k, shard)
-        score, end = self.overlap_scores(rs, pair_a, pair_b, match_score, mismatch, indel)
-        edges = self.expand_edges(pair_a, pair_b, score, end, copies, node_off)
+        edges = self.overlap_edges_fused(rs, pair_a, pair_b, copies, node_off, match_score, mismatch, indel)
         if stats is not None:
             stats["pairs"] = int(pair_a.shape[0])
             stats["edges"] = int(edges.shape[0])

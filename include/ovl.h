@@ -105,6 +105,15 @@ int ovl_overlap_dp(ovl_ctx *ctx, const uint32_t *packed, int32_t row_words, cons
                    const int32_t *pair_a, const int32_t *pair_b, int64_t P, int32_t max_len,
                    int64_t match, int64_t mismatch, int64_t indel, int32_t *score, int32_t *end,
                    int32_t mode, int32_t group_lanes, int32_t cols_per_lane, void *stream);
+/* K4/K5 with K6 fused into the epilogue: instead of score/end the kernel writes the pair's
+ * copy_a x copy_b edge rows (overlapGraphs.py:55-60) itself.  copies == NULL: every read occurs
+ * once, edges[p] = (a, b, score, end).  Otherwise edge_off[P+1] comes from ovl_expand_count and
+ * edges has edge_off[P] rows. */
+int ovl_overlap_dp_edges(ovl_ctx *ctx, const uint32_t *packed, int32_t row_words, const int32_t *len,
+                         const int32_t *pair_a, const int32_t *pair_b, int64_t P, int32_t max_len,
+                         int64_t match, int64_t mismatch, int64_t indel, const int32_t *copies,
+                         const int64_t *node_off, const int64_t *edge_off, int32_t *edges,
+                         void *stream);
 /* which kernel ovl_overlap_dp would pick: out[0]=mode (1 packed, 2 int32), out[1]=lanes,
  * out[2]=columns per lane.  Returns OVL_E_UNSUPPORTED when nothing fits. */
 int ovl_overlap_dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_t indel,

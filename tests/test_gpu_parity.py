@@ -291,6 +291,27 @@ def test_edge_rows_insertion_order(eng):
     assert np.array_equal(edges, want)
 
 
+def test_fused_epilogue_equals_separate_expansion(eng):
+    """K6 fused into the DP epilogue == DP (score/end) followed by the stand-alone expansion."""
+    import torch
+    synth = load_pkg("synth")
+    bases, offsets = synth.simulate_reads(synth.phix_like_genome(), 6000, 100, 0.01, seed=9)
+    ub, uo, counts, _ = synth.dedup(bases, offsets)
+    assert counts.max() > 1
+    rs = eng.upload_reads(ub, uo)
+    idx = eng.kmer_index(rs, 5)
+    pa, pb, _ = eng.candidate_pairs(rs, idx, 5)
+    node_off = np.zeros(len(counts) + 1, np.int64)
+    np.cumsum(counts, out=node_off[1:])
+    d_copies = torch.from_numpy(counts).to(eng.device)
+    d_node = torch.from_numpy(node_off).to(eng.device)
+    score, end = eng.overlap_scores(rs, pa, pb)
+    for cp, no in [(d_copies, d_node), (None, None)]:
+        sep = eng.expand_edges(pa, pb, score, end, cp, no)
+        fused = eng.overlap_edges_fused(rs, pa, pb, cp, no)
+        assert torch.equal(sep, fused)
+
+
 def test_sharded_edges_concatenate(eng):
     """Rank slices of the pair list produce edge slices whose concatenation is the 1-GPU list."""
     synth = load_pkg("synth")
