@@ -370,10 +370,18 @@ def run_ours(args):
             else (probe["viaddmnmx_s16x2"] * 2 + probe["imad"]) / 1e3
         peak_int32 = probe["lop3"] / 1e3            # int32 lanes x clock (one op per lane-instr)
         pk, pk_kind = peaks()
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "dp_traffic.json")) as fh:
+                ent = json.load(fh).get(f"{args.workload}:k{args.k}:gpus{world}")
+            if ent:
+                traffic = ent["dram_bytes_read"] + ent["dram_bytes_write"]      # one ncu capture, per launch
+        except Exception:
+            traffic = None
         roofline = {"bound": "int-pipe (ALU DPX + FMA IMAD)",
                     "kernel": f"overlap_dp_kernel<{plan['lanes']},{plan['cols']},{plan['mode']}>",
                     "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak if peak else None,
-                    "traffic": None, "ops_per_cell": OPS_PER_CELL,
+                    "traffic": traffic, "ops_per_cell": OPS_PER_CELL,
                     "dp_gcups": cells_per_launch / (dp_ms_avg * 1e-3) / 1e9, "dp_ms": dp_ms_avg,
                     "peak_source": "ovl_int_peak_probe in this run: 4 ops x VIADDMNMX.16x2 rate + 2 ops x IMAD rate",
                     "frac_vs_int32_lanes": achieved / peak_int32, "peak_int32_lanes": peak_int32,
@@ -426,7 +434,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="phix_n50000_l150")
+    # BASELINE.json quotes the metric "at 1/2/4/8 B200" on configs[2] (4.6 Mb genome, 1M reads, l=150,
+    # p=0.005, sharded by read-ID range); it fits one GPU (~32 GB), so it is the workload at every N.
+    # configs[1] is --workload phix_n50000_l150 (numbers in DESIGN.md).
+    ap.add_argument("--workload", default="ecoli_n1m_l150")
     ap.add_argument("--k", type=int, default=5)
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

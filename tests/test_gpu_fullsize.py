@@ -1,0 +1,107 @@
+"""Full-size checks at BASELINE.json configs[1] (PhiX-like, N=50,000, l=150, p=0.01) and a slice of
+configs[3] (l=1000): size-independent properties plus oracle parity on random samples."""
+import numpy as np
+import pytest
+
+from conftest import load_pkg, has_cuda
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")]
+
+from oracle import overlap_oracle as orc  # noqa: E402  (the checker)
+
+
+@pytest.fixture(scope="module")
+def phix50k():
+    import torch
+    synth = load_pkg("synth")
+    eng = load_pkg("engine").get_engine()
+    bases, offsets = synth.make_workload("phix_n50000_l150")
+    ub, uo, counts, _ = synth.dedup(bases, offsets)
+    rs = eng.upload_reads(ub, uo)
+    idx = eng.kmer_index(rs, 5)
+    pa, pb, _ = eng.candidate_pairs(rs, idx, 5)
+    score, end = eng.overlap_scores(rs, pa, pb)
+    torch.cuda.synchronize()
+    return dict(eng=eng, ub=ub, uo=uo, counts=counts, rs=rs, idx=idx, pa=pa, pb=pb, score=score, end=end)
+
+
+def test_candidate_list_properties(phix50k):
+    d = phix50k
+    pa, pb = d["pa"].cpu().numpy().astype(np.int64), d["pb"].cpu().numpy().astype(np.int64)
+    U = len(d["counts"])
+    # ordered by (a, b), no self pairs, no duplicates
+    key = pa * U + pb
+    assert np.all(np.diff(key) > 0)
+    assert np.all(pa != pb)
+    # every pair satisfies suffix_k(a) == prefix_k(b), and the count equals an independent NumPy join
+    k = 5
+    lens = (d["uo"][1:] - d["uo"][:-1])
+    assert np.all(lens[pa] >= k) and np.all(lens[pb] >= k)
+    suf = np.stack([d["ub"][d["uo"][pa + 1] - k + i] for i in range(k)], axis=1)
+    pre = np.stack([d["ub"][d["uo"][pb] + i] for i in range(k)], axis=1)
+    assert np.array_equal(suf, pre)
+    valid = np.nonzero(lens >= k)[0]
+    code = np.zeros(256, np.int64)
+    code[np.frombuffer(b"ACGT", np.uint8)] = np.arange(4)
+    pk = sum(code[d["ub"][d["uo"][valid] + i]] * 4 ** i for i in range(k))
+    sk = sum(code[d["ub"][d["uo"][valid + 1] - k + i]] * 4 ** i for i in range(k))
+    hist = np.bincount(pk, minlength=4 ** k)
+    expect = int(hist[sk].sum() - (pk == sk).sum())
+    assert len(pa) == expect
+
+
+def test_scores_sample_vs_oracle_and_invariants(phix50k):
+    d = phix50k
+    score, end = d["score"].cpu().numpy(), d["end"].cpu().numpy()
+    pa, pb = d["pa"].cpu().numpy(), d["pb"].cpu().numpy()
+    lens = (d["uo"][1:] - d["uo"][:-1])
+    # default scoring: the k shared bases alone give >= 10*k - ... ; bounds from the recurrence
+    assert score.min() >= 0 and np.all(score <= 10 * np.minimum(lens[pa], lens[pb]))
+    assert np.all(end >= 0) and np.all(end <= lens[pb])
+    assert np.all(score >= 10 * 5 - 0)          # the shared 5-mer is an exact overlap of length 5
+    rng = np.random.default_rng(3)
+    sel = rng.choice(len(pa), size=20000, replace=False)
+    ws, we = orc.overlap_pairs(d["ub"], d["uo"], pa[sel], pb[sel])
+    assert np.array_equal(score[sel], ws) and np.array_equal(end[sel], we)
+    # finite indel on the same sample (gaps can only raise the score)
+    import torch
+    eng = d["eng"]
+    ta, tb = torch.from_numpy(pa[sel]).to(eng.device), torch.from_numpy(pb[sel]).to(eng.device)
+    s2, e2 = eng.overlap_scores(d["rs"], ta, tb, 10, -1, -2)
+    ws2, we2 = orc.overlap_pairs(d["ub"], d["uo"], pa[sel], pb[sel], 10, -1, -2)
+    assert np.array_equal(s2.cpu().numpy(), ws2) and np.array_equal(e2.cpu().numpy(), we2)
+    assert np.all(ws2 >= ws)
+
+
+def test_edge_list_checksum_is_shard_invariant(phix50k):
+    d = phix50k
+    eng = d["eng"]
+    whole = eng.overlap_edges(d["ub"], d["uo"], d["counts"], k=5)
+    E = int((d["counts"][d["pa"].cpu().numpy()].astype(np.int64) * d["counts"][d["pb"].cpu().numpy()]).sum())
+    assert whole.shape == (E, 4)
+    chk = int(whole.astype(np.int64).sum())
+    parts = [eng.overlap_edges(d["ub"], d["uo"], d["counts"], k=5, shard=(r, 8)) for r in range(8)]
+    assert sum(int(p.astype(np.int64).sum()) for p in parts) == chk
+    assert np.array_equal(np.concatenate(parts), whole)
+    # idempotence: a second run gives the same bytes
+    assert np.array_equal(eng.overlap_edges(d["ub"], d["uo"], d["counts"], k=5), whole)
+
+
+def test_long_reads_sample_vs_oracle():
+    """configs[3] shape: l = 1000, p = 0.02 (warp-per-couple instantiation), smaller genome."""
+    import torch
+    synth = load_pkg("synth")
+    eng = load_pkg("engine").get_engine()
+    genome = synth.random_genome(200_000, 11)
+    bases, offsets = synth.simulate_reads(genome, 8000, 1000, 0.02, seed=4)
+    ub, uo, counts, _ = synth.dedup(bases, offsets)
+    rs = eng.upload_reads(ub, uo)
+    assert eng.dp_plan(rs.max_len)["lanes"] == 32
+    idx = eng.kmer_index(rs, 8)
+    pa, pb, _ = eng.candidate_pairs(rs, idx, 8)
+    score, end = eng.overlap_scores(rs, pa, pb)
+    n = min(int(pa.shape[0]), 1500)
+    sel = np.random.default_rng(1).choice(int(pa.shape[0]), size=n, replace=False)
+    pa_h, pb_h = pa.cpu().numpy()[sel], pb.cpu().numpy()[sel]
+    ws, we = orc.overlap_pairs(ub, uo, pa_h, pb_h)
+    assert np.array_equal(score.cpu().numpy()[sel], ws) and np.array_equal(end.cpu().numpy()[sel], we)
