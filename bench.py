@@ -352,7 +352,7 @@ def run_ours(args):
         # ---- roofline of the dominant kernel (the DP): integer pipe, not HBM
         probe = {}
         names = {0: "iadd3", 1: "imad", 2: "vimnmx_s32", 3: "viaddmnmx_s16x2", 4: "dp_mix", 5: "prmt", 6: "lop3",
-                 7: "lop3_imad_pair"}
+                 7: "lop3_imad_pair", 8: "vimnmx3_imad_distinct_regs", 9: "dp_form1_column"}
         import ctypes
         nat = importlib.import_module(PKG + "._native")
         for kind, nm in names.items():
@@ -385,6 +385,9 @@ def run_ours(args):
                     "dp_gcups": cells_per_launch / (dp_ms_avg * 1e-3) / 1e9, "dp_ms": dp_ms_avg,
                     "peak_source": "ovl_int_peak_probe in this run: 4 ops x VIADDMNMX.16x2 rate + 2 ops x IMAD rate",
                     "frac_vs_int32_lanes": achieved / peak_int32, "peak_int32_lanes": peak_int32,
+                    # what a pure stream of the kernel's own form-1 columns (PRMT, IMAD, 2x VIADDMNMX on distinct
+                    # registers, no loop overhead) sustains on this GPU: 2 cells per 4 lane-instructions
+                    "same_mix_stream_gcups": probe["dp_form1_column"] / 4 * 2,
                     "int_probe_gops": probe, "hbm_peak_gbs": pk.get("hbm_gbs"), "hbm_peak_source": pk_kind}
         # ---- the k-mer stages (K0-K3) and edge expansion (K6): HBM-bound; algorithmic bytes per SURVEY 8(d)
         passes = (2 * args.k + 7) // 8

@@ -48,6 +48,9 @@ struct DpParams {
     int32_t gu;         // effective cost of an up move   (maxs - indel), clamped
     int32_t gl;         // effective cost of a left move  (-indel), clamped
     uint32_t one;       // == 1, a runtime value so the adds stay IMADs
+    // the same constants pre-packed for the kernel (both 16-bit halves in packed mode), so that
+    // they reach the instructions as uniform/constant operands and cost no register-file reads
+    uint32_t gu2, gl2, maxs2, beta2;
 };
 
 // optional fused edge expansion in the DP epilogue (all null: plain score/end output)
@@ -60,7 +63,7 @@ struct DpEdgeOut {
 
 constexpr int kDpThreads = 128;
 #ifndef OVL_DP_MINB
-#define OVL_DP_MINB 4          // resident CTAs per SM the register allocator must allow
+#define OVL_DP_MINB 3          // resident CTAs per SM the register allocator must allow (168 regs; measured best)
 #endif
 #ifndef OVL_DP_F2_NUM
 #define OVL_DP_F2_NUM 1        // columns using form 2 (FMA-heavy): NUM out of every DEN
@@ -144,11 +147,12 @@ __global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(
         }
     }
     __syncwarp();
+    const uint32_t lut_addr = (uint32_t)__cvta_generic_to_shared(lut);
 
     // ---- per-column state
     uint32_t up[T];        // C[i-1][j] for my columns (row 0: beta)
     uint32_t sel[T];       // PK: PRMT selector holding (tA[j], tB[j]);  else: t code
-    const uint32_t beta2 = PK ? pack2(prm.beta) : (uint32_t)prm.beta;
+    const uint32_t beta2 = prm.beta2;
 #pragma unroll
     for (int c = 0; c < T; ++c) {
         int j = min(r * T + c, max_col);
@@ -161,9 +165,7 @@ __global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(
         }
         up[c] = beta2;
     }
-    const uint32_t gu2 = PK ? pack2(prm.gu) : (uint32_t)prm.gu;
-    const uint32_t gl2 = PK ? pack2(prm.gl) : (uint32_t)prm.gl;
-    const uint32_t maxs2 = PK ? (uint32_t)prm.maxs * 0x10001u : (uint32_t)prm.maxs;
+    const uint32_t gu2 = prm.gu2, gl2 = prm.gl2, maxs2 = prm.maxs2;
     const uint32_t one = prm.one;
 
     // running best of the last row, per pair: cost (smaller is better), column j
@@ -190,9 +192,10 @@ __global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(
         uint32_t recv = __shfl_up_sync(kFull, out, 1, G);
         col0 += maxs2;                                     // lane 0 at step k: C[k+1][0]
         if (r == 0) recv = col0;
-        if (i >= 0 && i < nmax) {
+        if ((unsigned)i < (unsigned)nmax) {               // 0 <= i < nmax in one compare
             uint32_t left = recv, diag = diag_in;
-            const uint2 lu = lut[i];
+            uint2 lu;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lu.x), "=r"(lu.y) : "r"(lut_addr + 8u * (unsigned)i));
 #pragma unroll
             for (int c = 0; c < T; ++c) {
                 uint32_t g;

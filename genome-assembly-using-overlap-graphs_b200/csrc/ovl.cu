@@ -284,6 +284,15 @@ bool dp_params(int64_t match, int64_t mismatch, int64_t indel, int64_t N, int64_
     if (eqc >= (1ll << 30) || nec >= (1ll << 30)) return false;
     out->eqc = (int32_t)eqc; out->nec = (int32_t)nec; out->maxs = (int32_t)maxs; out->beta = (int32_t)beta;
     out->gu = (int32_t)gu; out->gl = (int32_t)gl; out->one = 1u;
+    if (packed) {
+        out->gu2 = ((uint32_t)gu & 0xffffu) * 0x10001u;
+        out->gl2 = ((uint32_t)gl & 0xffffu) * 0x10001u;
+        out->maxs2 = (uint32_t)(int32_t)maxs * 0x10001u;
+        out->beta2 = ((uint32_t)beta & 0xffffu) * 0x10001u;
+    } else {
+        out->gu2 = (uint32_t)(int32_t)gu; out->gl2 = (uint32_t)(int32_t)gl;
+        out->maxs2 = (uint32_t)(int32_t)maxs; out->beta2 = (uint32_t)(int32_t)beta;
+    }
     return true;
 }
 
@@ -498,6 +507,8 @@ int ovl_int_peak_probe(ovl_ctx* ctx, int32_t kind, int32_t iters, double* h_gops
         case 5: return run_probe<5>(ctx, iters, h_gops, h_ms);
         case 6: return run_probe<6>(ctx, iters, h_gops, h_ms);
         case 7: return run_probe<7>(ctx, iters, h_gops, h_ms);
+        case 8: return run_probe<8>(ctx, iters, h_gops, h_ms);
+        case 9: return run_probe<9>(ctx, iters, h_gops, h_ms);
         default: return fail(OVL_E_ARG, "ovl_int_peak_probe: unknown kind %d", kind);
     }
 }

@@ -12,9 +12,12 @@ constexpr int kProbeThreads = 256;
 
 template <int KIND>
 __global__ void __launch_bounds__(kProbeThreads) int_probe_kernel(uint32_t* out, int iters, uint32_t a0, uint32_t b0, uint32_t one) {
-    uint32_t v[kProbeChains], w[kProbeChains];
+    uint32_t v[kProbeChains], w[kProbeChains], x[kProbeChains], y[kProbeChains], z[kProbeChains];
 #pragma unroll
-    for (int c = 0; c < kProbeChains; ++c) { v[c] = a0 + threadIdx.x + c; w[c] = b0 ^ (c * 0x01010101u); }
+    for (int c = 0; c < kProbeChains; ++c) {
+        v[c] = a0 + threadIdx.x + c; w[c] = b0 ^ (c * 0x01010101u);
+        x[c] = a0 * (c + 3); y[c] = b0 + 7 * c + threadIdx.x; z[c] = (a0 ^ b0) + c;
+    }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int u = 0; u < kProbeUnroll; ++u) {
@@ -40,6 +43,16 @@ __global__ void __launch_bounds__(kProbeThreads) int_probe_kernel(uint32_t* out,
                 } else if (KIND == 7) {     // LOP3 and IMAD on independent chains: do ALU and FMA pipes co-issue?
                     asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[c]) : "r"(a0), "r"(b0));
                     asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(w[c]) : "r"(one), "r"(b0));
+                } else if (KIND == 8) {     // VIMNMX3 + IMAD with all-distinct register operands: register-file pressure
+                    v[c] = __vimin3_u16x2(v[c], x[c], y[c]);
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(w[c]) : "r"(one), "r"(z[c]));
+                } else if (KIND == 9) {     // form-1 column with distinct registers per chain (PRMT, IMAD, 2x VIADDMNMX)
+                    uint32_t dc;
+                    asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(dc) : "r"(x[c]), "r"(y[c]), "r"(v[c]));
+                    uint32_t a1;
+                    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a1) : "r"(dc), "r"(one), "r"(z[c]));
+                    uint32_t t1 = __viaddmin_u16x2(w[c], b0, a1);
+                    v[c] = __viaddmin_u16x2(v[c], a0, t1);
                 } else if (KIND == 5) {     // PRMT
                     asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(v[c]) : "r"(w[c]), "r"(b0));
                 } else {                    // LOP3
@@ -50,10 +63,10 @@ __global__ void __launch_bounds__(kProbeThreads) int_probe_kernel(uint32_t* out,
     }
     uint32_t acc = 0;
 #pragma unroll
-    for (int c = 0; c < kProbeChains; ++c) acc ^= v[c] + w[c];
+    for (int c = 0; c < kProbeChains; ++c) acc ^= v[c] + w[c] + (KIND >= 8 ? x[c] ^ y[c] ^ z[c] : 0u);
     if (acc == 0x12345678u) out[0] = acc;    // practically never; keeps the chains alive
 }
 
-inline int probe_ops_per_iter(int kind) { return kind == 4 ? 4 : (kind == 7 ? 2 : 1); }
+inline int probe_ops_per_iter(int kind) { return (kind == 4 || kind == 9) ? 4 : ((kind == 7 || kind == 8) ? 2 : 1); }
 
 }  // namespace ovl
