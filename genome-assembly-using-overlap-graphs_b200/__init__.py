@@ -22,9 +22,9 @@ def __getattr__(name):
     if name in ("overlap_alignment",):
         from .aligners import overlap_alignment
         return overlap_alignment
-    if name in ("construct_overlap_graph_nx_k",):
-        from .overlapGraphs import construct_overlap_graph_nx_k
-        return construct_overlap_graph_nx_k
+    if name in ("construct_overlap_graph_nx_k", "construct_overlap_graph_string", "construct_string_graph"):
+        from . import overlapGraphs
+        return getattr(overlapGraphs, name)
     if name in ("OverlapEngine", "get_engine"):
         from . import engine
         return getattr(engine, name)

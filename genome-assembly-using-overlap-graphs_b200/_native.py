@@ -63,6 +63,9 @@ _SIGS = {
     "ovl_expand_count": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "ovl_expand_fill": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "ovl_expand_unit": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "ovl_filter_workspace_bytes": (_sz, [_i64]),
+    "ovl_filter_count": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _sz, _vp]),
+    "ovl_filter_fill": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "ovl_align_pair_workspace_bytes": (_sz, [_i32, _i32]),
     "ovl_align_pair": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp, _vp, _vp]),
     "ovl_int_peak_probe": (ctypes.c_int, [_vp, _i32, _i32, ctypes.POINTER(ctypes.c_double),

@@ -68,6 +68,9 @@ constexpr int kDpThreads = 128;
 #ifndef OVL_DP_F2_NUM
 #define OVL_DP_F2_NUM 1        // columns using form 2 (FMA-heavy): NUM out of every DEN
 #endif
+#ifndef OVL_DP_PREPACK
+#define OVL_DP_PREPACK 0       // 1: take the packed constants from the kernel parameters (measured slower)
+#endif
 #ifndef OVL_DP_KUNROLL
 #define OVL_DP_KUNROLL 1       // unroll factor of the row loop
 #endif
@@ -152,7 +155,11 @@ __global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(
     // ---- per-column state
     uint32_t up[T];        // C[i-1][j] for my columns (row 0: beta)
     uint32_t sel[T];       // PK: PRMT selector holding (tA[j], tB[j]);  else: t code
+#if OVL_DP_PREPACK
     const uint32_t beta2 = prm.beta2;
+#else
+    const uint32_t beta2 = PK ? pack2(prm.beta) : (uint32_t)prm.beta;
+#endif
 #pragma unroll
     for (int c = 0; c < T; ++c) {
         int j = min(r * T + c, max_col);
@@ -165,7 +172,13 @@ __global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(
         }
         up[c] = beta2;
     }
+#if OVL_DP_PREPACK
     const uint32_t gu2 = prm.gu2, gl2 = prm.gl2, maxs2 = prm.maxs2;
+#else
+    const uint32_t gu2 = PK ? pack2(prm.gu) : (uint32_t)prm.gu;
+    const uint32_t gl2 = PK ? pack2(prm.gl) : (uint32_t)prm.gl;
+    const uint32_t maxs2 = PK ? (uint32_t)prm.maxs * 0x10001u : (uint32_t)prm.maxs;
+#endif
     const uint32_t one = prm.one;
 
     // running best of the last row, per pair: cost (smaller is better), column j

@@ -351,6 +351,16 @@ __global__ void __launch_bounds__(kFillThreads) expand_fill_kernel(const int64_t
     }
 }
 
+// order-preserving compaction of the edge rows with weight >= min_weight (keep_off = exclusive scan
+// of the keep flags): the `if score > 0` of the all-pairs builders, overlapGraphs.py:225 and :347
+__global__ void __launch_bounds__(256) filter_edges_kernel(const int4* __restrict__ edges, const int64_t* __restrict__ keep_off,
+                                                           int64_t E, int32_t min_weight, int4* __restrict__ out) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    int4 row = edges[e];
+    if (row.z >= min_weight) out[keep_off[e]] = row;
+}
+
 // every read appears once: edge row == pair row, no scan needed
 __global__ void __launch_bounds__(256) expand_unit_kernel(const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b,
                                                           const int32_t* __restrict__ score, const int32_t* __restrict__ end,

@@ -445,6 +445,30 @@ int ovl_expand_unit(ovl_ctx* ctx, const int32_t* pair_a, const int32_t* pair_b, 
     return OVL_OK;
 }
 
+// ---------------------------------------------------------------- edge filter (all-pairs builders)
+size_t ovl_filter_workspace_bytes(int64_t E) {
+    if (E < 1) E = 1;
+    return align256(scan_workspace_bytes(E, sizeof(int64_t))) + 256;
+}
+
+int ovl_filter_count(ovl_ctx* ctx, const int32_t* edges, int64_t E, int32_t min_weight, int64_t* keep_off, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    if (!ctx || !keep_off || !workspace || (E > 0 && !edges)) return fail(OVL_E_ARG, "ovl_filter_count: null argument");
+    if (workspace_bytes < ovl_filter_workspace_bytes(E)) return fail(OVL_E_ARG, "ovl_filter_count: workspace too small");
+    void* sums = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    CUDA_TRY((exclusive_scan<EdgeKept, int64_t>(EdgeKept{(const int4*)edges, min_weight}, keep_off, E, sums, (cudaStream_t)stream)));
+    return OVL_OK;
+}
+
+int ovl_filter_fill(ovl_ctx* ctx, const int32_t* edges, const int64_t* keep_off, int64_t E, int32_t min_weight, int32_t* out,
+                    void* stream) {
+    if (!ctx || (E > 0 && (!edges || !keep_off || !out))) return fail(OVL_E_ARG, "ovl_filter_fill: null argument");
+    if (E <= 0) return OVL_OK;
+    filter_edges_kernel<<<grid_for(E, 256), 256, 0, (cudaStream_t)stream>>>((const int4*)edges, keep_off, E, min_weight, (int4*)out);
+    LAUNCH_CHECK("filter_edges_kernel");
+    return OVL_OK;
+}
+
 // ---------------------------------------------------------------- K7
 size_t ovl_align_pair_workspace_bytes(int32_t n, int32_t m) {
     if (n < 0) n = 0;

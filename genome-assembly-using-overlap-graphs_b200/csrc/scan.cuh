@@ -29,6 +29,13 @@ struct CopyProduct {
     }
 };
 
+// 1 when edge row e is kept by the score filter of the all-pairs builders (overlapGraphs.py:225, :347)
+struct EdgeKept {
+    const int4* edges;
+    int32_t min_weight;
+    __device__ __forceinline__ int64_t operator()(int64_t e) const { return edges[e].z >= min_weight ? 1 : 0; }
+};
+
 template <typename TO>
 __device__ __forceinline__ TO block_exclusive_scan(TO v, TO* total, TO* smem /*[8+1]*/) {
     // inclusive warp scan of per-thread sums, then across the 8 warps

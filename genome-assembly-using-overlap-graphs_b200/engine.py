@@ -301,6 +301,22 @@ class OverlapEngine:
             self.launches += 1
         return edges[:E * 4].view(E, 4)
 
+    def filter_edges(self, edges: torch.Tensor, min_weight: int) -> torch.Tensor:
+        """Keep the edge rows with weight >= min_weight, order preserved (overlapGraphs.py:225, :347)."""
+        E = int(edges.shape[0])
+        if E == 0:
+            return edges
+        st = self._stream()
+        keep_off = self._empty(E + 1, torch.int64)
+        ws_bytes = int(nat.lib.ovl_filter_workspace_bytes(E))
+        ws = self._empty(ws_bytes, torch.uint8)
+        nat.check(nat.lib.ovl_filter_count(self._ctx, _ptr(edges), E, int(min_weight), _ptr(keep_off), _ptr(ws), ws_bytes, st))
+        kept = int(keep_off[E].item())
+        out = self._empty(kept * 4, torch.int32)
+        nat.check(nat.lib.ovl_filter_fill(self._ctx, _ptr(edges), _ptr(keep_off), E, int(min_weight), _ptr(out), st))
+        self.launches += 2 if E <= 16384 else 4
+        return out[:kept * 4].view(kept, 4)
+
     # ------------------------------------------------------------------ whole path
     def overlap_edges_device(self, rs: ReadSet, k: int, copies: Optional[torch.Tensor] = None,
                              node_off: Optional[torch.Tensor] = None, shard: Tuple[int, int] = (0, 1),
@@ -329,7 +345,8 @@ class OverlapEngine:
 
     def overlap_edges(self, bases, offsets, counts=None, k: int = 5, shard: Tuple[int, int] = (0, 1),
                       match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT,
-                      stats: Optional[dict] = None, to_host: bool = True, reuse_host_buffer: bool = False):
+                      stats: Optional[dict] = None, to_host: bool = True, reuse_host_buffer: bool = False,
+                      min_weight: Optional[int] = None, pairs=None):
         """HOST buffers in, HOST edge rows out: unique reads (ASCII bytes + offsets) and their
         multiplicities -> int32[E, 4] (node_a, node_b, weight, end_position) in the reference's
         insertion order.  This is the call the drop-in graph builder makes."""
@@ -344,7 +361,14 @@ class OverlapEngine:
                 np.cumsum(counts_np, out=no[1:])
                 copies = self._to_device(counts_np, torch.int32)
                 node_off = self._to_device(no, torch.int64)
-        edges = self.overlap_edges_device(rs, k, copies, node_off, shard, match_score, mismatch, indel, stats)
+        if pairs is not None:        # caller-supplied unique-read index pairs instead of the k-mer join
+            pa = self._to_device(pairs[0], torch.int32)
+            pb = self._to_device(pairs[1], torch.int32)
+            edges = self.overlap_edges_fused(rs, pa, pb, copies, node_off, match_score, mismatch, indel)
+        else:
+            edges = self.overlap_edges_device(rs, k, copies, node_off, shard, match_score, mismatch, indel, stats)
+        if min_weight is not None:
+            edges = self.filter_edges(edges, min_weight)
         self.check_alphabet(rs)
         if not to_host:
             return edges

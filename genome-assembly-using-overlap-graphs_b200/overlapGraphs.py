@@ -41,10 +41,10 @@ def _flatten(uniq):
     return bases, offsets
 
 
-def overlap_edge_rows(reads, k=5, _reuse_host_buffer=False):
+def overlap_edge_rows(reads, k=5, _reuse_host_buffer=False, min_weight=None):
     """The device part of the builder: returns (read_copies, uniq, counts, edges) where edges
     is int32[E, 4] = (node_a, node_b, weight, end_position) in insertion order and node ids
-    number the copies in (uid, copy) order."""
+    number the copies in (uid, copy) order.  min_weight keeps only rows with weight >= it."""
     assert k >= 0, "k-mer length must be non-negative"               # overlapGraphs.py:17
     read_copies = {}
     for read in reads:                                               # overlapGraphs.py:18-20
@@ -58,13 +58,11 @@ def overlap_edge_rows(reads, k=5, _reuse_host_buffer=False):
         return read_copies, uniq, counts, np.zeros((0, 4), np.int32)
     bases, offsets = _flatten(uniq)
     eng = _engine.get_engine()
-    edges = eng.overlap_edges(bases, offsets, counts, k, reuse_host_buffer=_reuse_host_buffer)
+    edges = eng.overlap_edges(bases, offsets, counts, k, reuse_host_buffer=_reuse_host_buffer, min_weight=min_weight)
     return read_copies, uniq, counts, edges
 
 
-def construct_overlap_graph_nx_k(reads, k=5):
-    """Construct the overlap graph -- see overlapGraphs.py:5-16 for the contract."""
-    read_copies, uniq, counts, edges = overlap_edge_rows(reads, k, _reuse_host_buffer=True)   # consumed right below
+def _graph_from_rows(uniq, counts, edges):
     overlap_graph = nx.DiGraph()
     names = [f"{read}_{c}" for read, cnt in zip(uniq, counts.tolist()) for c in range(cnt)]   # :25-28
     overlap_graph.add_nodes_from(names)
@@ -73,7 +71,70 @@ def construct_overlap_graph_nx_k(reads, k=5):
         overlap_graph.add_edges_from(
             (names[u], names[v], {"weight": w, "end_position": e})
             for u, v, w, e in zip(cols[0], cols[1], cols[2], cols[3]))
-    return overlap_graph, read_copies
+    return overlap_graph
+
+
+def construct_overlap_graph_nx_k(reads, k=5):
+    """Construct the overlap graph -- see overlapGraphs.py:5-16 for the contract."""
+    read_copies, uniq, counts, edges = overlap_edge_rows(reads, k, _reuse_host_buffer=True)   # consumed right below
+    return _graph_from_rows(uniq, counts, edges), read_copies
+
+
+def construct_overlap_graph_string(reads):
+    """Drop-in for overlapGraphs.py:196-232: every ordered pair of distinct reads is aligned and
+    edges are kept only for score > 0 (same node naming and copy expansion as the k-mer builder)."""
+    read_copies, uniq, counts, edges = overlap_edge_rows(reads, 0, _reuse_host_buffer=True, min_weight=1)
+    return _graph_from_rows(uniq, counts, edges), read_copies
+
+
+def construct_string_graph(reads):
+    """Drop-in for overlapGraphs.py:332-351: nodes are the reads themselves; for every position pair
+    i < j of the READ LIST (duplicates included, itertools.combinations order) the pair
+    (reads[i], reads[j]) is aligned and an edge is added when score > 0.
+
+    A pair of distinct strings (u, v) is visited iff some occurrence of u precedes some occurrence
+    of v; (u, u) is visited iff u occurs twice.  Each needed pair is aligned once on the GPU; the
+    graph is then assembled in the reference's insertion order: sources by first appearance, the
+    successors of u by their first occurrence after u's first occurrence."""
+    graph = nx.DiGraph()
+    first, last, order = {}, {}, []
+    for pos, read in enumerate(reads):
+        if not isinstance(read, str):
+            raise TypeError("reads must be str")
+        if read not in first:
+            first[read] = pos
+            order.append(read)
+        last[read] = pos
+    graph.add_nodes_from(order)
+    U = len(order)
+    if U == 0 or len(reads) < 2:
+        print(f"graph: {graph.edges}")                               # overlapGraphs.py:350
+        return graph
+    uid = {r: i for i, r in enumerate(order)}
+    pos_uid = np.fromiter((uid[r] for r in reads), dtype=np.int64, count=len(reads))
+    first_pos = np.fromiter((first[r] for r in order), dtype=np.int64, count=U)
+    last_pos = np.fromiter((last[r] for r in order), dtype=np.int64, count=U)
+    pa, pb = [], []
+    for u in range(U):
+        sub = pos_uid[first_pos[u] + 1:]
+        if sub.size == 0:
+            continue
+        vals, idx = np.unique(sub, return_index=True)
+        succ = vals[np.argsort(idx, kind="stable")]                  # first occurrence after u's first occurrence
+        pa.append(np.full(succ.shape[0], u, dtype=np.int32))
+        pb.append(succ.astype(np.int32))
+    pa = np.concatenate(pa) if pa else np.zeros(0, np.int32)
+    pb = np.concatenate(pb) if pb else np.zeros(0, np.int32)
+    assert np.all((last_pos[pb] > first_pos[pa]))
+    if pa.size:
+        bases, offsets = _flatten(order)
+        eng = _engine.get_engine()
+        rows = eng.overlap_edges(bases, offsets, None, 0, pairs=(pa, pb), min_weight=1, reuse_host_buffer=True)
+        cols = rows.T.tolist()
+        graph.add_edges_from((order[u], order[v], {"weight": w, "end_position": e})
+                             for u, v, w, e in zip(cols[0], cols[1], cols[2], cols[3]))
+    print(f"graph: {graph.edges}")                                   # overlapGraphs.py:350
+    return graph
 
 
 def __getattr__(name):

@@ -135,6 +135,15 @@ int ovl_expand_unit(ovl_ctx *ctx, const int32_t *pair_a, const int32_t *pair_b,
                     const int32_t *score, const int32_t *end, int64_t P, int32_t *edges,
                     void *stream);
 
+/* The `if score > 0` of the all-pairs builders (overlapGraphs.py:225, :347): order-preserving
+ * compaction of edge rows with weight >= min_weight.  ovl_filter_count writes the exclusive scan
+ * keep_off[E+1] of the keep flags (keep_off[E] = rows kept); ovl_filter_fill writes them. */
+size_t ovl_filter_workspace_bytes(int64_t E);
+int ovl_filter_count(ovl_ctx *ctx, const int32_t *edges, int64_t E, int32_t min_weight,
+                     int64_t *keep_off, void *workspace, size_t workspace_bytes, void *stream);
+int ovl_filter_fill(ovl_ctx *ctx, const int32_t *edges, const int64_t *keep_off, int64_t E,
+                    int32_t min_weight, int32_t *out, void *stream);
+
 /* K7: one pair with traceback: everything aligners.py:27-76 computes, for the single-pair
  * drop-in.  s, t are int32 code points (any alphabet); arithmetic is the reference's (int64
  * candidates, int32 storage).  result[0..2] = (best_score, alignment_end_position, n_ops);

@@ -195,6 +195,31 @@ def construct_overlap_graph(reads: Sequence[str], k: int = 5, nthreads: int = 0,
     return nodes, edges, read_copies
 
 
+def construct_overlap_graph_string(reads: Sequence[str], nthreads: int = 0):
+    """Restates overlapGraphs.py:196-232: all ordered pairs of distinct reads, edges for score > 0."""
+    nodes, edges, read_copies = construct_overlap_graph(reads, 0, nthreads=nthreads)
+    return nodes, [e for e in edges if e[2] > 0], read_copies
+
+
+def construct_string_graph(reads: Sequence[str]):
+    """Restates overlapGraphs.py:332-351 literally: combinations over the read list, score > 0.
+    Returns a NetworkX DiGraph built with the same call sequence as the reference."""
+    import itertools
+    import networkx as nx
+    g = nx.DiGraph()
+    for r in reads:
+        g.add_node(r)
+    cache: Dict[Tuple[str, str], Tuple[int, int]] = {}
+    for a, b in itertools.combinations(reads, 2):
+        if (a, b) not in cache:
+            out = overlap_alignment(a, b)
+            cache[(a, b)] = (out[3], out[4])
+        score, end = cache[(a, b)]
+        if score > 0:
+            g.add_edge(a, b, weight=score, end_position=end)
+    return g
+
+
 def to_networkx(nodes, edges):
     import networkx as nx
     g = nx.DiGraph()

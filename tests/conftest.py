@@ -39,6 +39,12 @@ def golden_graphs():
         return json.load(fh)["cases"]
 
 
+@pytest.fixture(scope="session")
+def golden_allpairs():
+    with open(os.path.join(GOLDEN, "allpairs.json")) as fh:
+        return json.load(fh)["cases"]
+
+
 def has_cuda() -> bool:
     try:
         import torch

@@ -164,6 +164,34 @@ def make_graphs():
     return cases
 
 
+def make_allpairs():
+    """overlapGraphs.construct_overlap_graph_string (:196-232) and construct_string_graph (:332-351)."""
+    import contextlib
+    import io
+    rng = random.Random(5150)
+    out = []
+    toy = ['TGTTC', 'TGCGT', 'ACGTG', 'CACGT', 'AGCAC', 'GATAG', 'CGATA', 'GTACG', 'CGTAC', 'ATGCG']
+    g = rand_seq(rng, 90)
+    dup_reads = sim_reads(rng, g, 60, 14, 0.03) + ["ACG", "ACG", "A", "TTTTTTTT", "TTTTTTTT", "GGGG", "CCCC"]
+    for name, reads in [("toy", toy), ("dups", dup_reads), ("two", ["ACGT", "ACGT"]), ("one", ["ACGT"]), ("empty", [])]:
+        G, rc = ref_graphs.construct_overlap_graph_string(list(reads))
+        nodes = list(G.nodes)
+        idx = {n: i for i, n in enumerate(nodes)}
+        case = {"name": name, "reads": list(reads), "string_nodes": nodes,
+                "string_read_copies": [[r, c] for r, c in rc.items()],
+                "string_edges": [[idx[u], idx[v], d["weight"], d["end_position"]] for u, v, d in G.edges(data=True)]}
+        with contextlib.redirect_stdout(io.StringIO()) as buf:
+            H = ref_graphs.construct_string_graph(list(reads))
+        hn = list(H.nodes)
+        hidx = {n: i for i, n in enumerate(hn)}
+        case["sg_nodes"] = hn
+        case["sg_edges"] = [[hidx[u], hidx[v], d["weight"], d["end_position"]] for u, v, d in H.edges(data=True)]
+        case["sg_pred"] = [[hidx[p] for p in H.pred[n]] for n in hn]
+        case["sg_stdout_sha256"] = hashlib.sha256(buf.getvalue().encode()).hexdigest()
+        out.append(case)
+    return out
+
+
 if __name__ == "__main__":
     pairs = make_pairs()
     with open(os.path.join(HERE, "pairs.json"), "w") as fh:
@@ -174,5 +202,11 @@ if __name__ == "__main__":
         json.dump({"generator": "tests/golden/make_golden.py",
                    "source": "live reference overlapGraphs.construct_overlap_graph_nx_k",
                    "cases": graphs}, fh, separators=(",", ":"))
+    allp = make_allpairs()
+    with open(os.path.join(HERE, "allpairs.json"), "w") as fh:
+        json.dump({"generator": "tests/golden/make_golden.py",
+                   "source": "live reference overlapGraphs.construct_overlap_graph_string / construct_string_graph",
+                   "cases": allp}, fh, separators=(",", ":"))
+    print(len(allp), "all-pairs cases")
     print(len(pairs), "pair cases;", len(graphs), "graph cases;",
           sum(len(c["edges"]) for c in graphs), "edges")

@@ -264,6 +264,46 @@ def test_graph_builder_golden(golden_graphs, nat):
             assert type(d["weight"]) is int and type(d["end_position"]) is int
 
 
+def test_allpairs_builders_golden(golden_allpairs, capsys):
+    """Drop-ins of construct_overlap_graph_string / construct_string_graph vs the live reference's output."""
+    g = load_pkg("overlapGraphs")
+    for c in golden_allpairs:
+        G, rc = g.construct_overlap_graph_string(c["reads"])
+        nodes = list(G.nodes)
+        assert nodes == c["string_nodes"], c["name"]
+        assert [[r, n] for r, n in rc.items()] == c["string_read_copies"]
+        idx = {n: i for i, n in enumerate(nodes)}
+        assert [[idx[u], idx[v], d["weight"], d["end_position"]] for u, v, d in G.edges(data=True)] == c["string_edges"], c["name"]
+        capsys.readouterr()
+        H = g.construct_string_graph(c["reads"])
+        out = capsys.readouterr().out
+        hn = list(H.nodes)
+        assert hn == c["sg_nodes"], c["name"]
+        hidx = {n: i for i, n in enumerate(hn)}
+        assert [[hidx[u], hidx[v], d["weight"], d["end_position"]] for u, v, d in H.edges(data=True)] == c["sg_edges"], c["name"]
+        assert [[hidx[p] for p in H.pred[n]] for n in hn] == c["sg_pred"], c["name"]
+        assert hashlib.sha256(out.encode()).hexdigest() == c["sg_stdout_sha256"], c["name"]
+        for _, _, d in list(H.edges(data=True))[:3]:
+            assert type(d["weight"]) is int and type(d["end_position"]) is int
+
+
+def test_allpairs_builders_vs_oracle_random(eng, capsys):
+    g = load_pkg("overlapGraphs")
+    rng = random.Random(77)
+    reads = overlapping_reads(rng, 120, 80, 20, 0.02) + rand_reads(rng, 10, 1, 8)
+    G, rc = g.construct_overlap_graph_string(reads)
+    nodes, edges, rc2 = orc.construct_overlap_graph_string(reads)
+    G2 = orc.to_networkx(nodes, edges)
+    assert list(rc.items()) == list(rc2.items()) and list(G.nodes) == list(G2.nodes)
+    assert list(G.edges(data=True)) == list(G2.edges(data=True))
+    H = g.construct_string_graph(reads)
+    H2 = orc.construct_string_graph(reads)
+    capsys.readouterr()
+    assert list(H.nodes) == list(H2.nodes)
+    assert list(H.edges(data=True)) == list(H2.edges(data=True))
+    assert [list(H.pred[n]) for n in H.nodes] == [list(H2.pred[n]) for n in H2.nodes]
+
+
 def test_graph_builder_vs_oracle_with_duplicates(eng):
     g = load_pkg("overlapGraphs")
     rng = random.Random(2024)

@@ -64,6 +64,23 @@ def test_graphs_match_reference_golden(golden_graphs):
         assert got == c["edges"], c["name"]
 
 
+def test_allpairs_builders_match_reference_golden(golden_allpairs):
+    """overlapGraphs.construct_overlap_graph_string (:196-232) and construct_string_graph (:332-351)."""
+    for c in golden_allpairs:
+        nodes, edges, rc = orc.construct_overlap_graph_string(c["reads"])
+        assert nodes == c["string_nodes"], c["name"]
+        assert [[r, n] for r, n in rc.items()] == c["string_read_copies"]
+        idx = {n: i for i, n in enumerate(nodes)}
+        got = sorted(([idx[u], idx[v], w, e] for u, v, w, e in edges), key=lambda r: r[0])
+        assert got == c["string_edges"], c["name"]
+        H = orc.construct_string_graph(c["reads"])
+        hn = list(H.nodes)
+        assert hn == c["sg_nodes"], c["name"]
+        hidx = {n: i for i, n in enumerate(hn)}
+        assert [[hidx[u], hidx[v], d["weight"], d["end_position"]] for u, v, d in H.edges(data=True)] == c["sg_edges"]
+        assert [[hidx[p] for p in H.pred[n]] for n in hn] == c["sg_pred"]
+
+
 def test_negative_k_asserts():
     with pytest.raises(AssertionError):
         orc.construct_overlap_graph(["ACGT"], k=-1)
