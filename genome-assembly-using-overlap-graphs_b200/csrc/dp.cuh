@@ -9,6 +9,10 @@
 // sweeps the rows as a wavefront: at step k lane r computes row k-r, taking its left
 // neighbour's last column from the previous step with one __shfl_up_sync.  G*T >= longest t.
 //
+// Staging.  The 2-bit packed rows of a warp's pairs (s and t of every pair, 48 B each at l = 150)
+// are brought into shared memory by TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) that
+// complete on one mbarrier per warp; everything after that reads shared memory only.
+//
 // Cost space.  The recurrence is evaluated on  C[i][j] = beta + i*maxs - H[i][j]  with
 // maxs = max(match, mismatch):
 //     diag:  C[i-1][j-1] + dc,   dc = maxs - score  in {0, |match - mismatch|}
@@ -91,12 +95,32 @@ __device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t one, uint32_t c
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(c));
     return d;
 }
-__device__ __forceinline__ uint32_t base_code(const uint32_t* __restrict__ row, int i) {
+__device__ __forceinline__ uint32_t base_code(const uint32_t* row, int i) {
     return (row[i >> 4] >> ((i & 15) * 2)) & 3u;
 }
 __device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; }
 __device__ __forceinline__ constexpr bool dp_form2(int c) {
     return OVL_DP_F2_NUM > 0 && (c * OVL_DP_F2_NUM) % OVL_DP_F2_DEN < OVL_DP_F2_NUM;
+}
+
+// ---- TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
 }
 
 // rows of the per-couple LUT array, padded so that consecutive couples start 8 banks apart
@@ -114,7 +138,12 @@ __global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(
     constexpr int PAIRS = PK ? 2 : 1;
     constexpr int GROUPS_PER_WARP = 32 / G;
     constexpr int GROUPS_PER_CTA = (kDpThreads / 32) * GROUPS_PER_WARP;
-    extern __shared__ uint2 smem_lut[];                // [GROUPS_PER_CTA][lut_rows] (lutA, lutB)
+    constexpr int ROWS_PER_GROUP = 2 * PAIRS;          // s and t of each pair
+    // dynamic shared memory: [packed read rows][per-row score tables][one mbarrier per warp]
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* smem_rows = reinterpret_cast<uint32_t*>(smem_raw);              // [GROUPS_PER_CTA][ROWS_PER_GROUP][row_words]
+    uint2* smem_lut = reinterpret_cast<uint2*>(smem_rows + (size_t)GROUPS_PER_CTA * ROWS_PER_GROUP * row_words);
+    uint64_t* smem_bar = reinterpret_cast<uint64_t*>(smem_lut + (size_t)GROUPS_PER_CTA * lut_rows);
 
     const unsigned lane = lane_id();
     const int r = lane % G;                            // lane within the group
@@ -122,9 +151,33 @@ __global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(
     const int64_t grp = (int64_t)blockIdx.x * GROUPS_PER_CTA + gib;
     const int64_t p0 = grp * PAIRS;
 
+    // ---- stage the packed reads of this warp's pairs in shared memory with TMA bulk copies:
+    // one 1-D copy per read row (row_words*4 bytes, 16-byte aligned at both ends), all completing
+    // on the warp's mbarrier.  Lane l issues the copies of rows l, l+32, ... of the warp.
+    const int wib = threadIdx.x >> 5;
+    const uint32_t bar = smem_u32(smem_bar + wib);
+    uint32_t* warp_rows = smem_rows + (size_t)wib * GROUPS_PER_WARP * ROWS_PER_GROUP * row_words;
+    {
+        constexpr int NROWS = GROUPS_PER_WARP * ROWS_PER_GROUP;
+        const uint32_t row_bytes = (uint32_t)row_words * 4u;
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, NROWS * row_bytes);
+        }
+        __syncwarp();
+        const int64_t warp_p0 = ((int64_t)blockIdx.x * GROUPS_PER_CTA + (int64_t)wib * GROUPS_PER_WARP) * PAIRS;
+        for (int idx = lane; idx < NROWS; idx += 32) {
+            int64_t p = warp_p0 + idx / 2;                  // rows come in (s, t) order per pair
+            int32_t uid = 0;
+            if (p < P) uid = (idx & 1) ? pair_b[p] : pair_a[p];
+            tma_load_1d(smem_u32(warp_rows + (size_t)idx * row_words), packed + (size_t)uid * row_words, row_bytes, bar);
+        }
+    }
+
     int32_t n[PAIRS], m[PAIRS];
     const uint32_t* srow[PAIRS];
     const uint32_t* trow[PAIRS];
+    uint32_t* grp_rows = smem_rows + (size_t)gib * ROWS_PER_GROUP * row_words;
 #pragma unroll
     for (int h = 0; h < PAIRS; ++h) {
         int64_t p = p0 + h;
@@ -132,9 +185,10 @@ __global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(
         int32_t a = live ? pair_a[p] : 0, b = live ? pair_b[p] : 0;
         n[h] = live ? len[a] : 0;
         m[h] = live ? len[b] : 0;
-        srow[h] = packed + (size_t)a * row_words;
-        trow[h] = packed + (size_t)b * row_words;
+        srow[h] = grp_rows + (size_t)(2 * h) * row_words;
+        trow[h] = grp_rows + (size_t)(2 * h + 1) * row_words;
     }
+    while (!mbar_try_wait(bar, 0)) { }                      // the rows have landed (phase 0 completes once)
     const int nmax = PK ? max(n[0], n[PAIRS - 1]) : n[0];
     const int max_col = row_words * 16 - 1;
 

@@ -329,7 +329,9 @@ int launch_dp(const uint32_t* packed, int32_t row_words, const int32_t* len, con
     int64_t grid = (groups + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA;
     if (grid > 0x7fffffffll) return fail(OVL_E_ARG, "ovl_overlap_dp: too many pairs for one launch (%lld)", (long long)P);
     int lut_rows = dp_lut_rows(max_len);
-    size_t smem = (size_t)GROUPS_PER_CTA * lut_rows * sizeof(uint2);
+    size_t smem = (size_t)GROUPS_PER_CTA * 2 * PAIRS * row_words * sizeof(uint32_t)       // TMA-staged read rows
+                + (size_t)GROUPS_PER_CTA * lut_rows * sizeof(uint2)                       // per-row score tables
+                + (kDpThreads / 32) * sizeof(uint64_t);                                   // one mbarrier per warp
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(overlap_dp_kernel<G, T, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(OVL_E_CUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));

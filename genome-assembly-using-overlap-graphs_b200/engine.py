@@ -78,9 +78,16 @@ class OverlapEngine:
     def _empty(self, n: int, dtype) -> torch.Tensor:
         return torch.empty(max(int(n), 1), dtype=dtype, device=self.device)
 
+    @staticmethod
+    def _from_numpy(x: np.ndarray) -> torch.Tensor:
+        x = np.ascontiguousarray(x)
+        if not x.flags.writeable:          # e.g. np.frombuffer over bytes: torch wants a writable array
+            x = x.copy()
+        return torch.from_numpy(x)
+
     def _to_device(self, x, dtype) -> torch.Tensor:
         if isinstance(x, np.ndarray):
-            x = torch.from_numpy(np.ascontiguousarray(x))
+            x = self._from_numpy(x)
         if x.dtype != dtype:
             x = x.to(dtype)
         return x.to(self.device, non_blocking=True)
@@ -103,7 +110,7 @@ class OverlapEngine:
         total = int(bases.shape[0]) if U > 0 else 0
         ascii_dev = torch.empty(total + 64, dtype=torch.uint8, device=self.device)   # 32 B slack for K0
         if total:
-            src = torch.from_numpy(np.ascontiguousarray(bases)) if isinstance(bases, np.ndarray) else bases
+            src = self._from_numpy(bases) if isinstance(bases, np.ndarray) else bases
             ascii_dev[:total].copy_(src[:total], non_blocking=True)
         off_dev = self._to_device(offsets, torch.int64)
         return self.pack_reads(ascii_dev, off_dev, U, max_len)
