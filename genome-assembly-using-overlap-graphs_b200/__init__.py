@@ -22,7 +22,8 @@ def __getattr__(name):
     if name in ("overlap_alignment",):
         from .aligners import overlap_alignment
         return overlap_alignment
-    if name in ("construct_overlap_graph_nx_k", "construct_overlap_graph_string", "construct_string_graph"):
+    if name in ("construct_overlap_graph_nx_k", "construct_overlap_graph_string", "construct_string_graph",
+                "construct_overlap_graphs_batch"):
         from . import overlapGraphs
         return getattr(overlapGraphs, name)
     if name in ("OverlapEngine", "get_engine"):

@@ -47,9 +47,9 @@ _SIGS = {
     "ovl_ctx_sm_count": (ctypes.c_int, [_vp]),
     "ovl_row_words": (_i32, [_i32]),
     "ovl_pack_reads": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
-    "ovl_kmer_keys": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "ovl_kmer_keys": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "ovl_index_workspace_bytes": (_sz, [_i64]),
-    "ovl_index_build": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ovl_index_build": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ovl_join_workspace_bytes": (_sz, [_i64]),
     "ovl_join_count": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ovl_join_fill": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
@@ -68,6 +68,8 @@ _SIGS = {
     "ovl_filter_fill": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "ovl_align_pair_workspace_bytes": (_sz, [_i32, _i32]),
     "ovl_align_pair": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp, _vp, _vp]),
+    "ovl_local_align_workspace_bytes": (_sz, [_i32, _i32]),
+    "ovl_local_align": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp, _vp, _vp]),
     "ovl_int_peak_probe": (ctypes.c_int, [_vp, _i32, _i32, ctypes.POINTER(ctypes.c_double),
                                           ctypes.POINTER(ctypes.c_double)]),
 }

@@ -60,6 +60,51 @@ def overlap_alignment(s, t, match_score=10, mismatch=-1, indel=-2 ** 31):
     return alignment_to_print, align_s, align_t, int(score), int(end)
 
 
+def local_alignment(query, reference, match_score=10, mismatch=-1, indel=-1):
+    """Best local alignment of `query` in `reference` -- drop-in for aligners.py:85-167.
+
+    Returns (alignment_to_print, aligned_reference, aligned_query, best_score, start_pos, end_pos).
+    """
+    if not isinstance(query, str) or not isinstance(reference, str):
+        raise TypeError("local_alignment expects str arguments (the reference raises a Numba TypingError)")
+    for name, v in (("match_score", match_score), ("mismatch", mismatch), ("indel", indel)):
+        if isinstance(v, bool) or not isinstance(v, (int, np.integer)):
+            raise TypeError(f"{name} must be an integer")
+    eng = _engine.get_engine()
+    score, start, end, best_i, ops = eng.local_align(_codes(query), _codes(reference), int(match_score),
+                                                     int(mismatch), int(indel))
+    i, j = best_i, end
+    a_q, a_r = [], []
+    for op in ops.tolist():                                           # aligners.py:143-160
+        if op == 1:
+            a_q.append(query[i - 1]); a_r.append(reference[j - 1]); i -= 1; j -= 1
+        elif op == 2:
+            a_q.append(query[i - 1]); a_r.append("-"); i -= 1
+        else:
+            a_q.append("-"); a_r.append(reference[j - 1]); j -= 1
+    aligned_query = "".join(reversed(a_q))
+    aligned_reference = "".join(reversed(a_r))
+    alignment_to_print = (f"\nTarget:   {aligned_reference}\n          {'|' * len(aligned_reference)}\nQuery:    "
+                          f"{aligned_query}")                          # aligners.py:166-167
+    return alignment_to_print, aligned_reference, aligned_query, int(score), int(start), int(end)
+
+
+def align_read_or_contig_to_reference(read_or_contig, reference_genome, read_length, match_score=10, mismatch=-1,
+                                      indel=-1):
+    """Drop-in for aligners.py:170-202: local alignment against the genome, or -- for a sequence
+    shorter than a read -- against the genome's last len(sequence) bases."""
+    n = len(read_or_contig)
+    if n < read_length:
+        to_print, aligned_ref, aligned, score, start, end = local_alignment(
+            read_or_contig, reference_genome[-n:], match_score, mismatch, indel)
+        start = len(reference_genome) - n + start
+        end = len(reference_genome) - n + end
+    else:
+        to_print, aligned_ref, aligned, score, start, end = local_alignment(
+            read_or_contig, reference_genome, match_score, mismatch, indel)
+    return to_print, aligned_ref, aligned, score, start, end
+
+
 def __getattr__(name):
     ref = _engine.reference_module("aligners")
     if ref is not None and hasattr(ref, name):

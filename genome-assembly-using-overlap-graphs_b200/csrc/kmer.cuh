@@ -99,8 +99,12 @@ __device__ __forceinline__ uint64_t extract_bits64(const uint32_t* __restrict__ 
     return ((uint64_t)hi << 32) | lo;
 }
 
+// `segment` (optional) tags every read with the read set it belongs to; the tag goes into the key
+// bits above the k-mer, so that one index / one join serves many independent read sets at once
+// (the parameter sweep of experiments.py) without ever pairing reads across sets.
 __global__ void __launch_bounds__(256) kmer_keys_kernel(const uint32_t* __restrict__ packed, int row_words,
                                                         const int32_t* __restrict__ len, int64_t U, int k,
+                                                        const int32_t* __restrict__ segment,
                                                         uint64_t* __restrict__ prefix_key,
                                                         uint64_t* __restrict__ suffix_key) {
     int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,6 +116,11 @@ __global__ void __launch_bounds__(256) kmer_keys_kernel(const uint32_t* __restri
         uint64_t mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
         pk = (((uint64_t)row[1] << 32) | row[0]) & mask;
         sk = extract_bits64(row, row_words, 2 * (n - k)) & mask;
+        if (segment != nullptr) {
+            uint64_t tag = (uint64_t)(uint32_t)segment[u] << (2 * k);
+            pk |= tag;
+            sk |= tag;
+        }
     }
     prefix_key[u] = pk;
     suffix_key[u] = sk;

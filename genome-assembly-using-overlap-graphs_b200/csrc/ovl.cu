@@ -105,11 +105,12 @@ int ovl_pack_reads(ovl_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, i
 }
 
 int ovl_kmer_keys(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, int64_t U, int32_t k,
-                  uint64_t* prefix_key, uint64_t* suffix_key, void* stream) {
+                  const int32_t* segment, uint64_t* prefix_key, uint64_t* suffix_key, void* stream) {
     if (!ctx || !packed || !len || !prefix_key || !suffix_key) return fail(OVL_E_ARG, "ovl_kmer_keys: null argument");
     if (k < 1 || k > OVL_MAX_K) return fail(OVL_E_UNSUPPORTED, "ovl_kmer_keys: k=%d outside 1..%d", k, OVL_MAX_K);
     if (U <= 0) return OVL_OK;
-    kmer_keys_kernel<<<grid_for(U, 256), 256, 0, (cudaStream_t)stream>>>(packed, row_words, len, U, k, prefix_key, suffix_key);
+    if (segment && k > 31) return fail(OVL_E_UNSUPPORTED, "ovl_kmer_keys: segment tags need 2k < 64 (k=%d)", k);
+    kmer_keys_kernel<<<grid_for(U, 256), 256, 0, (cudaStream_t)stream>>>(packed, row_words, len, U, k, segment, prefix_key, suffix_key);
     LAUNCH_CHECK("kmer_keys_kernel");
     return OVL_OK;
 }
@@ -129,7 +130,7 @@ size_t ovl_index_workspace_bytes(int64_t U) {
     return hist + sums + keys + uids + 256;
 }
 
-int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len, int64_t U, int32_t k, uint64_t* sorted_key,
+int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len, int64_t U, int32_t k, int32_t key_bits, uint64_t* sorted_key,
                     uint32_t* sorted_uid, int64_t* n_indexed, void* workspace, size_t workspace_bytes, void* stream) {
     if (!ctx || !prefix_key || !len || !sorted_key || !sorted_uid || !n_indexed || !workspace) return fail(OVL_E_ARG, "ovl_index_build: null argument");
     if (k < 1 || k > OVL_MAX_K) return fail(OVL_E_UNSUPPORTED, "ovl_index_build: k=%d outside 1..%d", k, OVL_MAX_K);
@@ -143,7 +144,9 @@ int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len
     uint64_t* tmp_key = (uint64_t*)ws;            ws += align256((size_t)U * sizeof(uint64_t));
     uint32_t* tmp_uid = (uint32_t*)ws;
 
-    int passes = (2 * k + 7) / 8;
+    if (key_bits <= 0) key_bits = 2 * k;                 // no segment tag above the k-mer
+    if (key_bits < 2 * k || key_bits > 64) return fail(OVL_E_ARG, "ovl_index_build: key_bits=%d outside [2k, 64]", key_bits);
+    int passes = (key_bits + 7) / 8;
     // ping-pong so that the last pass lands in (sorted_key, sorted_uid)
     uint64_t* kbuf[2] = {sorted_key, tmp_key};
     uint32_t* ubuf[2] = {sorted_uid, tmp_uid};
@@ -490,6 +493,27 @@ int ovl_align_pair(ovl_ctx* ctx, const int32_t* s, int32_t n, const int32_t* t, 
     int8_t* tb = (int8_t*)(ws + align256(((size_t)3 * (n + 1) + (size_t)(m + 1)) * sizeof(int32_t)));
     align_pair_kernel<<<1, kAlignThreads, 0, (cudaStream_t)stream>>>(s, n, t, m, match, mismatch, indel, diag, last_row, tb, result, ops);
     LAUNCH_CHECK("align_pair_kernel");
+    return OVL_OK;
+}
+
+// ---------------------------------------------------------------- K8
+size_t ovl_local_align_workspace_bytes(int32_t n, int32_t m) {
+    if (n < 0) n = 0;
+    if (m < 0) m = 0;
+    return align256((size_t)3 * (n + 1) * sizeof(int32_t)) + align256((size_t)(n + 1) * (m + 1)) + 256;
+}
+
+int ovl_local_align(ovl_ctx* ctx, const int32_t* query, int32_t n, const int32_t* reference, int32_t m, int64_t match,
+                    int64_t mismatch, int64_t indel, void* workspace, size_t workspace_bytes, int32_t* result, uint8_t* ops,
+                    void* stream) {
+    if (!ctx || !workspace || !result || !ops || (n > 0 && !query) || (m > 0 && !reference)) return fail(OVL_E_ARG, "ovl_local_align: null argument");
+    if (n < 0 || m < 0) return fail(OVL_E_ARG, "ovl_local_align: negative length");
+    if (workspace_bytes < ovl_local_align_workspace_bytes(n, m)) return fail(OVL_E_ARG, "ovl_local_align: workspace too small");
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    int32_t* diag = (int32_t*)ws;
+    int8_t* tb = (int8_t*)(ws + align256((size_t)3 * (n + 1) * sizeof(int32_t)));
+    local_align_kernel<<<1, kAlignThreads, 0, (cudaStream_t)stream>>>(query, n, reference, m, match, mismatch, indel, diag, tb, result, ops);
+    LAUNCH_CHECK("local_align_kernel");
     return OVL_OK;
 }
 

@@ -135,23 +135,32 @@ class OverlapEngine:
                                      "the 2-bit CUDA path does not support them")
 
     # ------------------------------------------------------------------ K1 + K2
-    def kmer_index(self, rs: ReadSet, k: int) -> KmerIndex:
+    def kmer_index(self, rs: ReadSet, k: int, segments: Optional[torch.Tensor] = None,
+                   n_segments: int = 1) -> KmerIndex:
+        """Prefix index (overlapGraphs.py:30-40).  `segments` (int32[U] device tensor) tags every read
+        with its read set; reads of different sets then never share a key."""
         if k < 1 or k > nat.OVL_MAX_K:
             raise nat.OvlUnsupported(f"k={k}: the k-mer index covers 1 <= k <= {nat.OVL_MAX_K}")
+        key_bits = 0
+        if segments is not None:
+            seg_bits = max(1, int(n_segments - 1).bit_length())
+            key_bits = 2 * k + seg_bits
+            if key_bits > 64:
+                raise nat.OvlUnsupported(f"k={k} with {n_segments} read sets needs {key_bits} key bits (> 64)")
         U = rs.n_reads
         pk = self._empty(U, torch.int64)
         sk = self._empty(U, torch.int64)
         nat.check(nat.lib.ovl_kmer_keys(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length), U, k,
-                                        _ptr(pk), _ptr(sk), self._stream()))
+                                        _ptr(segments), _ptr(pk), _ptr(sk), self._stream()))
         sorted_key = self._empty(U, torch.int64)
         sorted_uid = self._empty(U, torch.int32)
         n_indexed = torch.zeros(1, dtype=torch.int64, device=self.device)
         ws_bytes = int(nat.lib.ovl_index_workspace_bytes(U))
         ws = self._empty(ws_bytes, torch.uint8)
-        nat.check(nat.lib.ovl_index_build(self._ctx, _ptr(pk), _ptr(rs.length), U, k, _ptr(sorted_key), _ptr(sorted_uid),
+        nat.check(nat.lib.ovl_index_build(self._ctx, _ptr(pk), _ptr(rs.length), U, k, key_bits, _ptr(sorted_key), _ptr(sorted_uid),
                                           _ptr(n_indexed), _ptr(ws), ws_bytes, self._stream()))
         if U > 0:
-            self.launches += 1 + 5 * ((2 * k + 7) // 8)
+            self.launches += 1 + 5 * (((key_bits or 2 * k) + 7) // 8)
         return KmerIndex(k, pk, sk, sorted_key, sorted_uid, n_indexed)
 
     # ------------------------------------------------------------------ K3
@@ -277,6 +286,26 @@ class OverlapEngine:
         n_ops = int(res[2])
         return int(res[0]), int(res[1]), ops[:n_ops].cpu().numpy()
 
+    # ------------------------------------------------------------------ K8
+    def local_align(self, q_codes: np.ndarray, r_codes: np.ndarray, match_score: int = 10, mismatch: int = -1,
+                    indel: int = -1):
+        """Smith-Waterman with traceback (aligners.py:85-167).  Returns (best_score, start_pos, end_pos,
+        best_i, ops) with ops from the best cell backwards (1 diagonal, 2 up, 3 left)."""
+        n, m = int(q_codes.shape[0]), int(r_codes.shape[0])
+        both = np.concatenate([q_codes.astype(np.int32), r_codes.astype(np.int32), np.zeros(1, np.int32)])
+        dev = self._to_device(both, torch.int32)
+        ws_bytes = int(nat.lib.ovl_local_align_workspace_bytes(n, m))
+        ws = self._empty(ws_bytes, torch.uint8)
+        result = torch.zeros(8, dtype=torch.int32, device=self.device)
+        ops = self._empty(n + m + 1, torch.uint8)
+        nat.check(nat.lib.ovl_local_align(self._ctx, ctypes.c_void_p(dev.data_ptr()), n,
+                                          ctypes.c_void_p(dev.data_ptr() + 4 * n), m,
+                                          int(match_score), int(mismatch), int(indel),
+                                          _ptr(ws), ws_bytes, _ptr(result), _ptr(ops), self._stream()))
+        self.launches += 1
+        res = result.cpu().numpy()
+        return int(res[0]), int(res[1]), int(res[2]), int(res[4]), ops[:int(res[3])].cpu().numpy()
+
     # ------------------------------------------------------------------ K6
     def expand_edges(self, pair_a, pair_b, score, end, copies: Optional[torch.Tensor] = None,
                      node_off: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -328,9 +357,12 @@ class OverlapEngine:
     def overlap_edges_device(self, rs: ReadSet, k: int, copies: Optional[torch.Tensor] = None,
                              node_off: Optional[torch.Tensor] = None, shard: Tuple[int, int] = (0, 1),
                              match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT,
-                             stats: Optional[dict] = None) -> torch.Tensor:
+                             stats: Optional[dict] = None, segments: Optional[torch.Tensor] = None,
+                             n_segments: int = 1) -> torch.Tensor:
         """Reads already packed in HBM -> device edge rows (this rank's shard)."""
-        index = self.kmer_index(rs, k) if k > 0 else None
+        if segments is not None and k == 0:
+            raise nat.OvlUnsupported("batched read sets need k > 0 (k = 0 pairs every read with every other)")
+        index = self.kmer_index(rs, k, segments, n_segments) if k > 0 else None
         pair_a, pair_b, _ = self.candidate_pairs(rs, index, k, shard)
         edges = self.overlap_edges_fused(rs, pair_a, pair_b, copies, node_off, match_score, mismatch, indel)
         if stats is not None:
@@ -353,7 +385,7 @@ class OverlapEngine:
     def overlap_edges(self, bases, offsets, counts=None, k: int = 5, shard: Tuple[int, int] = (0, 1),
                       match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT,
                       stats: Optional[dict] = None, to_host: bool = True, reuse_host_buffer: bool = False,
-                      min_weight: Optional[int] = None, pairs=None):
+                      min_weight: Optional[int] = None, pairs=None, segments=None, n_segments: int = 1):
         """HOST buffers in, HOST edge rows out: unique reads (ASCII bytes + offsets) and their
         multiplicities -> int32[E, 4] (node_a, node_b, weight, end_position) in the reference's
         insertion order.  This is the call the drop-in graph builder makes."""
@@ -373,7 +405,9 @@ class OverlapEngine:
             pb = self._to_device(pairs[1], torch.int32)
             edges = self.overlap_edges_fused(rs, pa, pb, copies, node_off, match_score, mismatch, indel)
         else:
-            edges = self.overlap_edges_device(rs, k, copies, node_off, shard, match_score, mismatch, indel, stats)
+            seg_dev = self._to_device(segments, torch.int32) if segments is not None else None
+            edges = self.overlap_edges_device(rs, k, copies, node_off, shard, match_score, mismatch, indel, stats,
+                                              seg_dev, n_segments)
         if min_weight is not None:
             edges = self.filter_edges(edges, min_weight)
         self.check_alphabet(rs)

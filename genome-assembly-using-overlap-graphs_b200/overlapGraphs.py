@@ -80,6 +80,54 @@ def construct_overlap_graph_nx_k(reads, k=5):
     return _graph_from_rows(uniq, counts, edges), read_copies
 
 
+def construct_overlap_graphs_batch(read_lists, k=5):
+    """Many independent read sets in ONE GPU job (not in the reference: this is the graph-build step
+    of its parameter sweep, experiments.py:451-539, which the reference runs as one process per
+    parameter set).  Returns [construct_overlap_graph_nx_k(reads, k) for reads in read_lists] --
+    same graphs, same order -- but with one pack / index / join / DP pass over all sets: every read
+    is tagged with its set number in the key bits above the k-mer, so reads of different sets never
+    become candidates."""
+    assert k >= 0, "k-mer length must be non-negative"
+    if k == 0 or len(read_lists) <= 1:
+        return [construct_overlap_graph_nx_k(reads, k) for reads in read_lists]
+    per_set = []
+    all_uniq, seg, all_counts = [], [], []
+    for s_id, reads in enumerate(read_lists):
+        read_copies = {}
+        for read in reads:
+            read_copies[read] = read_copies.get(read, 0) + 1
+        uniq = list(read_copies.keys())
+        for r in uniq:
+            if not isinstance(r, str):
+                raise TypeError("reads must be str")
+        counts = np.fromiter(read_copies.values(), dtype=np.int32, count=len(uniq))
+        per_set.append((read_copies, uniq, counts))
+        all_uniq.extend(uniq)
+        all_counts.append(counts)
+        seg.append(np.full(len(uniq), s_id, dtype=np.int32))
+    if not all_uniq:
+        return [(nx.DiGraph(), rc) for rc, _, _ in per_set]
+    counts_all = np.concatenate(all_counts)
+    bases, offsets = _flatten(all_uniq)
+    eng = _engine.get_engine()
+    # counts are always passed so that node ids are offsets into the concatenated copy list
+    edges = eng.overlap_edges(bases, offsets, np.maximum(counts_all, 1) if counts_all.max() > 1 else None, k,
+                              reuse_host_buffer=True, segments=np.concatenate(seg), n_segments=len(read_lists))
+    node_base = np.zeros(len(per_set) + 1, dtype=np.int64)
+    if counts_all.max() > 1:
+        np.cumsum([int(c.sum()) for _, _, c in per_set], out=node_base[1:])
+    else:
+        np.cumsum([len(u) for _, u, _ in per_set], out=node_base[1:])
+    bounds = np.searchsorted(edges[:, 0], node_base, side="left") if edges.shape[0] else np.zeros(len(per_set) + 1, np.int64)
+    out = []
+    for s_id, (read_copies, uniq, counts) in enumerate(per_set):
+        rows = edges[bounds[s_id]:bounds[s_id + 1]].copy()
+        rows[:, 0] -= int(node_base[s_id])
+        rows[:, 1] -= int(node_base[s_id])
+        out.append((_graph_from_rows(uniq, counts, rows), read_copies))
+    return out
+
+
 def construct_overlap_graph_string(reads):
     """Drop-in for overlapGraphs.py:196-232: every ordered pair of distinct reads is aligned and
     edges are kept only for score > 0 (same node naming and copy expansion as the k-mer builder)."""

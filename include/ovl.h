@@ -62,15 +62,21 @@ int ovl_pack_reads(ovl_ctx *ctx, const uint8_t *ascii, const int64_t *offsets, i
 /* K1: prefix / suffix k-mer keys, overlapGraphs.py:33-37 (read[:k]) and :44-47 (read[-k:]).
  * Reads shorter than k can match nothing but themselves: their keys are placeholders and the
  * index / join skip them by length. */
+/* segment (optional, int32[U]): the read set each read belongs to.  The tag is stored in the key
+ * bits above the k-mer (needs 2k + bits(segment) <= 64), so one index and one join serve many
+ * independent read sets -- the parameter sweep of experiments.py:451-539 as ONE job -- and reads of
+ * different sets never pair. */
 int ovl_kmer_keys(ovl_ctx *ctx, const uint32_t *packed, int32_t row_words, const int32_t *len,
-                  int64_t U, int32_t k, uint64_t *prefix_key, uint64_t *suffix_key, void *stream);
+                  int64_t U, int32_t k, const int32_t *segment, uint64_t *prefix_key,
+                  uint64_t *suffix_key, void *stream);
 
 /* K2: the prefix index, overlapGraphs.py:30-40, as a stable sort of (prefix_key, uid):
  * sorted_key / sorted_uid hold the *n_indexed reads with len >= k, keys ascending and uids
  * ascending inside equal keys (the reference's bucket-append order). */
 size_t ovl_index_workspace_bytes(int64_t U);
+/* key_bits: number of significant key bits to sort on (2k + segment-tag bits); 0 means 2k. */
 int ovl_index_build(ovl_ctx *ctx, const uint64_t *prefix_key, const int32_t *len, int64_t U, int32_t k,
-                    uint64_t *sorted_key, uint32_t *sorted_uid, int64_t *n_indexed,
+                    int32_t key_bits, uint64_t *sorted_key, uint32_t *sorted_uid, int64_t *n_indexed,
                     void *workspace, size_t workspace_bytes, void *stream);
 
 /* K3: candidate generation, overlapGraphs.py:43-52, for source reads a in [a_begin, a_end).
@@ -153,6 +159,15 @@ size_t ovl_align_pair_workspace_bytes(int32_t n, int32_t m);
 int ovl_align_pair(ovl_ctx *ctx, const int32_t *s, int32_t n, const int32_t *t, int32_t m,
                    int64_t match, int64_t mismatch, int64_t indel, void *workspace,
                    size_t workspace_bytes, int32_t *result, uint8_t *ops, void *stream);
+
+/* K8: Smith-Waterman local alignment with traceback = aligners.local_alignment, aligners.py:85-167
+ * (the aligner the evaluation uses to map reads / contigs to the genome, performanceMeasures.py:219).
+ * result[0..4] = (best_score, start_pos, end_pos, n_ops, best_i); ops[0..n_ops) is the traceback
+ * from the best cell backwards: 1 diagonal, 2 up (gap in reference), 3 left (gap in query). */
+size_t ovl_local_align_workspace_bytes(int32_t n, int32_t m);
+int ovl_local_align(ovl_ctx *ctx, const int32_t *query, int32_t n, const int32_t *reference, int32_t m,
+                    int64_t match, int64_t mismatch, int64_t indel, void *workspace,
+                    size_t workspace_bytes, int32_t *result, uint8_t *ops, void *stream);
 
 /* Roofline denominator for the DP: runs a dependency-free instruction stream on every SM and
  * returns lane-operations per second (1e9/s).  kind: 0 IADD3, 1 IMAD, 2 VIMNMX.S32,

@@ -175,6 +175,58 @@ int ovo_overlap_pairs(const uint8_t *bases, const int64_t *offsets,
     return rc;
 }
 
+/*
+ * Full restatement of aligners.py:106-167 (local_alignment): Smith-Waterman with the reference's
+ * branch order (diag if >= up, >= left and >= 0; else up if >= left and >= 0; else left if >= 0;
+ * else 0), first strict maximum in row-major order, walk while dp > 0 and traceback != 0.
+ * out[0..3] = best_score, start_pos, end_pos, best_i;  aligned strings as in ovo_overlap_alignment
+ * (a_q = aligned query, a_r = aligned reference).
+ */
+int ovo_local_alignment(const uint8_t *q, int32_t n, const uint8_t *r, int32_t m,
+                        int64_t match, int64_t mismatch, int64_t indel,
+                        int32_t *out, uint8_t *a_q, uint8_t *a_r, int32_t *align_len)
+{
+    size_t W = (size_t)m + 1;
+    int32_t *dp = (int32_t *)calloc((size_t)(n + 1) * W, sizeof(int32_t));
+    int8_t *tb = (int8_t *)calloc((size_t)(n + 1) * W, sizeof(int8_t));
+    if (!dp || !tb) { free(dp); free(tb); return OVO_ENOMEM; }
+    int64_t best = 0;
+    int32_t bi = 0, bj = 0;
+    for (int32_t i = 1; i <= n; ++i) {
+        const int32_t *prev = dp + (size_t)(i - 1) * W;
+        int32_t *cur = dp + (size_t)i * W;
+        int8_t *tbr = tb + (size_t)i * W;
+        for (int32_t j = 1; j <= m; ++j) {
+            int64_t diag = (int64_t)prev[j - 1] + (q[i - 1] == r[j - 1] ? match : mismatch);
+            int64_t up = (int64_t)prev[j] + indel;
+            int64_t left = (int64_t)cur[j - 1] + indel;
+            if (diag >= up && diag >= left && diag >= 0) { cur[j] = (int32_t)diag; tbr[j] = 1; }
+            else if (up >= left && up >= 0)              { cur[j] = (int32_t)up;   tbr[j] = 2; }
+            else if (left >= 0)                          { cur[j] = (int32_t)left; tbr[j] = 3; }
+            else                                         { cur[j] = 0; }
+            if ((int64_t)cur[j] > best) { best = cur[j]; bi = i; bj = j; }
+        }
+    }
+    int32_t i = bi, j = bj, L = 0;
+    while (i > 0 && j > 0 && dp[(size_t)i * W + j] > 0) {
+        int8_t d = tb[(size_t)i * W + j];
+        if (d == 1)      { a_q[L] = q[i - 1]; a_r[L] = r[j - 1]; --i; --j; }
+        else if (d == 2) { a_q[L] = q[i - 1]; a_r[L] = '-';      --i; }
+        else if (d == 3) { a_q[L] = '-';      a_r[L] = r[j - 1]; --j; }
+        else break;
+        ++L;
+    }
+    for (int32_t a = 0, b = L - 1; a < b; ++a, --b) {
+        uint8_t x = a_q[a]; a_q[a] = a_q[b]; a_q[b] = x;
+        x = a_r[a]; a_r[a] = a_r[b]; a_r[b] = x;
+    }
+    a_q[L] = 0; a_r[L] = 0;
+    *align_len = L;
+    out[0] = (int32_t)best; out[1] = j; out[2] = bj; out[3] = bi;
+    free(dp); free(tb);
+    return OVO_OK;
+}
+
 int ovo_max_threads(void)
 {
 #ifdef _OPENMP

@@ -54,6 +54,10 @@ def _load():
                                           ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                           i32p, i32p, ctypes.c_int32, ctypes.c_int32]
         lib.ovo_overlap_pairs.restype = ctypes.c_int
+        lib.ovo_local_alignment.argtypes = [u8p, ctypes.c_int32, u8p, ctypes.c_int32,
+                                            ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                            i32p, u8p, u8p, i32p]
+        lib.ovo_local_alignment.restype = ctypes.c_int
         lib.ovo_max_threads.restype = ctypes.c_int
         _lib = lib
     return _lib
@@ -98,6 +102,29 @@ def overlap_alignment(s: str, t: str, match_score: int = 10, mismatch: int = -1,
     # aligners.py:78
     to_print = f"\nTarget:   {align_t}\n          {'|' * len(align_t)}\nQuery:    {align_s}"
     return to_print, align_s, align_t, int(score.value), int(end.value)
+
+
+def local_alignment(query: str, reference: str, match_score: int = 10, mismatch: int = -1, indel: int = -1):
+    """Restates ``aligners.local_alignment`` (aligners.py:85-167): same 6-tuple."""
+    lib = _load()
+    qb, rb = _as_u8(query), _as_u8(reference)
+    n, m = len(qb), len(rb)
+    a_q = np.zeros(n + m + 2, dtype=np.uint8)
+    a_r = np.zeros(n + m + 2, dtype=np.uint8)
+    out = np.zeros(4, dtype=np.int32)
+    L = ctypes.c_int32()
+    qb_ = qb if n else np.zeros(1, np.uint8)
+    rb_ = rb if m else np.zeros(1, np.uint8)
+    rc = lib.ovo_local_alignment(_ptr(qb_, ctypes.c_uint8), n, _ptr(rb_, ctypes.c_uint8), m,
+                                 int(match_score), int(mismatch), int(indel), _ptr(out, ctypes.c_int32),
+                                 _ptr(a_q, ctypes.c_uint8), _ptr(a_r, ctypes.c_uint8), ctypes.byref(L))
+    if rc != 0:
+        raise MemoryError("oracle allocation failed")
+    aligned_query = a_q[:L.value].tobytes().decode("latin-1")
+    aligned_reference = a_r[:L.value].tobytes().decode("latin-1")
+    to_print = (f"\nTarget:   {aligned_reference}\n          {'|' * len(aligned_reference)}\nQuery:    "
+                f"{aligned_query}")                                    # aligners.py:166-167
+    return to_print, aligned_reference, aligned_query, int(out[0]), int(out[1]), int(out[2])
 
 
 def concat_reads(reads: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:

@@ -45,6 +45,12 @@ def golden_allpairs():
         return json.load(fh)["cases"]
 
 
+@pytest.fixture(scope="session")
+def golden_local():
+    with open(os.path.join(GOLDEN, "local.json")) as fh:
+        return json.load(fh)
+
+
 def has_cuda() -> bool:
     try:
         import torch

@@ -164,6 +164,45 @@ def make_graphs():
     return cases
 
 
+def make_local():
+    """aligners.local_alignment (aligners.py:85-167) and align_read_or_contig_to_reference (:170-202)."""
+    rng = random.Random(8086)
+    cases = []
+
+    def one(q, r, prm):
+        out = ref_aligners.local_alignment(q, r) if prm is None else ref_aligners.local_alignment(q, r, *prm)
+        ma, mi, ind = (10, -1, -1) if prm is None else prm
+        assert type(out[3]) is int and type(out[4]) is int and type(out[5]) is int
+        cases.append({"query": q, "reference": r, "match": ma, "mismatch": mi, "indel": ind, "out": list(out)})
+
+    for q, r in [("ACGT", "TTACGTGG"), ("AAAA", "CCCC"), ("", "ACGT"), ("ACGT", ""), ("", ""), ("A", "A"),
+                 ("ACGTACGT", "ACGTACGT"), ("ACGTTTACGT", "ACGTACGT"), ("GGGACGTGGG", "TTTACGTTTT")]:
+        one(q, r, None)
+    params = [None, (10, -1, -1), (10, -1, -2), (1, -1, -1), (5, -4, -3), (2, -3, -2), (10, -1, 0), (3, 0, -1)]
+    for it in range(160):
+        g = rand_seq(rng, rng.randint(20, 120))
+        st = rng.randrange(len(g))
+        q = mutate(rng, g[st:st + rng.randint(1, 40)], 0.08, 0.08) or "A"
+        kind = it % 4
+        if kind == 1:
+            q = rand_seq(rng, rng.randint(1, 30))
+        elif kind == 2:
+            q, g = rand_seq(rng, rng.randint(1, 25), "AC"), rand_seq(rng, rng.randint(1, 60), "AC")
+        elif kind == 3:
+            q = g[st:st + 30] + rand_seq(rng, 5) + g[st:st + 10]
+        one(q, g, params[it % len(params)])
+    wrapped = []
+    genome = rand_seq(rng, 400)
+    for _ in range(30):
+        st = rng.randrange(len(genome))
+        L = rng.choice([5, 12, 30, 60])
+        read = mutate(rng, genome[st:st + L], 0.05)
+        rl = rng.choice([10, 30, 50])
+        out = ref_aligners.align_read_or_contig_to_reference(read, genome, rl)
+        wrapped.append({"seq": read, "genome": genome, "read_length": rl, "out": list(out)})
+    return {"local": cases, "wrapped": wrapped}
+
+
 def make_allpairs():
     """overlapGraphs.construct_overlap_graph_string (:196-232) and construct_string_graph (:332-351)."""
     import contextlib
@@ -202,6 +241,12 @@ if __name__ == "__main__":
         json.dump({"generator": "tests/golden/make_golden.py",
                    "source": "live reference overlapGraphs.construct_overlap_graph_nx_k",
                    "cases": graphs}, fh, separators=(",", ":"))
+    loc = make_local()
+    with open(os.path.join(HERE, "local.json"), "w") as fh:
+        json.dump({"generator": "tests/golden/make_golden.py",
+                   "source": "live reference aligners.local_alignment / align_read_or_contig_to_reference", **loc},
+                  fh, separators=(",", ":"))
+    print(len(loc["local"]), "local-alignment cases;", len(loc["wrapped"]), "wrapper cases")
     allp = make_allpairs()
     with open(os.path.join(HERE, "allpairs.json"), "w") as fh:
         json.dump({"generator": "tests/golden/make_golden.py",

@@ -93,6 +93,32 @@ def orc_any(s, t, ma=10, mi=-1, ind=-2 ** 31):
     return f"\nTarget:   {a_t}\n          {'|' * len(a_t)}\nQuery:    {a_s}", a_s, a_t, int(best), bj
 
 
+# --------------------------------------------------------------------------- K8 local alignment
+def test_local_alignment_golden(golden_local):
+    al = load_pkg("aligners")
+    for c in golden_local["local"]:
+        got = al.local_alignment(c["query"], c["reference"], c["match"], c["mismatch"], c["indel"])
+        assert list(got) == c["out"], (c["query"], c["reference"], c["match"], c["mismatch"], c["indel"])
+        assert all(type(x) is int for x in got[3:])
+    for c in golden_local["wrapped"]:
+        got = al.align_read_or_contig_to_reference(c["seq"], c["genome"], c["read_length"])
+        assert list(got) == c["out"]
+
+
+def test_local_alignment_contig_vs_genome_oracle():
+    """The evaluation's use (performanceMeasures.py:219): contigs of a few hundred bases against the
+    5,386-base genome."""
+    al = load_pkg("aligners")
+    synth = load_pkg("synth")
+    genome = synth.phix_like_genome().tobytes().decode()
+    rng = random.Random(3)
+    for L in (100, 700, 1800):
+        st = rng.randrange(len(genome) - L)
+        contig = "".join(ch if rng.random() > 0.02 else rng.choice("ACGT") for ch in genome[st:st + L])
+        contig = contig[:L // 2] + contig[L // 2 + 3:]                       # a deletion
+        assert al.local_alignment(contig, genome) == orc.local_alignment(contig, genome)
+
+
 # --------------------------------------------------------------------------- K0 / K1 / K2 / K3
 def np_pack(reads, row_words):
     code = {"A": 0, "C": 1, "T": 2, "G": 3}
@@ -302,6 +328,29 @@ def test_allpairs_builders_vs_oracle_random(eng, capsys):
     assert list(H.nodes) == list(H2.nodes)
     assert list(H.edges(data=True)) == list(H2.edges(data=True))
     assert [list(H.pred[n]) for n in H.nodes] == [list(H2.pred[n]) for n in H2.nodes]
+
+
+def test_batched_read_sets_equal_individual_builds(eng):
+    """The sweep as one job (experiments.py:451-539): identical graphs to one build per read set."""
+    g = load_pkg("overlapGraphs")
+    synth = load_pkg("synth")
+    genome = synth.phix_like_genome()
+    sets = []
+    for i, (n, l, p) in enumerate([(100, 50, 0.001), (316, 100, 0.01), (1000, 150, 0.1), (100, 150, 0.01), (0, 50, 0.0)]):
+        b, o = synth.simulate_reads(genome, n, l, p, seed=100 + i) if n else (np.zeros(0, np.uint8), np.zeros(1, np.int64))
+        sets.append(synth.to_strings(b, o))
+    sets.append(sets[0] + sets[0][:10])                       # a set with duplicate reads
+    for k in (5, 10, 15):
+        got = g.construct_overlap_graphs_batch(sets, k=k)
+        assert len(got) == len(sets)
+        for reads, (G, rc) in zip(sets, got):
+            G1, rc1 = g.construct_overlap_graph_nx_k(reads, k=k)
+            assert list(rc.items()) == list(rc1.items())
+            assert list(G.nodes) == list(G1.nodes)
+            assert list(G.edges(data=True)) == list(G1.edges(data=True))
+            assert [list(G.pred[n]) for n in G.nodes] == [list(G1.pred[n]) for n in G1.nodes]
+        nodes, edges, _ = orc.construct_overlap_graph(sets[2], k)
+        assert list(got[2][0].edges(data=True)) == list(orc.to_networkx(nodes, edges).edges(data=True))
 
 
 def test_graph_builder_vs_oracle_with_duplicates(eng):

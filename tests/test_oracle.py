@@ -81,6 +81,14 @@ def test_allpairs_builders_match_reference_golden(golden_allpairs):
         assert [[hidx[p] for p in H.pred[n]] for n in hn] == c["sg_pred"]
 
 
+def test_local_alignment_matches_reference_golden(golden_local):
+    """aligners.local_alignment (aligners.py:85-167)."""
+    assert len(golden_local["local"]) >= 150
+    for c in golden_local["local"]:
+        got = orc.local_alignment(c["query"], c["reference"], c["match"], c["mismatch"], c["indel"])
+        assert list(got) == c["out"], (c["query"], c["reference"], c["match"], c["mismatch"], c["indel"])
+
+
 def test_negative_k_asserts():
     with pytest.raises(AssertionError):
         orc.construct_overlap_graph(["ACGT"], k=-1)
