@@ -257,6 +257,70 @@ class OverlapEngine:
         self.launches += 1
         return edges[:E * 4].view(E, 4)
 
+    def overlap_edges_fused_to_host(self, rs: ReadSet, pair_a: torch.Tensor, pair_b: torch.Tensor,
+                                    copies: Optional[torch.Tensor] = None, node_off: Optional[torch.Tensor] = None,
+                                    match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT,
+                                    chunk_pairs: int = 48_000_000) -> np.ndarray:
+        """DP + fused edge expansion, with the device->host copy of the edge rows overlapped with the
+        DP: the pair list is cut into chunks, each chunk's rows are copied to the pinned host buffer
+        on a second stream while the next chunk computes.  Returns a view of the pinned buffer."""
+        P = int(pair_a.shape[0])
+        if P == 0:
+            return np.zeros((0, 4), np.int32)
+        main = torch.cuda.current_stream(self.device)
+        st = self._stream()
+        n_chunks = max(1, min(64, (P + chunk_pairs - 1) // chunk_pairs))
+        if P >= 1_000_000:
+            n_chunks = max(n_chunks, 8)        # even a few-ms job hides most of its copy behind the DP
+        bounds = [P * c // n_chunks for c in range(n_chunks + 1)]
+        edge_off = None
+        if copies is not None:
+            edge_off = self._empty(P + 1, torch.int64)
+            ws_bytes = int(nat.lib.ovl_expand_workspace_bytes(P))
+            ws = self._empty(ws_bytes, torch.uint8)
+            nat.check(nat.lib.ovl_expand_count(self._ctx, _ptr(pair_a), _ptr(pair_b), _ptr(copies), P,
+                                               _ptr(edge_off), _ptr(ws), ws_bytes, st))
+            self.launches += 1 if P <= 16384 else 3
+            idx = torch.tensor(bounds, dtype=torch.int64, device=self.device)
+            e_bounds = edge_off[idx].cpu().tolist()           # host sync: output size + chunk boundaries
+        else:
+            e_bounds = bounds
+        E = int(e_bounds[-1])
+        edges = self._empty(E * 4, torch.int32).view(-1, 4)
+        if self._pinned_out is None or self._pinned_out.shape[0] < max(E, 1):
+            self._pinned_out = torch.empty((max(E, 1) * 5 // 4 + 16, 4), dtype=torch.int32).pin_memory()
+        host = self._pinned_out[:E]
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(self.device)
+        for c in range(n_chunks):
+            p0, p1 = bounds[c], bounds[c + 1]
+            if p1 == p0:
+                continue
+            a_ptr = ctypes.c_void_p(pair_a.data_ptr() + 4 * p0)
+            b_ptr = ctypes.c_void_p(pair_b.data_ptr() + 4 * p0)
+            if copies is not None:
+                off_ptr = ctypes.c_void_p(edge_off.data_ptr() + 8 * p0)       # offsets stay global
+                out_ptr = _ptr(edges)
+            else:
+                off_ptr = ctypes.c_void_p(0)
+                out_ptr = ctypes.c_void_p(edges.data_ptr() + 16 * p0)
+            nat.check(nat.lib.ovl_overlap_dp_edges(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length),
+                                                   a_ptr, b_ptr, p1 - p0, rs.max_len,
+                                                   int(match_score), int(mismatch), int(indel),
+                                                   _ptr(copies), _ptr(node_off), off_ptr, out_ptr, st))
+            self.launches += 1
+            done = torch.cuda.Event()
+            done.record(main)
+            e0, e1 = int(e_bounds[c]), int(e_bounds[c + 1])
+            if e1 > e0:
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(done)
+                    host[e0:e1].copy_(edges[e0:e1], non_blocking=True)
+        self._copy_stream.synchronize()
+        main.wait_stream(self._copy_stream)
+        edges.record_stream(self._copy_stream)
+        return host.numpy()
+
     @staticmethod
     def dp_plan(max_len: int, match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT, mode: int = 0):
         out = (ctypes.c_int32 * 3)()
@@ -404,6 +468,15 @@ class OverlapEngine:
             pa = self._to_device(pairs[0], torch.int32)
             pb = self._to_device(pairs[1], torch.int32)
             edges = self.overlap_edges_fused(rs, pa, pb, copies, node_off, match_score, mismatch, indel)
+        elif to_host and min_weight is None and segments is None:
+            # the common host call: overlap the D2H of the edge rows with the DP, chunk by chunk
+            index = self.kmer_index(rs, k) if k > 0 else None
+            pa, pb, _ = self.candidate_pairs(rs, index, k, shard)
+            host = self.overlap_edges_fused_to_host(rs, pa, pb, copies, node_off, match_score, mismatch, indel)
+            if stats is not None:
+                stats["pairs"], stats["edges"] = int(pa.shape[0]), int(host.shape[0])
+            self.check_alphabet(rs)
+            return host if reuse_host_buffer else host.copy()
         else:
             seg_dev = self._to_device(segments, torch.int32) if segments is not None else None
             edges = self.overlap_edges_device(rs, k, copies, node_off, shard, match_score, mismatch, indel, stats,

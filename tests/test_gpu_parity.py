@@ -353,6 +353,20 @@ def test_batched_read_sets_equal_individual_builds(eng):
         assert list(got[2][0].edges(data=True)) == list(orc.to_networkx(nodes, edges).edges(data=True))
 
 
+@pytest.mark.parametrize("reads,k", [
+    ([], 5), (["ACGTACGT"], 3), (["ACGTACGT"] * 4, 3), (["ACG", "CG", "A"], 5), (["ACGT", "CGTA"], 8),
+    (["ACGTAC", "GTACGT", "ACGTAC", ""], 3), (["", ""], 0), (["A"], 0), (["ACGT", "ACGT", "CGTT"], 0),
+    (["AAAAAAAAAA", "AAAAAAAAAA", "AAAAAAAAA"], 2)])
+def test_graph_builder_degenerate_inputs(reads, k):
+    g = load_pkg("overlapGraphs")
+    G, rc = g.construct_overlap_graph_nx_k(reads, k=k)
+    nodes, edges, rc2 = orc.construct_overlap_graph(reads, k)
+    G2 = orc.to_networkx(nodes, edges)
+    assert list(rc.items()) == list(rc2.items())
+    assert list(G.nodes) == list(G2.nodes)
+    assert list(G.edges(data=True)) == list(G2.edges(data=True))
+
+
 def test_graph_builder_vs_oracle_with_duplicates(eng):
     g = load_pkg("overlapGraphs")
     rng = random.Random(2024)
