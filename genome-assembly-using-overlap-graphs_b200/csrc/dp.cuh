@@ -73,7 +73,8 @@ constexpr int kDpThreads = 128;
 #define OVL_DP_F2_NUM 1        // columns using form 2 (FMA-heavy): NUM out of every DEN
 #endif
 #ifndef OVL_DP_PREPACK
-#define OVL_DP_PREPACK 0       // 1: take the packed constants from the kernel parameters (measured slower)
+#define OVL_DP_PREPACK 0       // 1: take the packed constants from the kernel parameters (measured slower: 8.4 vs
+                               // 8.95 TCUPS; gap costs as immediates were slower too: 8.75 vs 9.09)
 #endif
 #ifndef OVL_DP_KUNROLL
 #define OVL_DP_KUNROLL 1       // unroll factor of the row loop
