@@ -559,6 +559,8 @@ int ovl_int_peak_probe(ovl_ctx* ctx, int32_t kind, int32_t iters, double* h_gops
         case 7: return run_probe<7>(ctx, iters, h_gops, h_ms);
         case 8: return run_probe<8>(ctx, iters, h_gops, h_ms);
         case 9: return run_probe<9>(ctx, iters, h_gops, h_ms);
+        case 10: return run_probe<10>(ctx, iters, h_gops, h_ms);
+        case 11: return run_probe<11>(ctx, iters, h_gops, h_ms);
         default: return fail(OVL_E_ARG, "ovl_int_peak_probe: unknown kind %d", kind);
     }
 }

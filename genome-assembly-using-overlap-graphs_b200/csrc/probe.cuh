@@ -53,6 +53,21 @@ __global__ void __launch_bounds__(kProbeThreads) int_probe_kernel(uint32_t* out,
                     asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a1) : "r"(dc), "r"(one), "r"(z[c]));
                     uint32_t t1 = __viaddmin_u16x2(w[c], b0, a1);
                     v[c] = __viaddmin_u16x2(v[c], a0, t1);
+                } else if (KIND == 10) {    // form-2 DP column per chain (PRMT, 3x IMAD, VIMNMX3)
+                    uint32_t dc;
+                    asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(dc) : "r"(x[c]), "r"(y[c]), "r"(v[c]));
+                    uint32_t a1, a2, a3;
+                    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a1) : "r"(dc), "r"(one), "r"(z[c]));
+                    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a2) : "r"(w[c]), "r"(one), "r"(b0));
+                    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a3) : "r"(v[c]), "r"(one), "r"(a0));
+                    v[c] = __vimin3_u16x2(a1, a2, a3);
+                } else if (KIND == 11) {    // 2 ALU (PRMT, VIMNMX3) + 2 IMAD per chain: balanced pipes
+                    uint32_t dc;
+                    asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(dc) : "r"(x[c]), "r"(y[c]), "r"(v[c]));
+                    uint32_t a1, a3;
+                    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a1) : "r"(dc), "r"(one), "r"(z[c]));
+                    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a3) : "r"(v[c]), "r"(one), "r"(a0));
+                    v[c] = __vimin3_u16x2(a1, w[c], a3);
                 } else if (KIND == 5) {     // PRMT
                     asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(v[c]) : "r"(w[c]), "r"(b0));
                 } else {                    // LOP3
@@ -67,6 +82,10 @@ __global__ void __launch_bounds__(kProbeThreads) int_probe_kernel(uint32_t* out,
     if (acc == 0x12345678u) out[0] = acc;    // practically never; keeps the chains alive
 }
 
-inline int probe_ops_per_iter(int kind) { return (kind == 4 || kind == 9) ? 4 : ((kind == 7 || kind == 8) ? 2 : 1); }
+inline int probe_ops_per_iter(int kind) {
+    if (kind == 10) return 5;
+    if (kind == 4 || kind == 9 || kind == 11) return 4;
+    return (kind == 7 || kind == 8) ? 2 : 1;
+}
 
 }  // namespace ovl

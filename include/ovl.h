@@ -173,7 +173,8 @@ int ovl_local_align(ovl_ctx *ctx, const int32_t *query, int32_t n, const int32_t
  * returns lane-operations per second (1e9/s).  kind: 0 IADD3, 1 IMAD, 2 VIMNMX.S32,
  * 3 VIADDMNMX.S16x2, 4 the DP inner-loop mix (PRMT, IMAD, 2x VIADDMNMX.S16x2), 5 PRMT, 6 LOP3,
  * 7 LOP3 + IMAD on independent chains (do the ALU and FMA pipes issue side by side?),
- * 8 VIMNMX3 + IMAD with all-distinct register operands, 9 one form-1 DP column per chain.
+ * 8 VIMNMX3 + IMAD with all-distinct register operands, 9 one form-1 DP column per chain,
+ * 10 one form-2 DP column per chain, 11 a 2 ALU + 2 IMAD column.
  * Synchronises the device.  h_gops receives giga lane-instructions per second. */
 int ovl_int_peak_probe(ovl_ctx *ctx, int32_t kind, int32_t iters, double *h_gops, double *h_ms);
 
