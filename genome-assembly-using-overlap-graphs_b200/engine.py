@@ -260,12 +260,14 @@ class OverlapEngine:
     def overlap_edges_fused_to_host(self, rs: ReadSet, pair_a: torch.Tensor, pair_b: torch.Tensor,
                                     copies: Optional[torch.Tensor] = None, node_off: Optional[torch.Tensor] = None,
                                     match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT,
-                                    chunk_pairs: int = 48_000_000) -> np.ndarray:
+                                    chunk_pairs: int = 48_000_000, host_sink=None) -> np.ndarray:
         """DP + fused edge expansion, with the device->host copy of the edge rows overlapped with the
         DP: the pair list is cut into chunks, each chunk's rows are copied to the pinned host buffer
         on a second stream while the next chunk computes.  Returns a view of the pinned buffer."""
         P = int(pair_a.shape[0])
         if P == 0:
+            if host_sink is not None:
+                host_sink(0)                       # collective sinks must be called by every rank
             return np.zeros((0, 4), np.int32)
         main = torch.cuda.current_stream(self.device)
         st = self._stream()
@@ -287,9 +289,12 @@ class OverlapEngine:
             e_bounds = bounds
         E = int(e_bounds[-1])
         edges = self._empty(E * 4, torch.int32).view(-1, 4)
-        if self._pinned_out is None or self._pinned_out.shape[0] < max(E, 1):
-            self._pinned_out = torch.empty((max(E, 1) * 5 // 4 + 16, 4), dtype=torch.int32).pin_memory()
-        host = self._pinned_out[:E]
+        if host_sink is not None:
+            host = host_sink(E)                    # caller-provided page-locked destination (E rows)
+        else:
+            if self._pinned_out is None or self._pinned_out.shape[0] < max(E, 1):
+                self._pinned_out = torch.empty((max(E, 1) * 5 // 4 + 16, 4), dtype=torch.int32).pin_memory()
+            host = self._pinned_out[:E]
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(self.device)
         for c in range(n_chunks):
@@ -449,7 +454,8 @@ class OverlapEngine:
     def overlap_edges(self, bases, offsets, counts=None, k: int = 5, shard: Tuple[int, int] = (0, 1),
                       match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT,
                       stats: Optional[dict] = None, to_host: bool = True, reuse_host_buffer: bool = False,
-                      min_weight: Optional[int] = None, pairs=None, segments=None, n_segments: int = 1):
+                      min_weight: Optional[int] = None, pairs=None, segments=None, n_segments: int = 1,
+                      host_sink=None):
         """HOST buffers in, HOST edge rows out: unique reads (ASCII bytes + offsets) and their
         multiplicities -> int32[E, 4] (node_a, node_b, weight, end_position) in the reference's
         insertion order.  This is the call the drop-in graph builder makes."""
@@ -472,11 +478,12 @@ class OverlapEngine:
             # the common host call: overlap the D2H of the edge rows with the DP, chunk by chunk
             index = self.kmer_index(rs, k) if k > 0 else None
             pa, pb, _ = self.candidate_pairs(rs, index, k, shard)
-            host = self.overlap_edges_fused_to_host(rs, pa, pb, copies, node_off, match_score, mismatch, indel)
+            host = self.overlap_edges_fused_to_host(rs, pa, pb, copies, node_off, match_score, mismatch, indel,
+                                                    host_sink=host_sink)
             if stats is not None:
                 stats["pairs"], stats["edges"] = int(pa.shape[0]), int(host.shape[0])
             self.check_alphabet(rs)
-            return host if reuse_host_buffer else host.copy()
+            return host if (reuse_host_buffer or host_sink is not None) else host.copy()
         else:
             seg_dev = self._to_device(segments, torch.int32) if segments is not None else None
             edges = self.overlap_edges_device(rs, k, copies, node_off, shard, match_score, mismatch, indel, stats,

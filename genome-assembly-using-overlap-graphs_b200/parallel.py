@@ -47,3 +47,92 @@ def gather_edges(edges: torch.Tensor, dst: int = 0, group=None) -> Optional[torc
         for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, flat, dst, group)]):
             w.wait()
     return None
+
+
+class SharedEdgeSink:
+    """Host-side landing zone for the edge rows of all ranks of ONE node: a POSIX shared-memory
+    segment that every rank maps and page-locks (cudaHostRegister), so each GPU copies its slice
+    over its own PCIe link straight to its final position and rank 0 ends up with the complete,
+    ordered list in host memory -- no NVLink gather and no single-link funnel.
+
+    Use as the `host_sink` of OverlapEngine.overlap_edges(): calling it with the local row count
+    all-gathers the counts, (re)sizes the segment collectively if needed and returns the pinned
+    CPU tensor slice this rank must fill.  After a barrier, `rows()` on rank 0 is the whole list.
+    """
+
+    def __init__(self, group=None, cuda: bool = True, initial_rows: int = 1 << 20):
+        self.group = group
+        self.cuda = cuda and torch.cuda.is_available()
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.shm = None
+        self.tensor = None
+        self.capacity = 0
+        self.total = 0
+        self._registered = None
+        self._ensure(initial_rows)
+
+    def _release(self):
+        if self._registered is not None:
+            torch.cuda.cudart().cudaHostUnregister(self._registered)
+            self._registered = None
+        self.tensor = None
+        if self.shm is not None:
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+            self.shm = None
+
+    def _ensure(self, rows: int):
+        """Collective: every rank calls with the same `rows`."""
+        from multiprocessing import shared_memory
+        import numpy as np
+        if rows <= self.capacity:
+            return
+        self._release()
+        rows = int(rows + rows // 16 + 1024)
+        rows = (rows + 255) // 256 * 256           # 4 KiB multiple: cudaHostRegister wants page-granular sizes
+        nbytes = rows * 16
+        name = [None]
+        if self.rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            name[0] = self.shm.name
+        dist.broadcast_object_list(name, src=0, group=self.group)
+        if self.rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+            try:                                   # the creator owns the segment: do not let this process unlink it
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        arr = np.ndarray((rows, 4), dtype=np.int32, buffer=self.shm.buf)
+        self.tensor = torch.from_numpy(arr)
+        if self.cuda:
+            # page-lock the mapping in every process, one rank at a time: concurrent registration of
+            # the same not-yet-populated segment fails with cudaErrorOperatingSystem (measured)
+            for r in range(self.world):
+                if r == self.rank:
+                    err = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), nbytes, 0)
+                    if int(err) != 0:
+                        raise RuntimeError(f"cudaHostRegister of the shared edge buffer ({nbytes} bytes) failed: "
+                                           f"cudaError {int(err)}")
+                    self._registered = self.tensor.data_ptr()
+                dist.barrier(group=self.group)
+        self.capacity = rows
+        dist.barrier(group=self.group)
+
+    def __call__(self, n_local: int) -> torch.Tensor:
+        sizes = [None] * self.world
+        dist.all_gather_object(sizes, int(n_local), group=self.group)
+        self.total = int(sum(sizes))
+        self._ensure(self.total)
+        off = int(sum(sizes[:self.rank]))
+        return self.tensor[off:off + int(n_local)]
+
+    def rows(self):
+        """NumPy view of the complete list (meaningful on every rank after a barrier)."""
+        return self.tensor[:self.total].numpy()
+
+    def close(self):
+        dist.barrier(group=self.group)
+        self._release()

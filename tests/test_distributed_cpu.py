@@ -52,6 +52,45 @@ def _run(sizes):
     assert np.array_equal(got, np.arange(total * 4, dtype=np.int32).reshape(total, 4))
 
 
+def _sink_worker(rank, world, port, sizes, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    par = load_pkg("parallel")
+    sink = par.SharedEdgeSink(cuda=False, initial_rows=2)
+    for rnd in range(2):                                     # second round forces a collective re-size
+        n = sizes[rank] * (1 + 300 * rnd)
+        all_n = [s * (1 + 300 * rnd) for s in sizes]
+        start = sum(all_n[:rank])
+        dst = sink(n)
+        dst.copy_(torch.arange(start * 4, (start + n) * 4, dtype=torch.int32).view(-1, 4))
+        dist.barrier()
+        if rank == 0:
+            q.put(sink.rows().copy())
+        dist.barrier()
+    sink.close()
+    dist.destroy_process_group()
+
+
+def test_shared_edge_sink_world2():
+    sizes = [5, 3]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sink_worker, args=(r, 2, port, sizes, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for rnd in range(2):
+        got = q.get(timeout=120)
+        total = sum(sizes) * (1 + 300 * rnd)
+        assert np.array_equal(got, np.arange(total * 4, dtype=np.int32).reshape(total, 4))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+
+
 def test_gather_edges_world2():
     _run([5, 3])
 
