@@ -253,6 +253,8 @@ def run_ours(args):
 
     shard = (rank, world)
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    peer = None          # set after the first (NCCL-gather) pass, when the total edge count is known
+    exchange = "none (1 GPU)"
 
     def device_step(record=None):
         rs = eng.pack_reads(d_ascii, d_off, U, max_len)
@@ -263,7 +265,12 @@ def run_ours(args):
         # K6 is fused into the DP epilogue; with duplicate reads a scan of the per-pair edge counts
         # (and one host read of the total) comes first
         edges = eng.overlap_edges_fused(rs, pa, pb, d_copies, d_node_off,
-                                        events=(record["dp0"], record["dp1"]) if record is not None else None)
+                                        events=(record["dp0"], record["dp1"]) if record is not None else None,
+                                        sink=peer.slot if peer is not None else None)
+        if peer is not None:
+            # the DP epilogue has stored this rank's rows straight into rank 0's buffer over NVLink
+            peer.barrier()
+            return rs, pa, pb, None, peer.result()
         if world > 1:
             edges_all = par.gather_edges(edges, 0)
         else:
@@ -290,6 +297,23 @@ def run_ours(args):
     checksum = int(edges_all.to(torch.int64).sum().item()) if (rank == 0 and edges_all is not None) else 0
     plan = eng.dp_plan(max_len)
     del rs, pa, pb, edges, edges_all
+    if world > 1:
+        exchange = "NCCL send/recv gather of the per-rank edge slices"
+        if not args.no_peer_stores:
+            try:
+                peer = par.PeerEdgeBuffer(n_edges, dev)
+                # self-check: the peer-store path must reproduce the gathered list
+                _, _, _, _, chk_all = device_step()
+                ok = torch.tensor([1 if (rank != 0 or int(chk_all.to(torch.int64).sum().item()) == checksum) else 0],
+                                  device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok.item()) != 1:
+                    raise RuntimeError("peer-store edge list differs from the gathered one")
+                exchange = "DP epilogue stores edge rows directly into rank 0's HBM (NVLink peer memory)"
+            except Exception as exc:                      # noqa: BLE001
+                if rank == 0:
+                    print(f"[bench] peer-memory path unavailable ({exc}); using the NCCL gather", file=sys.stderr)
+                peer = None
 
     # ---- value leg: inputs resident in HBM
     sampler = ClockSampler(local_rank)
@@ -421,7 +445,7 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": args.workload, "k": args.k, "seed": args.seed, "reads": n_reads,
                            "unique_reads": U, "max_read_len": max_len, "candidate_pairs": pairs, "edges": n_edges,
-                           "cells": cells, "edge_checksum": checksum, "sharding": f"pair-range x{world}",
+                           "cells": cells, "edge_checksum": checksum, "sharding": f"pair-range x{world}", "exchange": exchange,
                            "l2": "flushed between timed iterations (256 MiB memset)",
                            "scoring": "match 10, mismatch -1, indel -2^31 (reference defaults)"},
                 "pairs_per_s": pairs / (kmer_total_ms / args.steps * 1e-3),
@@ -455,6 +479,7 @@ def main():
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peer-stores", action="store_true", help="N>1: gather with NCCL instead of peer-memory stores")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

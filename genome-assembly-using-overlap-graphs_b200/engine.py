@@ -228,12 +228,14 @@ class OverlapEngine:
     def overlap_edges_fused(self, rs: ReadSet, pair_a: torch.Tensor, pair_b: torch.Tensor,
                             copies: Optional[torch.Tensor] = None, node_off: Optional[torch.Tensor] = None,
                             match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT,
-                            events=None) -> torch.Tensor:
+                            events=None, sink=None) -> Optional[torch.Tensor]:
         """DP + edge expansion in one kernel (overlapGraphs.py:53-60): the DP epilogue writes the
         copy_a x copy_b edge rows, so score/end never travel through HBM."""
         P = int(pair_a.shape[0])
         st = self._stream()
         if P == 0:
+            if sink is not None:
+                sink(0)                            # collective sinks must be called by every rank
             return torch.empty((0, 4), dtype=torch.int32, device=self.device)
         edge_off = None
         E = P
@@ -245,17 +247,24 @@ class OverlapEngine:
                                                _ptr(edge_off), _ptr(ws), ws_bytes, st))
             self.launches += 1 if P <= 16384 else 3
             E = int(edge_off[P].item())                       # host sync: the output size
-        edges = self._empty(E * 4, torch.int32)
+        if sink is not None:
+            # `sink(E)` returns a raw device address -- possibly in a PEER GPU's memory (NVLink): the
+            # kernel's epilogue stores the rows there directly (parallel.PeerEdgeBuffer)
+            edges = None
+            out_ptr = ctypes.c_void_p(int(sink(E)))
+        else:
+            edges = self._empty(E * 4, torch.int32)
+            out_ptr = _ptr(edges)
         if events is not None:
             events[0].record()
         nat.check(nat.lib.ovl_overlap_dp_edges(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length),
                                                _ptr(pair_a), _ptr(pair_b), P, rs.max_len,
                                                int(match_score), int(mismatch), int(indel),
-                                               _ptr(copies), _ptr(node_off), _ptr(edge_off), _ptr(edges), st))
+                                               _ptr(copies), _ptr(node_off), _ptr(edge_off), out_ptr, st))
         if events is not None:
             events[1].record()
         self.launches += 1
-        return edges[:E * 4].view(E, 4)
+        return None if edges is None else edges[:E * 4].view(E, 4)
 
     def overlap_edges_fused_to_host(self, rs: ReadSet, pair_a: torch.Tensor, pair_b: torch.Tensor,
                                     copies: Optional[torch.Tensor] = None, node_off: Optional[torch.Tensor] = None,

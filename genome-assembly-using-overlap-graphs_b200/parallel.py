@@ -136,3 +136,48 @@ class SharedEdgeSink:
     def close(self):
         dist.barrier(group=self.group)
         self._release()
+
+
+class PeerEdgeBuffer:
+    """Fused compute + gather over NVLink peer memory: the destination rank's edge buffer is a
+    symmetric-memory allocation mapped into every rank's address space, and the DP kernel's fused
+    epilogue (csrc/dp.cuh, DpEdgeOut) stores its 16-byte edge rows straight into it at the rank's
+    global row offset.  No separate gather pass, no staging copy: the only collective left is the
+    exchange of the per-rank row counts (one all-gather of an int64) and a barrier.
+
+    `slot(n_local)` is the `sink` of OverlapEngine.overlap_edges_fused(): it returns the raw device
+    address (in the destination's buffer) where this rank's rows start.
+    """
+
+    def __init__(self, rows: int, device, group=None, dst: int = 0):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.dst = dst
+        self.capacity = int(rows + rows // 16 + 1024)
+        self.local = symm.empty(self.capacity * 4, dtype=torch.int32, device=device)
+        self.hdl = symm.rendezvous(self.local, self.group)
+        self.dst_ptr = int(self.hdl.buffer_ptrs[dst])
+        self.total = 0
+        self._sizes = torch.zeros(self.world, dtype=torch.int64, device=device)
+
+    def slot(self, n_local: int) -> int:
+        n = torch.tensor([int(n_local)], dtype=torch.int64, device=self.local.device)
+        dist.all_gather_into_tensor(self._sizes, n, group=self.group)
+        sizes = self._sizes.cpu().tolist()
+        self.total = int(sum(sizes))
+        if self.total > self.capacity:
+            raise RuntimeError(f"peer edge buffer too small: {self.total} rows > capacity {self.capacity}")
+        return self.dst_ptr + 16 * int(sum(sizes[:self.rank]))
+
+    def barrier(self) -> None:
+        """All ranks' kernels have finished storing (stream-ordered) and the stores are visible."""
+        torch.cuda.current_stream(self.local.device).synchronize()
+        self.hdl.barrier()
+
+    def result(self):
+        """The complete ordered edge list on the destination rank (None elsewhere)."""
+        if self.rank != self.dst:
+            return None
+        return self.local[:self.total * 4].view(self.total, 4)
