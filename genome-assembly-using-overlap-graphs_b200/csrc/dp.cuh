@@ -76,6 +76,9 @@ constexpr int kDpThreads = 128;
 #define OVL_DP_PREPACK 0       // 1: take the packed constants from the kernel parameters (measured slower: 8.4 vs
                                // 8.95 TCUPS; gap costs as immediates were slower too: 8.75 vs 9.09)
 #endif
+#ifndef OVL_DP_PLAIN_ADD
+#define OVL_DP_PLAIN_ADD 0
+#endif
 #ifndef OVL_DP_KUNROLL
 #define OVL_DP_KUNROLL 1       // unroll factor of the row loop
 #endif
@@ -92,9 +95,14 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 }
 // a + c as IMAD (a * 1 + c): runs on the FMA pipe instead of the ALU pipe
 __device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t one, uint32_t c) {
+#if OVL_DP_PLAIN_ADD
+    (void)one;
+    return a + c;                  // let ptxas pick IADD3 (ALU) or IMAD.IADD with an immediate 1 (FMA)
+#else
     uint32_t d;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(c));
     return d;
+#endif
 }
 __device__ __forceinline__ uint32_t base_code(const uint32_t* row, int i) {
     return (row[i >> 4] >> ((i & 15) * 2)) & 3u;

@@ -561,6 +561,11 @@ int ovl_int_peak_probe(ovl_ctx* ctx, int32_t kind, int32_t iters, double* h_gops
         case 9: return run_probe<9>(ctx, iters, h_gops, h_ms);
         case 10: return run_probe<10>(ctx, iters, h_gops, h_ms);
         case 11: return run_probe<11>(ctx, iters, h_gops, h_ms);
+        case 12: return run_probe<12>(ctx, iters, h_gops, h_ms);
+        case 13: return run_probe<13>(ctx, iters, h_gops, h_ms);
+        case 14: return run_probe<14>(ctx, iters, h_gops, h_ms);
+        case 15: return run_probe<15>(ctx, iters, h_gops, h_ms);
+        case 16: return run_probe<16>(ctx, iters, h_gops, h_ms);
         default: return fail(OVL_E_ARG, "ovl_int_peak_probe: unknown kind %d", kind);
     }
 }

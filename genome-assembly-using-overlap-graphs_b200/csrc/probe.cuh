@@ -68,6 +68,25 @@ __global__ void __launch_bounds__(kProbeThreads) int_probe_kernel(uint32_t* out,
                     asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a1) : "r"(dc), "r"(one), "r"(z[c]));
                     asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a3) : "r"(v[c]), "r"(one), "r"(a0));
                     v[c] = __vimin3_u16x2(a1, w[c], a3);
+                } else if (KIND == 12) {    // PRMT + VIADDMNMX on independent chains (ALU only)
+                    asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(v[c]) : "r"(x[c]), "r"(y[c]));
+                    w[c] = __viaddmin_u16x2(w[c], b0, z[c]);
+                } else if (KIND == 13) {    // VIADDMNMX + IMAD on independent chains
+                    v[c] = __viaddmin_u16x2(v[c], b0, x[c]);
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(w[c]) : "r"(one), "r"(z[c]));
+                } else if (KIND == 14) {    // PRMT + IMAD on independent chains
+                    asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(v[c]) : "r"(x[c]), "r"(y[c]));
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(w[c]) : "r"(one), "r"(z[c]));
+                } else if (KIND == 15) {    // 2x VIADDMNMX + IMAD (no PRMT), independent chains
+                    v[c] = __viaddmin_u16x2(v[c], b0, x[c]);
+                    y[c] = __viaddmin_u16x2(y[c], a0, x[c]);
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(w[c]) : "r"(one), "r"(z[c]));
+                } else if (KIND == 16) {    // form-1 column but the diagonal add on the ALU (IADD3) instead of IMAD
+                    uint32_t dc;
+                    asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(dc) : "r"(x[c]), "r"(y[c]), "r"(v[c]));
+                    uint32_t a1 = dc + z[c];
+                    uint32_t t1 = __viaddmin_u16x2(w[c], b0, a1);
+                    v[c] = __viaddmin_u16x2(v[c], a0, t1);
                 } else if (KIND == 5) {     // PRMT
                     asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(v[c]) : "r"(w[c]), "r"(b0));
                 } else {                    // LOP3
@@ -84,8 +103,9 @@ __global__ void __launch_bounds__(kProbeThreads) int_probe_kernel(uint32_t* out,
 
 inline int probe_ops_per_iter(int kind) {
     if (kind == 10) return 5;
-    if (kind == 4 || kind == 9 || kind == 11) return 4;
-    return (kind == 7 || kind == 8) ? 2 : 1;
+    if (kind == 4 || kind == 9 || kind == 11 || kind == 16) return 4;
+    if (kind == 15) return 3;
+    return (kind == 7 || kind == 8 || kind == 12 || kind == 13 || kind == 14) ? 2 : 1;
 }
 
 }  // namespace ovl
