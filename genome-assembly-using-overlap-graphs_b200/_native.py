@@ -45,6 +45,7 @@ _SIGS = {
     "ovl_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_vp)]),
     "ovl_ctx_destroy": (ctypes.c_int, [_vp]),
     "ovl_ctx_sm_count": (ctypes.c_int, [_vp]),
+    "ovl_ctx_launch_count": (_i64, [_vp]),
     "ovl_row_words": (_i32, [_i32]),
     "ovl_pack_reads": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "ovl_kmer_keys": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),

@@ -20,6 +20,7 @@ struct ovl_ctx {
     int device;
     int sm_count;
     uint32_t* probe_sink;
+    long long launches;          // kernels launched through this context (bench bookkeeping)
 };
 
 static thread_local char g_err[512] = "";
@@ -42,6 +43,7 @@ static int fail(int code, const char* fmt, ...) {
 
 #define LAUNCH_CHECK(name)                                                                   \
     do {                                                                                     \
+        ctx->launches += 1;                                                                  \
         cudaError_t e__ = cudaGetLastError();                                                \
         if (e__ != cudaSuccess)                                                              \
             return fail(OVL_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
@@ -72,6 +74,7 @@ int ovl_ctx_create(int device, ovl_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->probe_sink = nullptr;
+    c->launches = 0;
     *out = c;
     return OVL_OK;
 }
@@ -84,6 +87,7 @@ int ovl_ctx_destroy(ovl_ctx* ctx) {
 }
 
 int ovl_ctx_sm_count(const ovl_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+int64_t ovl_ctx_launch_count(const ovl_ctx* ctx) { return ctx ? (int64_t)ctx->launches : 0; }
 
 int32_t ovl_row_words(int32_t max_len) {
     int32_t w = (max_len + 15) / 16;
@@ -147,6 +151,7 @@ int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len
     if (key_bits <= 0) key_bits = 2 * k;                 // no segment tag above the k-mer
     if (key_bits < 2 * k || key_bits > 64) return fail(OVL_E_ARG, "ovl_index_build: key_bits=%d outside [2k, 64]", key_bits);
     int passes = (key_bits + 7) / 8;
+    int nl = 0;
     // ping-pong so that the last pass lands in (sorted_key, sorted_uid)
     uint64_t* kbuf[2] = {sorted_key, tmp_key};
     uint32_t* ubuf[2] = {sorted_uid, tmp_uid};
@@ -162,7 +167,7 @@ int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len
             radix_hist_kernel<false><<<grid, kSortThreads, 0, st>>>(src_key, len, k, n_indexed, 0, shift, W, hist);
         }
         LAUNCH_CHECK("radix_hist_kernel");
-        CUDA_TRY((exclusive_scan<LoadArray<int32_t>, int32_t>(LoadArray<int32_t>{hist}, hist, 256 * W, sums, st)));
+        CUDA_TRY((exclusive_scan<LoadArray<int32_t>, int32_t>(LoadArray<int32_t>{hist}, hist, 256 * W, sums, st, &nl)));
         if (p == 0) {
             radix_scatter_kernel<true><<<grid, kSortThreads, 0, st>>>(src_key, nullptr, len, k, nullptr, U, shift, W, hist,
                                                                        kbuf[dst], ubuf[dst], n_indexed);
@@ -175,6 +180,7 @@ int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len
         src_uid = ubuf[dst];
         dst ^= 1;
     }
+    ctx->launches += nl;
     return OVL_OK;
 }
 
@@ -203,7 +209,9 @@ int ovl_join_count(ovl_ctx* ctx, const uint64_t* suffix_key, const uint64_t* pre
                                                               n_indexed, bucket_lo, self_rank, cnt);
         LAUNCH_CHECK("join_count_kernel");
     }
-    CUDA_TRY((exclusive_scan<LoadArray<int64_t>, int64_t>(LoadArray<int64_t>{cnt}, pair_off, nA, sums, st)));
+    int nl = 0;
+    CUDA_TRY((exclusive_scan<LoadArray<int64_t>, int64_t>(LoadArray<int64_t>{cnt}, pair_off, nA, sums, st, &nl)));
+    ctx->launches += nl;
     return OVL_OK;
 }
 
@@ -324,7 +332,7 @@ bool dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_t indel, in
 }
 
 template <int G, int T, bool PK>
-int launch_dp(const uint32_t* packed, int32_t row_words, const int32_t* len, const int32_t* pair_a, const int32_t* pair_b,
+int launch_dp(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, const int32_t* pair_a, const int32_t* pair_b,
               int64_t P, int32_t max_len, const DpParams& prm, int32_t* score, int32_t* end, const DpEdgeOut& eo, cudaStream_t st) {
     constexpr int PAIRS = PK ? 2 : 1;
     constexpr int GROUPS_PER_CTA = (kDpThreads / 32) * (32 / G);
@@ -345,7 +353,7 @@ int launch_dp(const uint32_t* packed, int32_t row_words, const int32_t* len, con
 }
 
 #define DP_CASE(G_, T_, PK_) \
-    if (plan.G == G_ && plan.T == T_) return launch_dp<G_, T_, PK_>(packed, row_words, len, pair_a, pair_b, P, max_len, plan.prm, score, end, eo, st);
+    if (plan.G == G_ && plan.T == T_) return launch_dp<G_, T_, PK_>(ctx, packed, row_words, len, pair_a, pair_b, P, max_len, plan.prm, score, end, eo, st);
 #define DP_CASES_T(T_, PK_) \
     DP_CASE(1, T_, PK_) DP_CASE(2, T_, PK_) DP_CASE(4, T_, PK_) DP_CASE(8, T_, PK_) DP_CASE(16, T_, PK_) DP_CASE(32, T_, PK_)
 
@@ -424,7 +432,9 @@ int ovl_expand_count(ovl_ctx* ctx, const int32_t* pair_a, const int32_t* pair_b,
     cudaStream_t st = (cudaStream_t)stream;
     void* sums = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     // the per-pair edge count copies[a]*copies[b] is computed inside the scan: no count array
-    CUDA_TRY((exclusive_scan<CopyProduct, int64_t>(CopyProduct{pair_a, pair_b, copies}, edge_off, P, sums, st)));
+    int nl = 0;
+    CUDA_TRY((exclusive_scan<CopyProduct, int64_t>(CopyProduct{pair_a, pair_b, copies}, edge_off, P, sums, st, &nl)));
+    ctx->launches += nl;
     return OVL_OK;
 }
 
@@ -461,7 +471,9 @@ int ovl_filter_count(ovl_ctx* ctx, const int32_t* edges, int64_t E, int32_t min_
     if (!ctx || !keep_off || !workspace || (E > 0 && !edges)) return fail(OVL_E_ARG, "ovl_filter_count: null argument");
     if (workspace_bytes < ovl_filter_workspace_bytes(E)) return fail(OVL_E_ARG, "ovl_filter_count: workspace too small");
     void* sums = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    CUDA_TRY((exclusive_scan<EdgeKept, int64_t>(EdgeKept{(const int4*)edges, min_weight}, keep_off, E, sums, (cudaStream_t)stream)));
+    int nl = 0;
+    CUDA_TRY((exclusive_scan<EdgeKept, int64_t>(EdgeKept{(const int4*)edges, min_weight}, keep_off, E, sums, (cudaStream_t)stream, &nl)));
+    ctx->launches += nl;
     return OVL_OK;
 }
 

@@ -57,8 +57,12 @@ class OverlapEngine:
         nat.check(nat.lib.ovl_ctx_create(self.device_index, ctypes.byref(ctx)))
         self._ctx = ctx
         self.sm_count = int(nat.lib.ovl_ctx_sm_count(ctx))
-        self.launches = 0          # kernels launched through this engine (bench bookkeeping)
         self._pinned_out = None    # reusable pinned host buffer for edge rows (D2H at full PCIe rate)
+
+    @property
+    def launches(self) -> int:
+        """Kernels launched through this engine's context so far (counted inside libovl_b200.so)."""
+        return int(nat.lib.ovl_ctx_launch_count(self._ctx)) if getattr(self, "_ctx", None) else 0
 
     def close(self) -> None:
         if getattr(self, "_ctx", None):
@@ -124,7 +128,6 @@ class OverlapEngine:
         bad = torch.zeros(1, dtype=torch.int32, device=self.device)
         nat.check(nat.lib.ovl_pack_reads(self._ctx, _ptr(ascii_dev), _ptr(off_dev), U, row_words,
                                          _ptr(packed), _ptr(length), _ptr(bad), self._stream()))
-        self.launches += 1 if U > 0 else 0
         return ReadSet(packed, length, bad, row_words, U, max_len)
 
     def check_alphabet(self, rs: ReadSet) -> None:
@@ -159,8 +162,6 @@ class OverlapEngine:
         ws = self._empty(ws_bytes, torch.uint8)
         nat.check(nat.lib.ovl_index_build(self._ctx, _ptr(pk), _ptr(rs.length), U, k, key_bits, _ptr(sorted_key), _ptr(sorted_uid),
                                           _ptr(n_indexed), _ptr(ws), ws_bytes, self._stream()))
-        if U > 0:
-            self.launches += 1 + 5 * (((key_bits or 2 * k) + 7) // 8)
         return KmerIndex(k, pk, sk, sorted_key, sorted_uid, n_indexed)
 
     # ------------------------------------------------------------------ K3
@@ -180,7 +181,6 @@ class OverlapEngine:
             pair_b = self._empty(P, torch.int32)
             if P:
                 nat.check(nat.lib.ovl_all_pairs_fill(self._ctx, U, 0, p_begin, P, _ptr(pair_a), _ptr(pair_b), st))
-                self.launches += 1
             return pair_a[:P], pair_b[:P], p_begin
         assert index is not None and index.k == k
         lo = self._empty(U, torch.int32)
@@ -192,7 +192,6 @@ class OverlapEngine:
                                          _ptr(rs.length), k, 0, U,
                                          _ptr(index.sorted_key), _ptr(index.sorted_uid), _ptr(index.n_indexed),
                                          _ptr(lo), _ptr(self_rank), _ptr(pair_off), _ptr(ws), ws_bytes, st))
-        self.launches += 4 if U > 0 else 0
         total = int(pair_off[U].item())                      # host sync: the output size
         p_begin, p_end = total * rank // world, total * (rank + 1) // world
         P = p_end - p_begin
@@ -201,7 +200,6 @@ class OverlapEngine:
         if P:
             nat.check(nat.lib.ovl_join_fill(self._ctx, _ptr(pair_off), 0, U, _ptr(lo), _ptr(self_rank),
                                             _ptr(index.sorted_uid), p_begin, P, total, _ptr(pair_a), _ptr(pair_b), st))
-            self.launches += 1
         return pair_a[:P], pair_b[:P], p_begin
 
     # ------------------------------------------------------------------ K4 / K5
@@ -222,7 +220,6 @@ class OverlapEngine:
                                              _ptr(pair_a), _ptr(pair_b), P, rs.max_len,
                                              int(match_score), int(mismatch), int(indel),
                                              _ptr(score), _ptr(end), mode, lanes, cols, self._stream()))
-            self.launches += 1
         return score[:P], end[:P]
 
     def overlap_edges_fused(self, rs: ReadSet, pair_a: torch.Tensor, pair_b: torch.Tensor,
@@ -245,7 +242,6 @@ class OverlapEngine:
             ws = self._empty(ws_bytes, torch.uint8)
             nat.check(nat.lib.ovl_expand_count(self._ctx, _ptr(pair_a), _ptr(pair_b), _ptr(copies), P,
                                                _ptr(edge_off), _ptr(ws), ws_bytes, st))
-            self.launches += 1 if P <= 16384 else 3
             E = int(edge_off[P].item())                       # host sync: the output size
         if sink is not None:
             # `sink(E)` returns a raw device address -- possibly in a PEER GPU's memory (NVLink): the
@@ -263,7 +259,6 @@ class OverlapEngine:
                                                _ptr(copies), _ptr(node_off), _ptr(edge_off), out_ptr, st))
         if events is not None:
             events[1].record()
-        self.launches += 1
         return None if edges is None else edges[:E * 4].view(E, 4)
 
     def overlap_edges_fused_to_host(self, rs: ReadSet, pair_a: torch.Tensor, pair_b: torch.Tensor,
@@ -291,7 +286,6 @@ class OverlapEngine:
             ws = self._empty(ws_bytes, torch.uint8)
             nat.check(nat.lib.ovl_expand_count(self._ctx, _ptr(pair_a), _ptr(pair_b), _ptr(copies), P,
                                                _ptr(edge_off), _ptr(ws), ws_bytes, st))
-            self.launches += 1 if P <= 16384 else 3
             idx = torch.tensor(bounds, dtype=torch.int64, device=self.device)
             e_bounds = edge_off[idx].cpu().tolist()           # host sync: output size + chunk boundaries
         else:
@@ -322,7 +316,6 @@ class OverlapEngine:
                                                    a_ptr, b_ptr, p1 - p0, rs.max_len,
                                                    int(match_score), int(mismatch), int(indel),
                                                    _ptr(copies), _ptr(node_off), off_ptr, out_ptr, st))
-            self.launches += 1
             done = torch.cuda.Event()
             done.record(main)
             e0, e1 = int(e_bounds[c]), int(e_bounds[c + 1])
@@ -359,7 +352,6 @@ class OverlapEngine:
         t_ptr = ctypes.c_void_p(dev.data_ptr() + 4 * n)
         nat.check(nat.lib.ovl_align_pair(self._ctx, s_ptr, n, t_ptr, m, int(match_score), int(mismatch), int(indel),
                                          _ptr(ws), ws_bytes, _ptr(result), _ptr(ops), self._stream()))
-        self.launches += 1
         res = result.cpu().numpy()
         n_ops = int(res[2])
         return int(res[0]), int(res[1]), ops[:n_ops].cpu().numpy()
@@ -380,7 +372,6 @@ class OverlapEngine:
                                           ctypes.c_void_p(dev.data_ptr() + 4 * n), m,
                                           int(match_score), int(mismatch), int(indel),
                                           _ptr(ws), ws_bytes, _ptr(result), _ptr(ops), self._stream()))
-        self.launches += 1
         res = result.cpu().numpy()
         return int(res[0]), int(res[1]), int(res[2]), int(res[4]), ops[:int(res[3])].cpu().numpy()
 
@@ -398,21 +389,18 @@ class OverlapEngine:
             if P:
                 nat.check(nat.lib.ovl_expand_unit(self._ctx, _ptr(pair_a), _ptr(pair_b), _ptr(score), _ptr(end),
                                                   P, _ptr(edges), st))
-                self.launches += 1
             return edges[:P * 4].view(P, 4)
         edge_off = self._empty(P + 1, torch.int64)
         ws_bytes = int(nat.lib.ovl_expand_workspace_bytes(P))
         ws = self._empty(ws_bytes, torch.uint8)
         nat.check(nat.lib.ovl_expand_count(self._ctx, _ptr(pair_a), _ptr(pair_b), _ptr(copies), P,
                                            _ptr(edge_off), _ptr(ws), ws_bytes, st))
-        self.launches += 1 if P <= 16384 else 3
         E = int(edge_off[P].item())                           # host sync: the output size
         edges = self._empty(E * 4, torch.int32)
         if E:
             nat.check(nat.lib.ovl_expand_fill(self._ctx, _ptr(edge_off), P, _ptr(pair_a), _ptr(pair_b),
                                               _ptr(score), _ptr(end), _ptr(copies), _ptr(node_off), 0, E,
                                               _ptr(edges), st))
-            self.launches += 1
         return edges[:E * 4].view(E, 4)
 
     def filter_edges(self, edges: torch.Tensor, min_weight: int) -> torch.Tensor:
@@ -428,7 +416,6 @@ class OverlapEngine:
         kept = int(keep_off[E].item())
         out = self._empty(kept * 4, torch.int32)
         nat.check(nat.lib.ovl_filter_fill(self._ctx, _ptr(edges), _ptr(keep_off), E, int(min_weight), _ptr(out), st))
-        self.launches += 2 if E <= 16384 else 4
         return out[:kept * 4].view(kept, 4)
 
     # ------------------------------------------------------------------ whole path

@@ -42,6 +42,8 @@ int ovl_version(void);
 int ovl_ctx_create(int device, ovl_ctx **out);
 int ovl_ctx_destroy(ovl_ctx *ctx);
 int ovl_ctx_sm_count(const ovl_ctx *ctx);
+/* number of kernels launched through this context so far (measurement bookkeeping) */
+int64_t ovl_ctx_launch_count(const ovl_ctx *ctx);
 
 /* words per packed row for reads up to max_len bases: ceil(max_len/16) rounded up to a
  * multiple of 4 so that every row is 16-byte aligned. */
