@@ -13,13 +13,17 @@ namespace ovl {
 
 constexpr int kAlignThreads = 1024;
 
-// workspace layout (int32 units): diag[3][n+1] | last_row[m+1] ; then tb[(n+1)*(m+1)] bytes
+// workspace layout (int32 units): diag[3][n+1] | last_row[m+1] ; then tb[(n+1)*(m+1)] bytes.
+// SMEM = true keeps the three rolling anti-diagonals in shared memory (when 3*(n+1) ints fit).
+template <bool SMEM>
 __global__ void __launch_bounds__(kAlignThreads) align_pair_kernel(const int32_t* __restrict__ s, int n,
                                                                    const int32_t* __restrict__ t, int m,
                                                                    int64_t match, int64_t mismatch, int64_t indel,
-                                                                   int32_t* __restrict__ diag, int32_t* __restrict__ last_row,
+                                                                   int32_t* __restrict__ diag_g, int32_t* __restrict__ last_row,
                                                                    int8_t* __restrict__ tb,
                                                                    int32_t* __restrict__ result, uint8_t* __restrict__ ops) {
+    extern __shared__ int32_t diag_sh[];
+    int32_t* diag = SMEM ? diag_sh : diag_g;
     const int W = m + 1;
     const int stride = n + 1;
     for (int j = threadIdx.x; j <= m; j += blockDim.x) last_row[j] = 0;     // n == 0: row 0 is all zero
@@ -70,13 +74,18 @@ __global__ void __launch_bounds__(kAlignThreads) align_pair_kernel(const int32_t
 // with the tie order diag >= up >= left >= "restart" (aligners.py:121-132), the best cell is the
 // first strict maximum in row-major order (:135-137), the walk stops at a zero cell (:143-160).
 // tb byte = direction (1 diag, 2 up, 3 left, 0 restart) | 4 if the cell value is > 0.
+// The three rolling anti-diagonals live in shared memory when 3*(n+1) ints fit (SMEM = true: one
+// shared-memory round trip per diagonal instead of an L2 one), else in the global workspace.
+template <bool SMEM>
 __global__ void __launch_bounds__(kAlignThreads) local_align_kernel(const int32_t* __restrict__ q, int n,
                                                                     const int32_t* __restrict__ ref, int m,
                                                                     int64_t match, int64_t mismatch, int64_t indel,
-                                                                    int32_t* __restrict__ diag, int8_t* __restrict__ tb,
+                                                                    int32_t* __restrict__ diag_g, int8_t* __restrict__ tb,
                                                                     int32_t* __restrict__ result, uint8_t* __restrict__ ops) {
     __shared__ int32_t s_best[kAlignThreads / 32];
     __shared__ int32_t s_bi[kAlignThreads / 32], s_bj[kAlignThreads / 32];
+    extern __shared__ int32_t diag_s[];
+    int32_t* diag = SMEM ? diag_s : diag_g;
     const int W = m + 1;
     const int stride = n + 1;
     for (int i = threadIdx.x; i < 3 * stride; i += blockDim.x) diag[i] = 0;
@@ -106,7 +115,9 @@ __global__ void __launch_bounds__(kAlignThreads) local_align_kernel(const int32_
         if (threadIdx.x == 0) { cur[0] = 0; if (d <= n) cur[d] = 0; }
         __syncthreads();
     }
-    // block arg-max with the same tie rule
+    // block arg-max with the same tie rule (warps beyond blockDim hold the neutral (0, 0, 0))
+    if (threadIdx.x < kAlignThreads / 32) { s_best[threadIdx.x] = 0; s_bi[threadIdx.x] = 0; s_bj[threadIdx.x] = 0; }
+    __syncthreads();
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         int32_t ob = __shfl_xor_sync(kFull, best, off), oi = __shfl_xor_sync(kFull, bi, off), oj = __shfl_xor_sync(kFull, bj, off);

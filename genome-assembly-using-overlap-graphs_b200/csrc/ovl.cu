@@ -503,7 +503,15 @@ int ovl_align_pair(ovl_ctx* ctx, const int32_t* s, int32_t n, const int32_t* t, 
     int32_t* diag = (int32_t*)ws;
     int32_t* last_row = diag + (size_t)3 * (n + 1);
     int8_t* tb = (int8_t*)(ws + align256(((size_t)3 * (n + 1) + (size_t)(m + 1)) * sizeof(int32_t)));
-    align_pair_kernel<<<1, kAlignThreads, 0, (cudaStream_t)stream>>>(s, n, t, m, match, mismatch, indel, diag, last_row, tb, result, ops);
+    int threads = std::min(kAlignThreads, std::max(32, ((std::max(std::min(n, m), 1) + 31) / 32) * 32));
+    size_t smem = (size_t)3 * (n + 1) * sizeof(int32_t);
+    if (smem <= 200 * 1024) {
+        if (smem > 48 * 1024)
+            CUDA_TRY(cudaFuncSetAttribute(align_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        align_pair_kernel<true><<<1, threads, smem, (cudaStream_t)stream>>>(s, n, t, m, match, mismatch, indel, diag, last_row, tb, result, ops);
+    } else {
+        align_pair_kernel<false><<<1, threads, 0, (cudaStream_t)stream>>>(s, n, t, m, match, mismatch, indel, diag, last_row, tb, result, ops);
+    }
     LAUNCH_CHECK("align_pair_kernel");
     return OVL_OK;
 }
@@ -524,7 +532,16 @@ int ovl_local_align(ovl_ctx* ctx, const int32_t* query, int32_t n, const int32_t
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     int32_t* diag = (int32_t*)ws;
     int8_t* tb = (int8_t*)(ws + align256((size_t)3 * (n + 1) * sizeof(int32_t)));
-    local_align_kernel<<<1, kAlignThreads, 0, (cudaStream_t)stream>>>(query, n, reference, m, match, mismatch, indel, diag, tb, result, ops);
+    // as many threads as the longest anti-diagonal needs (a block barrier per diagonal: fewer warps, cheaper barrier)
+    int threads = std::min(kAlignThreads, std::max(32, ((std::min(n, m) + 31) / 32) * 32));
+    size_t smem = (size_t)3 * (n + 1) * sizeof(int32_t);
+    if (smem <= 200 * 1024) {
+        if (smem > 48 * 1024)
+            CUDA_TRY(cudaFuncSetAttribute(local_align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        local_align_kernel<true><<<1, threads, smem, (cudaStream_t)stream>>>(query, n, reference, m, match, mismatch, indel, diag, tb, result, ops);
+    } else {
+        local_align_kernel<false><<<1, threads, 0, (cudaStream_t)stream>>>(query, n, reference, m, match, mismatch, indel, diag, tb, result, ops);
+    }
     LAUNCH_CHECK("local_align_kernel");
     return OVL_OK;
 }

@@ -164,6 +164,16 @@ class OverlapEngine:
                                           _ptr(n_indexed), _ptr(ws), ws_bytes, self._stream()))
         return KmerIndex(k, pk, sk, sorted_key, sorted_uid, n_indexed)
 
+    def _check_fits(self, pairs: int, what: str) -> None:
+        """Refuse loudly (instead of running the GPU out of memory) when the pair list, its edge
+        offsets and the edge rows of `pairs` candidate pairs cannot fit in free HBM."""
+        need = int(pairs) * (4 + 4 + 8 + 16) + (64 << 20)
+        free, _ = torch.cuda.mem_get_info(self.device)
+        free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+        if need > free:
+            raise nat.OvlUnsupported(f"{what}: {pairs:,} candidate pairs need about {need / 2**30:.1f} GiB of HBM "
+                                     f"({free / 2**30:.1f} GiB free); use a larger k or shard over more GPUs")
+
     # ------------------------------------------------------------------ K3
     def candidate_pairs(self, rs: ReadSet, index: Optional[KmerIndex], k: int,
                         shard: Tuple[int, int] = (0, 1)) -> Tuple[torch.Tensor, torch.Tensor, int]:
@@ -177,6 +187,7 @@ class OverlapEngine:
             total = U * (U - 1) if U > 1 else 0
             p_begin, p_end = total * rank // world, total * (rank + 1) // world
             P = p_end - p_begin
+            self._check_fits(P, "k = 0 (all ordered pairs)")
             pair_a = self._empty(P, torch.int32)
             pair_b = self._empty(P, torch.int32)
             if P:
@@ -195,6 +206,7 @@ class OverlapEngine:
         total = int(pair_off[U].item())                      # host sync: the output size
         p_begin, p_end = total * rank // world, total * (rank + 1) // world
         P = p_end - p_begin
+        self._check_fits(P, f"k = {k}")
         pair_a = self._empty(P, torch.int32)
         pair_b = self._empty(P, torch.int32)
         if P:

@@ -261,6 +261,15 @@ def test_batch_dp_wide_scores_use_int32_kernel(eng):
         assert np.array_equal(s, ws) and np.array_equal(e, we), prm
 
 
+def test_oversized_pair_list_is_refused_not_oom(eng, nat):
+    """k = 0 on 300,000 reads would be 9e10 pairs (~2.6 TiB): a clear error, not an out-of-memory crash."""
+    rng = random.Random(8)
+    reads = list(dict.fromkeys(rand_reads(rng, 300000, 12, 14)))
+    rs, _, _ = upload(eng, reads)
+    with pytest.raises(nat.OvlUnsupported, match="GiB"):
+        eng.candidate_pairs(rs, None, 0)
+
+
 def test_batch_dp_unsupported_is_loud(eng, nat):
     reads = ["ACGT" * 10, "CGTA" * 10]
     pa, pb = np.array([0], np.int32), np.array([1], np.int32)
