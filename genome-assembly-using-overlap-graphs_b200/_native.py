@@ -49,6 +49,10 @@ _SIGS = {
     "ovl_row_words": (_i32, [_i32]),
     "ovl_pack_reads": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "ovl_kmer_keys": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "ovl_kmer_hashes": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "ovl_join_count_verify": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ovl_join_fill_verify": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i64,
+                                            _vp, _vp, _vp]),
     "ovl_index_workspace_bytes": (_sz, [_i64]),
     "ovl_index_build": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ovl_join_workspace_bytes": (_sz, [_i64]),

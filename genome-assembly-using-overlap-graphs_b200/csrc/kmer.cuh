@@ -126,6 +126,85 @@ __global__ void __launch_bounds__(256) kmer_keys_kernel(const uint32_t* __restri
     suffix_key[u] = sk;
 }
 
+// ------------------------------------------------------------------ K1h / K3v: k > 32
+// A k-mer longer than 32 bases does not fit a u64, so the index is built on a 64-bit HASH of the
+// k-mer and the join verifies every candidate by comparing the two k-mers base by base (2-bit
+// words): equal hashes are necessary, the comparison makes the result exact.  Buckets are tiny at
+// such k, so one thread per source read walks its hash bucket.
+__device__ __forceinline__ uint64_t kmer_word(const uint32_t* __restrict__ row, int row_words, int start, int k, int w) {
+    // bases [start + 32w, start + 32w + 32) of the read, clipped to the k-mer, as one 64-bit word
+    uint64_t v = extract_bits64(row, row_words, 2 * (start + 32 * w));
+    int left = k - 32 * w;
+    return left >= 32 ? v : (v & ((1ull << (2 * left)) - 1ull));
+}
+__device__ __forceinline__ uint64_t kmer_hash(const uint32_t* __restrict__ row, int row_words, int start, int k) {
+    uint64_t h = 0x243f6a8885a308d3ull ^ (uint64_t)k;
+    for (int w = 0; 32 * w < k; ++w) {
+        h ^= kmer_word(row, row_words, start, k, w);
+        h *= 0x9e3779b97f4a7c15ull;
+        h ^= h >> 32;
+    }
+    return h;
+}
+__device__ __forceinline__ bool kmer_equal(const uint32_t* __restrict__ ra, int sa, const uint32_t* __restrict__ rb, int sb,
+                                           int row_words, int k) {
+    for (int w = 0; 32 * w < k; ++w)
+        if (kmer_word(ra, row_words, sa, k, w) != kmer_word(rb, row_words, sb, k, w)) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) kmer_hash_kernel(const uint32_t* __restrict__ packed, int row_words,
+                                                        const int32_t* __restrict__ len, int64_t U, int k,
+                                                        uint64_t* __restrict__ prefix_key, uint64_t* __restrict__ suffix_key) {
+    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= U) return;
+    int n = len[u];
+    uint64_t pk = 0, sk = 0;
+    if (n >= k) {
+        const uint32_t* row = packed + u * row_words;
+        pk = kmer_hash(row, row_words, 0, k);
+        sk = kmer_hash(row, row_words, n - k, k);
+    }
+    prefix_key[u] = pk;
+    suffix_key[u] = sk;
+}
+
+// count (FILL = false) or write (FILL = true) the verified candidates of every source read
+template <bool FILL>
+__global__ void __launch_bounds__(256) join_verify_kernel(const uint32_t* __restrict__ packed, int row_words,
+                                                          const int32_t* __restrict__ len, int k,
+                                                          const uint64_t* __restrict__ suffix_key, int64_t nA, int64_t a_begin,
+                                                          const uint64_t* __restrict__ sorted_key, const uint32_t* __restrict__ sorted_uid,
+                                                          const int64_t* __restrict__ n_indexed,
+                                                          int64_t* __restrict__ cnt_out,            // !FILL
+                                                          const int64_t* __restrict__ pair_off,      // FILL
+                                                          int64_t p_begin, int64_t p_count,
+                                                          int32_t* __restrict__ pair_a, int32_t* __restrict__ pair_b) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nA) return;
+    int64_t a = a_begin + i;
+    int64_t cnt = 0;
+    int na = len[a];
+    if (na >= k) {
+        uint64_t key = suffix_key[a];
+        int64_t n = *n_indexed;
+        int64_t lo = lower_bound<uint64_t>(sorted_key, 0, n, key);
+        const uint32_t* ra = packed + a * row_words;
+        int64_t out = FILL ? pair_off[i] : 0;
+        for (int64_t j = lo; j < n && sorted_key[j] == key; ++j) {
+            int64_t b = sorted_uid[j];
+            if (b == a) continue;                                        // overlapGraphs.py:52
+            if (!kmer_equal(ra, na - k, packed + b * row_words, 0, row_words, k)) continue;   // hash collision
+            if (FILL) {
+                int64_t q = out + cnt - p_begin;
+                if (q >= 0 && q < p_count) { pair_a[q] = (int32_t)a; pair_b[q] = (int32_t)b; }
+            }
+            ++cnt;
+        }
+    }
+    if (!FILL) cnt_out[i] = cnt;
+}
+
 // ------------------------------------------------------------------ K2 radix sort (stable, LSD, 8-bit digits)
 // Each warp owns kSortChunk consecutive elements; a pass is: per-warp digit histogram ->
 // exclusive scan over (digit-major, warp-minor) -> per-warp stable scatter.  Stability keeps

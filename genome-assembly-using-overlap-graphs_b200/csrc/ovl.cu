@@ -119,6 +119,16 @@ int ovl_kmer_keys(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const
     return OVL_OK;
 }
 
+int ovl_kmer_hashes(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, int64_t U, int32_t k,
+                    uint64_t* prefix_key, uint64_t* suffix_key, void* stream) {
+    if (!ctx || !packed || !len || !prefix_key || !suffix_key) return fail(OVL_E_ARG, "ovl_kmer_hashes: null argument");
+    if (k < 1) return fail(OVL_E_ARG, "ovl_kmer_hashes: k must be positive");
+    if (U <= 0) return OVL_OK;
+    kmer_hash_kernel<<<grid_for(U, 256), 256, 0, (cudaStream_t)stream>>>(packed, row_words, len, U, k, prefix_key, suffix_key);
+    LAUNCH_CHECK("kmer_hash_kernel");
+    return OVL_OK;
+}
+
 // ---------------------------------------------------------------- K2
 // workspace: [hist int32 256*W][scan sums][tmp keys u64 U][tmp uids u32 U]
 static inline int64_t sort_warps(int64_t U) { return (U + kSortChunk - 1) / kSortChunk; }
@@ -137,7 +147,8 @@ size_t ovl_index_workspace_bytes(int64_t U) {
 int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len, int64_t U, int32_t k, int32_t key_bits, uint64_t* sorted_key,
                     uint32_t* sorted_uid, int64_t* n_indexed, void* workspace, size_t workspace_bytes, void* stream) {
     if (!ctx || !prefix_key || !len || !sorted_key || !sorted_uid || !n_indexed || !workspace) return fail(OVL_E_ARG, "ovl_index_build: null argument");
-    if (k < 1 || k > OVL_MAX_K) return fail(OVL_E_UNSUPPORTED, "ovl_index_build: k=%d outside 1..%d", k, OVL_MAX_K);
+    if (k < 1) return fail(OVL_E_ARG, "ovl_index_build: k must be positive");
+    if (k > OVL_MAX_K && key_bits != 64) return fail(OVL_E_ARG, "ovl_index_build: k=%d > %d needs hashed keys (key_bits = 64)", k, OVL_MAX_K);
     if (workspace_bytes < ovl_index_workspace_bytes(U)) return fail(OVL_E_ARG, "ovl_index_build: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     if (U <= 0) { CUDA_TRY(cudaMemsetAsync(n_indexed, 0, sizeof(int64_t), st)); return OVL_OK; }
@@ -149,7 +160,7 @@ int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len
     uint32_t* tmp_uid = (uint32_t*)ws;
 
     if (key_bits <= 0) key_bits = 2 * k;                 // no segment tag above the k-mer
-    if (key_bits < 2 * k || key_bits > 64) return fail(OVL_E_ARG, "ovl_index_build: key_bits=%d outside [2k, 64]", key_bits);
+    if ((key_bits < 2 * k && k <= OVL_MAX_K) || key_bits > 64) return fail(OVL_E_ARG, "ovl_index_build: key_bits=%d outside [2k, 64]", key_bits);
     int passes = (key_bits + 7) / 8;
     int nl = 0;
     // ping-pong so that the last pass lands in (sorted_key, sorted_uid)
@@ -231,6 +242,45 @@ int ovl_join_fill(ovl_ctx* ctx, const int64_t* pair_off, int64_t a_begin, int64_
             pair_off, nA, a_begin, bucket_lo, self_rank, sorted_uid, p_begin, p_count, pair_a, pair_b);
         LAUNCH_CHECK("join_fill_kernel");
     }
+    return OVL_OK;
+}
+
+int ovl_join_count_verify(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, int32_t k,
+                          const uint64_t* suffix_hash, int64_t a_begin, int64_t a_end, const uint64_t* sorted_hash,
+                          const uint32_t* sorted_uid, const int64_t* n_indexed, int64_t* pair_off, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    if (!ctx || !packed || !len || !suffix_hash || !sorted_hash || !sorted_uid || !n_indexed || !pair_off || !workspace)
+        return fail(OVL_E_ARG, "ovl_join_count_verify: null argument");
+    int64_t nA = a_end - a_begin;
+    if (nA < 0) return fail(OVL_E_ARG, "ovl_join_count_verify: a_end < a_begin");
+    if (workspace_bytes < ovl_join_workspace_bytes(nA)) return fail(OVL_E_ARG, "ovl_join_count_verify: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    int64_t* cnt = (int64_t*)ws;
+    void* sums = ws + align256((size_t)std::max<int64_t>(nA, 1) * sizeof(int64_t));
+    if (nA > 0) {
+        join_verify_kernel<false><<<grid_for(nA, 256), 256, 0, st>>>(packed, row_words, len, k, suffix_hash, nA, a_begin, sorted_hash,
+                                                                     sorted_uid, n_indexed, cnt, nullptr, 0, 0, nullptr, nullptr);
+        LAUNCH_CHECK("join_verify_kernel<count>");
+    }
+    int nl = 0;
+    CUDA_TRY((exclusive_scan<LoadArray<int64_t>, int64_t>(LoadArray<int64_t>{cnt}, pair_off, nA, sums, st, &nl)));
+    ctx->launches += nl;
+    return OVL_OK;
+}
+
+int ovl_join_fill_verify(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, int32_t k,
+                         const uint64_t* suffix_hash, int64_t a_begin, int64_t a_end, const uint64_t* sorted_hash,
+                         const uint32_t* sorted_uid, const int64_t* n_indexed, const int64_t* pair_off, int64_t p_begin,
+                         int64_t p_count, int32_t* pair_a, int32_t* pair_b, void* stream) {
+    if (!ctx || !packed || !len || !suffix_hash || !sorted_hash || !sorted_uid || !n_indexed || !pair_off || !pair_a || !pair_b)
+        return fail(OVL_E_ARG, "ovl_join_fill_verify: null argument");
+    int64_t nA = a_end - a_begin;
+    if (nA <= 0 || p_count <= 0) return OVL_OK;
+    join_verify_kernel<true><<<grid_for(nA, 256), 256, 0, (cudaStream_t)stream>>>(packed, row_words, len, k, suffix_hash, nA, a_begin,
+                                                                                   sorted_hash, sorted_uid, n_indexed, nullptr,
+                                                                                   pair_off, p_begin, p_count, pair_a, pair_b);
+    LAUNCH_CHECK("join_verify_kernel<fill>");
     return OVL_OK;
 }
 

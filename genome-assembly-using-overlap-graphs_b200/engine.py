@@ -142,9 +142,12 @@ class OverlapEngine:
                    n_segments: int = 1) -> KmerIndex:
         """Prefix index (overlapGraphs.py:30-40).  `segments` (int32[U] device tensor) tags every read
         with its read set; reads of different sets then never share a key."""
-        if k < 1 or k > nat.OVL_MAX_K:
-            raise nat.OvlUnsupported(f"k={k}: the k-mer index covers 1 <= k <= {nat.OVL_MAX_K}")
-        key_bits = 0
+        if k < 1:
+            raise ValueError("k must be positive for the k-mer index")
+        hashed = k > nat.OVL_MAX_K          # the k-mer does not fit a u64: index 64-bit hashes, verify in the join
+        key_bits = 64 if hashed else 0
+        if segments is not None and hashed:
+            raise nat.OvlUnsupported(f"batched read sets with k={k} > {nat.OVL_MAX_K} are not supported")
         if segments is not None:
             seg_bits = max(1, int(n_segments - 1).bit_length())
             key_bits = 2 * k + seg_bits
@@ -153,8 +156,12 @@ class OverlapEngine:
         U = rs.n_reads
         pk = self._empty(U, torch.int64)
         sk = self._empty(U, torch.int64)
-        nat.check(nat.lib.ovl_kmer_keys(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length), U, k,
-                                        _ptr(segments), _ptr(pk), _ptr(sk), self._stream()))
+        if hashed:
+            nat.check(nat.lib.ovl_kmer_hashes(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length), U, k,
+                                              _ptr(pk), _ptr(sk), self._stream()))
+        else:
+            nat.check(nat.lib.ovl_kmer_keys(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length), U, k,
+                                            _ptr(segments), _ptr(pk), _ptr(sk), self._stream()))
         sorted_key = self._empty(U, torch.int64)
         sorted_uid = self._empty(U, torch.int32)
         n_indexed = torch.zeros(1, dtype=torch.int64, device=self.device)
@@ -194,6 +201,8 @@ class OverlapEngine:
                 nat.check(nat.lib.ovl_all_pairs_fill(self._ctx, U, 0, p_begin, P, _ptr(pair_a), _ptr(pair_b), st))
             return pair_a[:P], pair_b[:P], p_begin
         assert index is not None and index.k == k
+        if k > nat.OVL_MAX_K:
+            return self._candidate_pairs_hashed(rs, index, k, shard)
         lo = self._empty(U, torch.int32)
         self_rank = self._empty(U, torch.int32)
         pair_off = self._empty(U + 1, torch.int64)
@@ -212,6 +221,31 @@ class OverlapEngine:
         if P:
             nat.check(nat.lib.ovl_join_fill(self._ctx, _ptr(pair_off), 0, U, _ptr(lo), _ptr(self_rank),
                                             _ptr(index.sorted_uid), p_begin, P, total, _ptr(pair_a), _ptr(pair_b), st))
+        return pair_a[:P], pair_b[:P], p_begin
+
+    def _candidate_pairs_hashed(self, rs: ReadSet, index: KmerIndex, k: int, shard: Tuple[int, int]):
+        """k > OVL_MAX_K: the index holds hashes; every hash match is verified base by base."""
+        U = rs.n_reads
+        rank, world = shard
+        st = self._stream()
+        pair_off = self._empty(U + 1, torch.int64)
+        ws_bytes = int(nat.lib.ovl_join_workspace_bytes(U))
+        ws = self._empty(ws_bytes, torch.uint8)
+        nat.check(nat.lib.ovl_join_count_verify(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length), k,
+                                                _ptr(index.suffix_key), 0, U, _ptr(index.sorted_key),
+                                                _ptr(index.sorted_uid), _ptr(index.n_indexed), _ptr(pair_off),
+                                                _ptr(ws), ws_bytes, st))
+        total = int(pair_off[U].item())
+        p_begin, p_end = total * rank // world, total * (rank + 1) // world
+        P = p_end - p_begin
+        self._check_fits(P, f"k = {k}")
+        pair_a = self._empty(P, torch.int32)
+        pair_b = self._empty(P, torch.int32)
+        if P:
+            nat.check(nat.lib.ovl_join_fill_verify(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length), k,
+                                                   _ptr(index.suffix_key), 0, U, _ptr(index.sorted_key),
+                                                   _ptr(index.sorted_uid), _ptr(index.n_indexed), _ptr(pair_off),
+                                                   p_begin, P, _ptr(pair_a), _ptr(pair_b), st))
         return pair_a[:P], pair_b[:P], p_begin
 
     # ------------------------------------------------------------------ K4 / K5

@@ -31,7 +31,7 @@ extern "C" {
 #define OVL_E_ARG (-2)       /* invalid argument */
 #define OVL_E_UNSUPPORTED (-3) /* valid for the reference, outside what the kernels implement */
 
-#define OVL_MAX_K 32          /* k-mer keys are 2k-bit integers in a uint64 */
+#define OVL_MAX_K 32          /* k-mer keys are 2k-bit integers in a uint64; larger k: hashed keys + verify */
 #define OVL_MAX_READ_LEN 1216 /* longest read the wavefront DP covers (32 lanes x 38 columns) */
 
 typedef struct ovl_ctx ovl_ctx;
@@ -72,6 +72,12 @@ int ovl_kmer_keys(ovl_ctx *ctx, const uint32_t *packed, int32_t row_words, const
                   int64_t U, int32_t k, const int32_t *segment, uint64_t *prefix_key,
                   uint64_t *suffix_key, void *stream);
 
+/* k > OVL_MAX_K: 64-bit hashes of the prefix / suffix k-mers instead of the k-mers themselves.  Build
+ * the index on them with ovl_index_build(key_bits = 64) and use the *_verify join below, which
+ * compares the actual k-mers of every hash match (exact result, same candidate order). */
+int ovl_kmer_hashes(ovl_ctx *ctx, const uint32_t *packed, int32_t row_words, const int32_t *len,
+                    int64_t U, int32_t k, uint64_t *prefix_hash, uint64_t *suffix_hash, void *stream);
+
 /* K2: the prefix index, overlapGraphs.py:30-40, as a stable sort of (prefix_key, uid):
  * sorted_key / sorted_uid hold the *n_indexed reads with len >= k, keys ascending and uids
  * ascending inside equal keys (the reference's bucket-append order). */
@@ -98,6 +104,17 @@ int ovl_join_fill(ovl_ctx *ctx, const int64_t *pair_off, int64_t a_begin, int64_
                   const int32_t *bucket_lo, const int32_t *self_rank, const uint32_t *sorted_uid,
                   int64_t p_begin, int64_t p_count, int64_t total_hint, int32_t *pair_a,
                   int32_t *pair_b, void *stream);
+/* The same join on hashed keys (k > OVL_MAX_K): every hash match is verified base by base. */
+int ovl_join_count_verify(ovl_ctx *ctx, const uint32_t *packed, int32_t row_words, const int32_t *len,
+                          int32_t k, const uint64_t *suffix_hash, int64_t a_begin, int64_t a_end,
+                          const uint64_t *sorted_hash, const uint32_t *sorted_uid,
+                          const int64_t *n_indexed, int64_t *pair_off, void *workspace,
+                          size_t workspace_bytes, void *stream);
+int ovl_join_fill_verify(ovl_ctx *ctx, const uint32_t *packed, int32_t row_words, const int32_t *len,
+                         int32_t k, const uint64_t *suffix_hash, int64_t a_begin, int64_t a_end,
+                         const uint64_t *sorted_hash, const uint32_t *sorted_uid,
+                         const int64_t *n_indexed, const int64_t *pair_off, int64_t p_begin,
+                         int64_t p_count, int32_t *pair_a, int32_t *pair_b, void *stream);
 /* k == 0 (overlapGraphs.py:49): all ordered pairs a != b, a in [a_begin, ...); pair index p
  * counts from a_begin: a = a_begin + p / (U-1). */
 int ovl_all_pairs_fill(ovl_ctx *ctx, int64_t U, int64_t a_begin, int64_t p_begin, int64_t p_count,

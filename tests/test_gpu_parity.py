@@ -193,6 +193,24 @@ def test_keys_index_and_join(eng, k):
     assert np.array_equal(torch.cat([p[1] for p in parts]).cpu().numpy(), wb)
 
 
+@pytest.mark.parametrize("k", [33, 40, 64, 65, 100])
+def test_join_with_hashed_keys_for_long_k(eng, k):
+    """k > 32: the index holds 64-bit hashes and the join verifies every match base by base."""
+    import torch
+    rng = random.Random(k)
+    reads = list(dict.fromkeys(overlapping_reads(rng, 1200, 900, 130, 0.004) + rand_reads(rng, 40, 0, 120) +
+                               ["G" * 120, "G" * 101 + "A", "A" + "G" * 110]))
+    rs, _, _ = upload(eng, reads)
+    idx = eng.kmer_index(rs, k)
+    pa, pb, _ = eng.candidate_pairs(rs, idx, k)
+    wa, wb = orc.candidate_pairs(reads, k)
+    assert len(wa) > 0
+    assert np.array_equal(pa.cpu().numpy(), wa) and np.array_equal(pb.cpu().numpy(), wb)
+    parts = [eng.candidate_pairs(rs, idx, k, (r, 3)) for r in range(3)]
+    assert np.array_equal(torch.cat([p[0] for p in parts]).cpu().numpy(), wa)
+    assert np.array_equal(torch.cat([p[1] for p in parts]).cpu().numpy(), wb)
+
+
 def test_all_pairs_k0(eng):
     reads = list(dict.fromkeys(rand_reads(random.Random(1), 40, 1, 12)))
     rs, _, _ = upload(eng, reads)
@@ -283,10 +301,6 @@ def test_batch_dp_unsupported_is_loud(eng, nat):
 def test_graph_builder_golden(golden_graphs, nat):
     g = load_pkg("overlapGraphs")
     for c in golden_graphs:
-        if c["k"] > nat.OVL_MAX_K:
-            with pytest.raises(nat.OvlUnsupported):
-                g.construct_overlap_graph_nx_k(c["reads"], k=c["k"])
-            continue
         G, read_copies = g.construct_overlap_graph_nx_k(c["reads"], k=c["k"])
         assert [[r, n] for r, n in read_copies.items()] == c["read_copies"], c["name"]
         nodes = list(G.nodes)
