@@ -65,7 +65,10 @@ struct DpEdgeOut {
     const int64_t* edge_off;     // exclusive scan of copies[a]*copies[b] over the pair list
 };
 
-constexpr int kDpThreads = 128;
+#ifndef OVL_DP_THREADS
+#define OVL_DP_THREADS 128
+#endif
+constexpr int kDpThreads = OVL_DP_THREADS;
 #ifndef OVL_DP_MINB
 #define OVL_DP_MINB 3          // resident CTAs per SM the register allocator must allow (168 regs; measured best)
 #endif

@@ -362,7 +362,7 @@ bool dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_t indel, in
     for (int m = 1; m <= 2; ++m) {
         if (mode != 0 && mode != m) continue;
         const int* Ts = m == 1 ? kPackedT : kScalarT;
-        int nT = m == 1 ? 4 : 1;
+        int nT = m == 1 ? (int)(sizeof(kPackedT) / sizeof(int)) : 1;
         int64_t best = -1;
         for (int gi = 0; gi < 6; ++gi) {
             for (int ti = 0; ti < nT; ++ti) {
