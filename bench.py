@@ -300,20 +300,26 @@ def run_ours(args):
     if world > 1:
         exchange = "NCCL send/recv gather of the per-rank edge slices"
         if not args.no_peer_stores:
+            err = None
             try:
                 peer = par.PeerEdgeBuffer(n_edges, dev)
+            except Exception as exc:                      # noqa: BLE001
+                err, peer = exc, None
+            agree = torch.tensor([1 if peer is not None else 0], device=dev)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)  # every rank takes the same path
+            if int(agree.item()) != 1:
+                peer = None
+                if rank == 0:
+                    print(f"[bench] peer-memory path unavailable ({err}); using the NCCL gather", file=sys.stderr)
+            else:
                 # self-check: the peer-store path must reproduce the gathered list
                 _, _, _, _, chk_all = device_step()
                 ok = torch.tensor([1 if (rank != 0 or int(chk_all.to(torch.int64).sum().item()) == checksum) else 0],
                                   device=dev)
                 dist.all_reduce(ok, op=dist.ReduceOp.MIN)
                 if int(ok.item()) != 1:
-                    raise RuntimeError("peer-store edge list differs from the gathered one")
+                    raise SystemExit("peer-store edge list differs from the gathered one")
                 exchange = "DP epilogue stores edge rows directly into rank 0's HBM (NVLink peer memory)"
-            except Exception as exc:                      # noqa: BLE001
-                if rank == 0:
-                    print(f"[bench] peer-memory path unavailable ({exc}); using the NCCL gather", file=sys.stderr)
-                peer = None
 
     # ---- value leg: inputs resident in HBM
     sampler = ClockSampler(local_rank)
