@@ -57,6 +57,7 @@ class OverlapEngine:
         nat.check(nat.lib.ovl_ctx_create(self.device_index, ctypes.byref(ctx)))
         self._ctx = ctx
         self.sm_count = int(nat.lib.ovl_ctx_sm_count(ctx))
+        self._total_mem = int(torch.cuda.get_device_properties(self.device).total_memory)
         self._pinned_out = None    # reusable pinned host buffer for edge rows (D2H at full PCIe rate)
 
     @property
@@ -175,6 +176,8 @@ class OverlapEngine:
         """Refuse loudly (instead of running the GPU out of memory) when the pair list, its edge
         offsets and the edge rows of `pairs` candidate pairs cannot fit in free HBM."""
         need = int(pairs) * (4 + 4 + 8 + 16) + (64 << 20)
+        if need < self._total_mem // 4:
+            return                                 # cudaMemGetInfo costs milliseconds: only ask when it can matter
         free, _ = torch.cuda.mem_get_info(self.device)
         free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
         if need > free:
