@@ -16,7 +16,7 @@ OVL_E_CUDA = -1
 OVL_E_ARG = -2
 OVL_E_UNSUPPORTED = -3
 OVL_MAX_K = 32
-OVL_MAX_READ_LEN = 1216
+OVL_MAX_READ_LEN = 2432
 
 
 class OvlError(RuntimeError):

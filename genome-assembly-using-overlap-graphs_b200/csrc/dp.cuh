@@ -143,7 +143,7 @@ __host__ __device__ inline int dp_lut_rows(int max_len) {
 
 // PK = true : two pairs per group (unsigned 16-bit halves).  PK = false: one pair per group (s32).
 template <int G, int T, bool PK>
-__global__ void __launch_bounds__(kDpThreads, OVL_DP_MINB) overlap_dp_kernel(
+__global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : OVL_DP_MINB)) overlap_dp_kernel(
     const uint32_t* __restrict__ packed, int row_words, const int32_t* __restrict__ len,
     const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b, int64_t P, int lut_rows,
     DpParams prm, int32_t* __restrict__ score_out, int32_t* __restrict__ end_out, DpEdgeOut eo) {

@@ -305,7 +305,7 @@ struct DpPlan {
     DpParams prm;
 };
 
-const int kPackedT[] = {19, 25, 32, 38};
+const int kPackedT[] = {19, 25, 32, 38, 76};   // 76 columns per lane only with 16 or 32 lanes (reads > 1,216 bases)
 const int kScalarT[] = {32};
 const int kLanes[] = {1, 2, 4, 8, 16, 32};
 
@@ -369,6 +369,7 @@ bool dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_t indel, in
                 int G = kLanes[gi], T = Ts[ti];
                 if (forceG && G != forceG) continue;
                 if (forceT && T != forceT) continue;
+                if (T == 76 && G < 16) continue;
                 if ((int64_t)G * T < N) continue;
                 DpParams prm;
                 if (!dp_params(match, mismatch, indel, N, (int64_t)G * T, m == 1, &prm)) continue;
@@ -440,6 +441,7 @@ static int dp_dispatch(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, 
     cudaStream_t st = (cudaStream_t)stream;
     if (plan.mode == 1) {
         DP_CASES_T(19, true) DP_CASES_T(25, true) DP_CASES_T(32, true) DP_CASES_T(38, true)
+        DP_CASE(16, 76, true) DP_CASE(32, 76, true)
     } else {
         DP_CASES_T(32, false)
     }

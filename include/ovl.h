@@ -32,7 +32,7 @@ extern "C" {
 #define OVL_E_UNSUPPORTED (-3) /* valid for the reference, outside what the kernels implement */
 
 #define OVL_MAX_K 32          /* k-mer keys are 2k-bit integers in a uint64; larger k: hashed keys + verify */
-#define OVL_MAX_READ_LEN 1216 /* longest read the wavefront DP covers (32 lanes x 38 columns) */
+#define OVL_MAX_READ_LEN 2432 /* longest read the wavefront DP covers (32 lanes x 76 columns) */
 
 typedef struct ovl_ctx ovl_ctx;
 

@@ -46,6 +46,8 @@ def test_host_only_entry_points():
     assert nat.lib.ovl_overlap_dp_plan(150, 10, -1000000, -2 ** 31, 0, ctypes.byref(out)) == 0
     assert out[0] == 2
     # too long for the wavefront kernels
+    assert nat.lib.ovl_overlap_dp_plan(2000, 10, -1, -2 ** 31, 0, ctypes.byref(out)) == 0
+    assert list(out) == [1, 32, 76]
     assert nat.lib.ovl_overlap_dp_plan(5000, 10, -1, -2, 0, ctypes.byref(out)) == nat.OVL_E_UNSUPPORTED
     assert b"5000" in nat.lib.ovl_last_error()
 

@@ -138,7 +138,7 @@ def np_key(r, k, suffix):
     return v
 
 
-@pytest.mark.parametrize("lo,hi,n", [(0, 40, 500), (1, 150, 700), (990, 1000, 40), (1, 1216, 30)])
+@pytest.mark.parametrize("lo,hi,n", [(0, 40, 500), (1, 150, 700), (990, 1000, 40), (1, 2432, 30)])
 def test_pack_reads(eng, lo, hi, n):
     import torch
     rng = random.Random(lo * 1000 + hi)
@@ -234,7 +234,7 @@ def run_dp(eng, reads, pa, pb, prm, **kw):
     return score.cpu().numpy(), end.cpu().numpy(), ws, we
 
 
-@pytest.mark.parametrize("max_len", [1, 7, 25, 38, 64, 100, 150, 151, 300, 1000, 1216])
+@pytest.mark.parametrize("max_len", [1, 7, 25, 38, 64, 100, 150, 151, 300, 1000, 1216, 1217, 2432])
 def test_batch_dp_lengths(eng, max_len):
     rng = random.Random(max_len)
     n_reads = 60 if max_len > 300 else 300
@@ -256,10 +256,10 @@ def test_batch_dp_every_instantiation(eng, nat):
         pa = np.array([rng.randrange(len(reads)) for _ in range(n_pairs)], dtype=np.int32)
         pb = np.array([rng.randrange(len(reads)) for _ in range(n_pairs)], dtype=np.int32)
         tried = 0
-        for mode, cols_list in [(1, (19, 25, 32, 38)), (2, (32,))]:
+        for mode, cols_list in [(1, (19, 25, 32, 38, 76)), (2, (32,))]:
             for lanes in (1, 2, 4, 8, 16, 32):
                 for cols in cols_list:
-                    if lanes * cols < max(len(r) for r in reads):
+                    if lanes * cols < max(len(r) for r in reads) or (cols == 76 and lanes < 16):
                         continue
                     for prm in [(10, -1, -2 ** 31), (10, -1, -2)]:
                         s, e, ws, we = run_dp(eng, reads, pa, pb, prm, mode=mode, lanes=lanes, cols=cols)
@@ -294,7 +294,7 @@ def test_batch_dp_unsupported_is_loud(eng, nat):
     with pytest.raises(nat.OvlUnsupported):
         run_dp(eng, reads, pa, pb, (2 ** 40, -1, -2))            # would overflow int32 storage
     with pytest.raises(nat.OvlUnsupported):
-        upload(eng, ["A" * 1300])                                # longer than the wavefront covers
+        upload(eng, ["A" * 2500])                                # longer than the wavefront covers
 
 
 # --------------------------------------------------------------------------- whole builder
