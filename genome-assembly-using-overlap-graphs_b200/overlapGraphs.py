@@ -41,6 +41,19 @@ def _flatten(uniq):
     return bases, offsets
 
 
+def _to_acgt(bases):
+    """Re-letter a read set that uses at most four distinct symbols (lower case, RNA, ...) as A/C/G/T.
+    Keys and the DP only test symbols for equality, so any bijection leaves every result unchanged."""
+    symbols = np.unique(bases)
+    if symbols.size > 4:
+        raise _engine.nat.OvlUnsupported(
+            f"reads use {symbols.size} distinct symbols ({bytes(symbols[:8]).decode('latin-1')!r}...); the 2-bit CUDA "
+            "path covers alphabets of at most four symbols")
+    lut = np.zeros(256, dtype=np.uint8)
+    lut[symbols] = np.frombuffer(b"ACGT", dtype=np.uint8)[:symbols.size]
+    return lut[bases]
+
+
 def overlap_edge_rows(reads, k=5, _reuse_host_buffer=False, min_weight=None):
     """The device part of the builder: returns (read_copies, uniq, counts, edges) where edges
     is int32[E, 4] = (node_a, node_b, weight, end_position) in insertion order and node ids
@@ -58,7 +71,13 @@ def overlap_edge_rows(reads, k=5, _reuse_host_buffer=False, min_weight=None):
         return read_copies, uniq, counts, np.zeros((0, 4), np.int32)
     bases, offsets = _flatten(uniq)
     eng = _engine.get_engine()
-    edges = eng.overlap_edges(bases, offsets, counts, k, reuse_host_buffer=_reuse_host_buffer, min_weight=min_weight)
+    try:
+        edges = eng.overlap_edges(bases, offsets, counts, k, reuse_host_buffer=_reuse_host_buffer, min_weight=min_weight)
+    except _engine.nat.OvlUnsupported as exc:
+        if "other than A, C, G, T" not in str(exc):
+            raise
+        edges = eng.overlap_edges(_to_acgt(bases), offsets, counts, k, reuse_host_buffer=_reuse_host_buffer,
+                                  min_weight=min_weight)
     return read_copies, uniq, counts, edges
 
 

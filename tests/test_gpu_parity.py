@@ -158,7 +158,13 @@ def test_pack_rejects_non_acgt(eng, nat):
             eng.check_alphabet(rs)
     g = load_pkg("overlapGraphs")
     with pytest.raises(nat.OvlUnsupported):
-        g.construct_overlap_graph_nx_k(["ACGTN", "GTNAC"], k=2)
+        g.construct_overlap_graph_nx_k(["ACGTN", "GTNAC"], k=2)          # five symbols
+    # at most four distinct symbols of any kind are re-lettered on the host and give the exact graph
+    for reads in (["acgtac", "gtacgg", "acggta"], ["ACGUAC", "GUACGG", "ACGGUA"], ["xyxxy", "xxyxy", "yxyxx", "xyxxy"]):
+        G, rc = g.construct_overlap_graph_nx_k(reads, k=2)
+        nodes, edges, rc2 = orc.construct_overlap_graph(reads, 2)
+        assert list(rc.items()) == list(rc2.items()) and list(G.nodes) == nodes
+        assert list(G.edges(data=True)) == list(orc.to_networkx(nodes, edges).edges(data=True))
 
 
 @pytest.mark.parametrize("k", [1, 3, 5, 8, 15, 16, 17, 31, 32])
