@@ -17,6 +17,7 @@ OVL_E_ARG = -2
 OVL_E_UNSUPPORTED = -3
 OVL_MAX_K = 32
 OVL_MAX_READ_LEN = 2432
+OVL_MAX_LONG_READ_LEN = 16384
 
 
 class OvlError(RuntimeError):

@@ -361,4 +361,82 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : OVL_DP_MINB)) overla
     }
 }
 
+// ------------------------------------------------------------------ long reads
+// Reads longer than the register wavefront covers (32 lanes x 76 columns): one CTA per pair sweeps
+// the anti-diagonals with three rolling diagonals in shared memory (int32 cost space, same
+// recurrence, same first-minimum rule).  Slower per cell than the packed kernel, any length whose
+// diagonals fit shared memory (3 * (n+1) ints).
+constexpr int kDpLongThreads = 256;
+
+__global__ void __launch_bounds__(kDpLongThreads) overlap_dp_long_kernel(
+    const uint32_t* __restrict__ packed, int row_words, const int32_t* __restrict__ len,
+    const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b, int64_t P,
+    DpParams prm, int32_t* __restrict__ score_out, int32_t* __restrict__ end_out, DpEdgeOut eo) {
+    extern __shared__ int32_t diag_l[];
+    __shared__ int s_best[kDpLongThreads / 32], s_bj[kDpLongThreads / 32];
+    const int64_t p = blockIdx.x;
+    if (p >= P) return;
+    const int32_t a = pair_a[p], b = pair_b[p];
+    const int n = len[a], m = len[b];
+    const uint32_t* srow = packed + (size_t)a * row_words;
+    const uint32_t* trow = packed + (size_t)b * row_words;
+    const int stride = n + 1;
+    // C[i][j] = beta + i*maxs - H[i][j];  row 0: beta, column 0: beta + i*maxs
+    for (int i = threadIdx.x; i < 3 * stride; i += blockDim.x) diag_l[i] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        diag_l[0] = prm.beta;                                   // d = 0: C[0][0]
+        diag_l[stride + 0] = prm.beta;                          // d = 1: C[0][1]
+        if (n >= 1) diag_l[stride + 1] = prm.beta + prm.maxs;   //        C[1][0]
+    }
+    int bestv = INT_MAX, bestj = 0;                             // last row: first minimum over j >= 1
+    __syncthreads();
+    for (int d = 2; d <= n + m; ++d) {
+        int32_t* cur = diag_l + (d % 3) * stride;
+        const int32_t* p1 = diag_l + ((d - 1) % 3) * stride;
+        const int32_t* p2 = diag_l + ((d - 2) % 3) * stride;
+        int ilo = max(1, d - m), ihi = min(n, d - 1);
+        for (int i = ilo + (int)threadIdx.x; i <= ihi; i += blockDim.x) {
+            int j = d - i;
+            int dc = base_code(srow, i - 1) == base_code(trow, j - 1) ? prm.eqc : prm.nec;
+            int v = min(min(p2[i - 1] + dc, p1[i - 1] + prm.gu), p1[i] + prm.gl);
+            cur[i] = v;
+            if (i == n && v < bestv) { bestv = v; bestj = j; }   // one thread owns row n: j ascending
+        }
+        if (threadIdx.x == 0) {
+            if (d <= m) cur[0] = prm.beta;                       // C[0][d]
+            if (d <= n) cur[d] = prm.beta + d * prm.maxs;        // C[d][0]
+        }
+        __syncthreads();
+    }
+    // the cells of row n are visited by different threads (i == n lands on thread (n - ilo) % blockDim):
+    // reduce (value, then smaller j)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        int ov = __shfl_xor_sync(kFull, bestv, off), oj = __shfl_xor_sync(kFull, bestj, off);
+        if (ov < bestv || (ov == bestv && oj < bestj)) { bestv = ov; bestj = oj; }
+    }
+    if (lane_id() == 0) { s_best[threadIdx.x >> 5] = bestv; s_bj[threadIdx.x >> 5] = bestj; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kDpLongThreads / 32; ++w)
+            if (s_best[w] < bestv || (s_best[w] == bestv && s_bj[w] < bestj)) { bestv = s_best[w]; bestj = s_bj[w]; }
+        int c0 = prm.beta + n * prm.maxs;                        // j = 0 (aligners.py:51-57): wins ties, it comes first
+        if (n == 0 || m == 0 || c0 <= bestv) { bestv = c0; bestj = 0; }
+        const int32_t score = prm.beta + n * prm.maxs - bestv;
+        if (eo.edges == nullptr) {
+            score_out[p] = score;
+            end_out[p] = bestj;
+        } else if (eo.copies == nullptr) {
+            eo.edges[p] = make_int4(a, b, score, bestj);
+        } else {
+            const int32_t ca = eo.copies[a], cb = eo.copies[b];
+            const int32_t na = (int32_t)eo.node_off[a], nb = (int32_t)eo.node_off[b];
+            int4* dst = eo.edges + eo.edge_off[p];
+            for (int32_t ia = 0; ia < ca; ++ia)
+                for (int32_t ib = 0; ib < cb; ++ib) *dst++ = make_int4(na + ia, nb + ib, score, bestj);
+        }
+    }
+}
+
 }  // namespace ovl

@@ -413,8 +413,16 @@ int launch_dp(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int
 extern "C" {
 
 int ovl_overlap_dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_t indel, int32_t mode, int32_t out[3]) {
-    if (max_len > OVL_MAX_READ_LEN)
-        return fail(OVL_E_UNSUPPORTED, "overlap DP: read length %d exceeds the supported maximum %d", max_len, OVL_MAX_READ_LEN);
+    if (max_len > OVL_MAX_LONG_READ_LEN)
+        return fail(OVL_E_UNSUPPORTED, "overlap DP: read length %d exceeds the supported maximum %d", max_len, OVL_MAX_LONG_READ_LEN);
+    if (max_len > OVL_MAX_READ_LEN) {
+        DpParams prm;
+        if (mode == 1 || !dp_params(match, mismatch, indel, max_len, max_len, false, &prm))
+            return fail(OVL_E_UNSUPPORTED, "overlap DP: scores for (match=%lld, mismatch=%lld, indel=%lld, len=%d) do not fit the long-read kernel",
+                        (long long)match, (long long)mismatch, (long long)indel, max_len);
+        out[0] = 3; out[1] = 0; out[2] = 0;        // mode 3: CTA-per-pair anti-diagonal kernel
+        return OVL_OK;
+    }
     DpPlan plan;
     if (!dp_plan(max_len, match, mismatch, indel, mode, 0, 0, &plan))
         return fail(OVL_E_UNSUPPORTED, "overlap DP: scores for (match=%lld, mismatch=%lld, indel=%lld, len=%d) do not fit the %s kernels",
@@ -432,8 +440,23 @@ static int dp_dispatch(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, 
     if (!ctx || !packed || !len || !pair_a || !pair_b) return fail(OVL_E_ARG, "%s: null argument", who);
     if (P <= 0) return OVL_OK;
     if (row_words < 4 || (row_words & 3) || max_len > 16 * row_words) return fail(OVL_E_ARG, "%s: row_words=%d does not hold max_len=%d", who, row_words, max_len);
-    if (max_len > OVL_MAX_READ_LEN)
-        return fail(OVL_E_UNSUPPORTED, "%s: read length %d exceeds the supported maximum %d", who, max_len, OVL_MAX_READ_LEN);
+    if (max_len > OVL_MAX_LONG_READ_LEN)
+        return fail(OVL_E_UNSUPPORTED, "%s: read length %d exceeds the supported maximum %d", who, max_len, OVL_MAX_LONG_READ_LEN);
+    if (max_len > OVL_MAX_READ_LEN) {
+        // longer than the register wavefront: CTA-per-pair anti-diagonal kernel (int32 cost space)
+        DpParams prm;
+        if (mode == 1 || !dp_params(match, mismatch, indel, max_len, max_len, false, &prm))
+            return fail(OVL_E_UNSUPPORTED, "%s: no kernel for (match=%lld, mismatch=%lld, indel=%lld, len=%d, mode=%d)",
+                        who, (long long)match, (long long)mismatch, (long long)indel, max_len, mode);
+        if (P > 0x7fffffffll) return fail(OVL_E_ARG, "%s: too many pairs for one launch (%lld)", who, (long long)P);
+        size_t smem = (size_t)3 * (max_len + 1) * sizeof(int32_t);
+        if (smem > 48 * 1024)
+            CUDA_TRY(cudaFuncSetAttribute(overlap_dp_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        overlap_dp_long_kernel<<<(unsigned)P, kDpLongThreads, smem, (cudaStream_t)stream>>>(packed, row_words, len, pair_a, pair_b, P,
+                                                                                          prm, score, end, eo);
+        LAUNCH_CHECK("overlap_dp_long_kernel");
+        return OVL_OK;
+    }
     DpPlan plan;
     if (!dp_plan(max_len, match, mismatch, indel, mode, group_lanes, cols_per_lane, &plan))
         return fail(OVL_E_UNSUPPORTED, "%s: no kernel for (match=%lld, mismatch=%lld, indel=%lld, len=%d, mode=%d, lanes=%d, cols=%d)",

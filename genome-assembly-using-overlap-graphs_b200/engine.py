@@ -121,8 +121,8 @@ class OverlapEngine:
         return self.pack_reads(ascii_dev, off_dev, U, max_len)
 
     def pack_reads(self, ascii_dev: torch.Tensor, off_dev: torch.Tensor, U: int, max_len: int) -> ReadSet:
-        if max_len > nat.OVL_MAX_READ_LEN:
-            raise nat.OvlUnsupported(f"read length {max_len} exceeds the supported maximum {nat.OVL_MAX_READ_LEN}")
+        if max_len > nat.OVL_MAX_LONG_READ_LEN:
+            raise nat.OvlUnsupported(f"read length {max_len} exceeds the supported maximum {nat.OVL_MAX_LONG_READ_LEN}")
         row_words = int(nat.lib.ovl_row_words(max_len))
         packed = self._empty(U * row_words * 4 + 16, torch.uint8)
         length = self._empty(U, torch.int32)
@@ -382,7 +382,7 @@ class OverlapEngine:
         out = (ctypes.c_int32 * 3)()
         nat.check(nat.lib.ovl_overlap_dp_plan(max_len, int(match_score), int(mismatch), int(indel), mode,
                                               ctypes.byref(out)))
-        return {"mode": "packed16" if out[0] == 1 else "int32", "lanes": int(out[1]), "cols": int(out[2])}
+        return {"mode": {1: "packed16", 2: "int32", 3: "long-read"}[int(out[0])], "lanes": int(out[1]), "cols": int(out[2])}
 
     # ------------------------------------------------------------------ K7
     def align_pair(self, s_codes: np.ndarray, t_codes: np.ndarray, match_score: int = 10, mismatch: int = -1,

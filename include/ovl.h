@@ -32,7 +32,8 @@ extern "C" {
 #define OVL_E_UNSUPPORTED (-3) /* valid for the reference, outside what the kernels implement */
 
 #define OVL_MAX_K 32          /* k-mer keys are 2k-bit integers in a uint64; larger k: hashed keys + verify */
-#define OVL_MAX_READ_LEN 2432 /* longest read the wavefront DP covers (32 lanes x 76 columns) */
+#define OVL_MAX_READ_LEN 2432 /* longest read the register-wavefront DP covers (32 lanes x 76 columns) */
+#define OVL_MAX_LONG_READ_LEN 16384 /* longest read of the CTA-per-pair anti-diagonal DP (diagonals in shared memory) */
 
 typedef struct ovl_ctx ovl_ctx;
 
@@ -123,7 +124,8 @@ int ovl_all_pairs_fill(ovl_ctx *ctx, int64_t U, int64_t a_begin, int64_t p_begin
 /* K4/K5: the DP call site overlapGraphs.py:53, i.e. aligners.py:27-57 for every pair:
  *   score[p], end[p] = overlap_alignment(read[pair_a[p]], read[pair_b[p]], match, mismatch, indel)[3:5]
  * indel is int64 like the reference's Numba-typed default (-2**31 never wraps).
- * max_len = longest read in the batch (<= OVL_MAX_READ_LEN, <= 16*row_words).
+ * max_len = longest read in the batch (<= OVL_MAX_LONG_READ_LEN, <= 16*row_words); batches whose longest
+ * read exceeds OVL_MAX_READ_LEN run the slower CTA-per-pair anti-diagonal kernel.
  * mode: 0 = choose, 1 = force the packed 16-bit kernel, 2 = force the 32-bit kernel.
  * group_lanes / cols_per_lane: 0 = choose, else force that instantiation (tests). */
 int ovl_overlap_dp(ovl_ctx *ctx, const uint32_t *packed, int32_t row_words, const int32_t *len,
@@ -139,7 +141,7 @@ int ovl_overlap_dp_edges(ovl_ctx *ctx, const uint32_t *packed, int32_t row_words
                          int64_t match, int64_t mismatch, int64_t indel, const int32_t *copies,
                          const int64_t *node_off, const int64_t *edge_off, int32_t *edges,
                          void *stream);
-/* which kernel ovl_overlap_dp would pick: out[0]=mode (1 packed, 2 int32), out[1]=lanes,
+/* which kernel ovl_overlap_dp would pick: out[0]=mode (1 packed, 2 int32, 3 long-read kernel), out[1]=lanes,
  * out[2]=columns per lane.  Returns OVL_E_UNSUPPORTED when nothing fits. */
 int ovl_overlap_dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_t indel,
                         int32_t mode, int32_t out[3]);

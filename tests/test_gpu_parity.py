@@ -274,6 +274,21 @@ def test_batch_dp_every_instantiation(eng, nat):
         assert tried >= 6
 
 
+def test_batch_dp_long_reads_use_the_anti_diagonal_kernel(eng):
+    rng = random.Random(31)
+    reads = overlapping_reads(rng, 30, 9000, 4000, 0.02) + rand_reads(rng, 6, 0, 3000) + ["", "ACGT"]
+    assert eng.dp_plan(4000)["mode"] == "long-read"
+    pa = np.array([rng.randrange(len(reads)) for _ in range(41)], dtype=np.int32)
+    pb = np.array([rng.randrange(len(reads)) for _ in range(41)], dtype=np.int32)
+    for prm in [(10, -1, -2 ** 31), (10, -1, -2), (2, -3, -2)]:
+        s, e, ws, we = run_dp(eng, reads, pa, pb, prm)
+        assert np.array_equal(s, ws) and np.array_equal(e, we), prm
+    g = load_pkg("overlapGraphs")
+    G, rc = g.construct_overlap_graph_nx_k(reads, k=12)
+    nodes, edges, rc2 = orc.construct_overlap_graph(reads, 12)
+    assert list(G.edges(data=True)) == list(orc.to_networkx(nodes, edges).edges(data=True))
+
+
 def test_batch_dp_wide_scores_use_int32_kernel(eng):
     rng = random.Random(5)
     reads = overlapping_reads(rng, 100, 400, 120, 0.05)
@@ -300,7 +315,7 @@ def test_batch_dp_unsupported_is_loud(eng, nat):
     with pytest.raises(nat.OvlUnsupported):
         run_dp(eng, reads, pa, pb, (2 ** 40, -1, -2))            # would overflow int32 storage
     with pytest.raises(nat.OvlUnsupported):
-        upload(eng, ["A" * 2500])                                # longer than the wavefront covers
+        upload(eng, ["A" * 20000])                               # longer than any kernel covers
 
 
 # --------------------------------------------------------------------------- whole builder
