@@ -65,6 +65,13 @@ _SIGS = {
     "ovl_overlap_dp_edges": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _i64, _vp, _vp, _vp,
                                             _vp, _vp]),
     "ovl_overlap_dp_plan": (ctypes.c_int, [_i32, _i64, _i64, _i64, _i32, ctypes.POINTER(_i32 * 3)]),
+    "ovl_pack_bytes": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "ovl_kmer_hashes8": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "ovl_join_count_verify8": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ovl_join_fill_verify8": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i64,
+                                             _vp, _vp, _vp]),
+    "ovl_overlap_dp8": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp,
+                                       _vp, _vp, _vp]),
     "ovl_expand_workspace_bytes": (_sz, [_i64]),
     "ovl_expand_count": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "ovl_expand_fill": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),

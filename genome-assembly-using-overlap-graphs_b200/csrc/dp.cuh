@@ -368,6 +368,14 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : OVL_DP_MINB)) overla
 // diagonals fit shared memory (3 * (n+1) ints).
 constexpr int kDpLongThreads = 256;
 
+// BITS = 2: 2-bit packed rows (row_words words per read); BITS = 8: byte rows (row_words*4 bytes per
+// read, any alphabet -- the route for read sets with more than four distinct symbols)
+template <int BITS>
+__device__ __forceinline__ uint32_t read_symbol(const uint32_t* row, int i) {
+    return BITS == 2 ? base_code(row, i) : (uint32_t)reinterpret_cast<const uint8_t*>(row)[i];
+}
+
+template <int BITS>
 __global__ void __launch_bounds__(kDpLongThreads) overlap_dp_long_kernel(
     const uint32_t* __restrict__ packed, int row_words, const int32_t* __restrict__ len,
     const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b, int64_t P,
@@ -398,7 +406,7 @@ __global__ void __launch_bounds__(kDpLongThreads) overlap_dp_long_kernel(
         int ilo = max(1, d - m), ihi = min(n, d - 1);
         for (int i = ilo + (int)threadIdx.x; i <= ihi; i += blockDim.x) {
             int j = d - i;
-            int dc = base_code(srow, i - 1) == base_code(trow, j - 1) ? prm.eqc : prm.nec;
+            int dc = read_symbol<BITS>(srow, i - 1) == read_symbol<BITS>(trow, j - 1) ? prm.eqc : prm.nec;
             int v = min(min(p2[i - 1] + dc, p1[i - 1] + prm.gu), p1[i] + prm.gl);
             cur[i] = v;
             if (i == n && v < bestv) { bestv = v; bestj = j; }   // one thread owns row n: j ascending

@@ -205,6 +205,88 @@ __global__ void __launch_bounds__(256) join_verify_kernel(const uint32_t* __rest
     if (!FILL) cnt_out[i] = cnt;
 }
 
+// ------------------------------------------------------------------ byte-coded reads (any alphabet)
+// Read sets with more than four distinct symbols cannot be 2-bit packed.  They are kept as padded
+// byte rows (row_bytes per read, 16-byte aligned) and take the general route: hashed k-mer keys with
+// byte-wise verification in the join, and the CTA-per-pair anti-diagonal DP (dp.cuh) comparing bytes.
+__global__ void __launch_bounds__(256) pack_bytes_kernel(const uint8_t* __restrict__ ascii, const int64_t* __restrict__ offsets,
+                                                         int64_t U, int row_bytes, uint8_t* __restrict__ rows,
+                                                         int32_t* __restrict__ len_out) {
+    int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one thread per 4 output bytes
+    int quads = row_bytes >> 2;
+    if (slot >= U * quads) return;
+    int64_t u = slot / quads;
+    int q = (int)(slot - u * quads);
+    int64_t o0 = offsets[u];
+    int len = (int)(offsets[u + 1] - o0);
+    if (q == 0) len_out[u] = len;
+    uint32_t w = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        int i = 4 * q + b;
+        if (i < len) w |= (uint32_t)ascii[o0 + i] << (8 * b);
+    }
+    reinterpret_cast<uint32_t*>(rows)[slot] = w;
+}
+
+__device__ __forceinline__ uint64_t bytes_hash(const uint8_t* __restrict__ p, int k) {
+    uint64_t h = 0x243f6a8885a308d3ull ^ (uint64_t)k;
+    for (int i = 0; i < k; ++i) { h ^= p[i]; h *= 0x100000001b3ull; h ^= h >> 29; }
+    return h * 0x9e3779b97f4a7c15ull;
+}
+
+__global__ void __launch_bounds__(256) kmer_hash8_kernel(const uint8_t* __restrict__ rows, int row_bytes,
+                                                         const int32_t* __restrict__ len, int64_t U, int k,
+                                                         uint64_t* __restrict__ prefix_key, uint64_t* __restrict__ suffix_key) {
+    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= U) return;
+    int n = len[u];
+    uint64_t pk = 0, sk = 0;
+    if (n >= k) {
+        const uint8_t* row = rows + u * row_bytes;
+        pk = bytes_hash(row, k);
+        sk = bytes_hash(row + (n - k), k);
+    }
+    prefix_key[u] = pk;
+    suffix_key[u] = sk;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) join_verify8_kernel(const uint8_t* __restrict__ rows, int row_bytes,
+                                                           const int32_t* __restrict__ len, int k,
+                                                           const uint64_t* __restrict__ suffix_key, int64_t nA, int64_t a_begin,
+                                                           const uint64_t* __restrict__ sorted_key, const uint32_t* __restrict__ sorted_uid,
+                                                           const int64_t* __restrict__ n_indexed, int64_t* __restrict__ cnt_out,
+                                                           const int64_t* __restrict__ pair_off, int64_t p_begin, int64_t p_count,
+                                                           int32_t* __restrict__ pair_a, int32_t* __restrict__ pair_b) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nA) return;
+    int64_t a = a_begin + i;
+    int64_t cnt = 0;
+    int na = len[a];
+    if (na >= k) {
+        uint64_t key = suffix_key[a];
+        int64_t n = *n_indexed;
+        int64_t lo = lower_bound<uint64_t>(sorted_key, 0, n, key);
+        const uint8_t* sa = rows + a * row_bytes + (na - k);
+        int64_t out = FILL ? pair_off[i] : 0;
+        for (int64_t j = lo; j < n && sorted_key[j] == key; ++j) {
+            int64_t b = sorted_uid[j];
+            if (b == a) continue;
+            const uint8_t* pb = rows + b * row_bytes;
+            bool same = true;
+            for (int x = 0; x < k; ++x) if (sa[x] != pb[x]) { same = false; break; }
+            if (!same) continue;
+            if (FILL) {
+                int64_t q = out + cnt - p_begin;
+                if (q >= 0 && q < p_count) { pair_a[q] = (int32_t)a; pair_b[q] = (int32_t)b; }
+            }
+            ++cnt;
+        }
+    }
+    if (!FILL) cnt_out[i] = cnt;
+}
+
 // ------------------------------------------------------------------ K2 radix sort (stable, LSD, 8-bit digits)
 // Each warp owns kSortChunk consecutive elements; a pass is: per-warp digit histogram ->
 // exclusive scan over (digit-major, warp-minor) -> per-warp stable scatter.  Stability keeps

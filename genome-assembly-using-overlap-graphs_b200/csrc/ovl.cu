@@ -436,24 +436,32 @@ int ovl_overlap_dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_
 static int dp_dispatch(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, const int32_t* pair_a,
                        const int32_t* pair_b, int64_t P, int32_t max_len, int64_t match, int64_t mismatch, int64_t indel,
                        int32_t* score, int32_t* end, const DpEdgeOut& eo, int32_t mode, int32_t group_lanes,
-                       int32_t cols_per_lane, void* stream, const char* who) {
+                       int32_t cols_per_lane, void* stream, const char* who, int code_bits = 2) {
     if (!ctx || !packed || !len || !pair_a || !pair_b) return fail(OVL_E_ARG, "%s: null argument", who);
     if (P <= 0) return OVL_OK;
-    if (row_words < 4 || (row_words & 3) || max_len > 16 * row_words) return fail(OVL_E_ARG, "%s: row_words=%d does not hold max_len=%d", who, row_words, max_len);
+    if (row_words < 4 || (row_words & 3) || max_len > (code_bits == 2 ? 16 : 4) * row_words)
+        return fail(OVL_E_ARG, "%s: row_words=%d does not hold max_len=%d", who, row_words, max_len);
     if (max_len > OVL_MAX_LONG_READ_LEN)
         return fail(OVL_E_UNSUPPORTED, "%s: read length %d exceeds the supported maximum %d", who, max_len, OVL_MAX_LONG_READ_LEN);
-    if (max_len > OVL_MAX_READ_LEN) {
-        // longer than the register wavefront: CTA-per-pair anti-diagonal kernel (int32 cost space)
+    if (max_len > OVL_MAX_READ_LEN || code_bits == 8) {
+        // longer than the register wavefront, or byte-coded reads: CTA-per-pair anti-diagonal kernel (int32 cost space)
         DpParams prm;
         if (mode == 1 || !dp_params(match, mismatch, indel, max_len, max_len, false, &prm))
             return fail(OVL_E_UNSUPPORTED, "%s: no kernel for (match=%lld, mismatch=%lld, indel=%lld, len=%d, mode=%d)",
                         who, (long long)match, (long long)mismatch, (long long)indel, max_len, mode);
         if (P > 0x7fffffffll) return fail(OVL_E_ARG, "%s: too many pairs for one launch (%lld)", who, (long long)P);
         size_t smem = (size_t)3 * (max_len + 1) * sizeof(int32_t);
-        if (smem > 48 * 1024)
-            CUDA_TRY(cudaFuncSetAttribute(overlap_dp_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        overlap_dp_long_kernel<<<(unsigned)P, kDpLongThreads, smem, (cudaStream_t)stream>>>(packed, row_words, len, pair_a, pair_b, P,
-                                                                                          prm, score, end, eo);
+        if (code_bits == 8) {
+            if (smem > 48 * 1024)
+                CUDA_TRY(cudaFuncSetAttribute(overlap_dp_long_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            overlap_dp_long_kernel<8><<<(unsigned)P, kDpLongThreads, smem, (cudaStream_t)stream>>>(packed, row_words, len, pair_a, pair_b, P,
+                                                                                                 prm, score, end, eo);
+        } else {
+            if (smem > 48 * 1024)
+                CUDA_TRY(cudaFuncSetAttribute(overlap_dp_long_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            overlap_dp_long_kernel<2><<<(unsigned)P, kDpLongThreads, smem, (cudaStream_t)stream>>>(packed, row_words, len, pair_a, pair_b, P,
+                                                                                                 prm, score, end, eo);
+        }
         LAUNCH_CHECK("overlap_dp_long_kernel");
         return OVL_OK;
     }
@@ -482,6 +490,18 @@ int ovl_overlap_dp(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, cons
                        mode, group_lanes, cols_per_lane, stream, "ovl_overlap_dp");
 }
 
+int ovl_overlap_dp8(ovl_ctx* ctx, const uint8_t* rows, int32_t row_words, const int32_t* len, const int32_t* pair_a,
+                    const int32_t* pair_b, int64_t P, int32_t max_len, int64_t match, int64_t mismatch, int64_t indel,
+                    int32_t* score, int32_t* end, const int32_t* copies, const int64_t* node_off, const int64_t* edge_off,
+                    int32_t* edges, void* stream) {
+    if (P > 0 && !edges && (!score || !end)) return fail(OVL_E_ARG, "ovl_overlap_dp8: null output");
+    if ((uintptr_t)edges & 15) return fail(OVL_E_ARG, "ovl_overlap_dp8: edges must be 16-byte aligned");
+    if (copies && (!node_off || !edge_off)) return fail(OVL_E_ARG, "ovl_overlap_dp8: copies given without node_off / edge_off");
+    DpEdgeOut eo{(int4*)edges, copies, node_off, edge_off};
+    return dp_dispatch(ctx, (const uint32_t*)rows, row_words, len, pair_a, pair_b, P, max_len, match, mismatch, indel, score, end, eo,
+                       0, 0, 0, stream, "ovl_overlap_dp8", 8);
+}
+
 int ovl_overlap_dp_edges(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, const int32_t* pair_a,
                          const int32_t* pair_b, int64_t P, int32_t max_len, int64_t match, int64_t mismatch, int64_t indel,
                          const int32_t* copies, const int64_t* node_off, const int64_t* edge_off, int32_t* edges,
@@ -492,6 +512,66 @@ int ovl_overlap_dp_edges(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words
     DpEdgeOut eo{(int4*)edges, copies, node_off, edge_off};
     return dp_dispatch(ctx, packed, row_words, len, pair_a, pair_b, P, max_len, match, mismatch, indel, nullptr, nullptr, eo,
                        0, 0, 0, stream, "ovl_overlap_dp_edges");
+}
+
+// ---------------------------------------------------------------- byte-coded reads (any alphabet)
+int ovl_pack_bytes(ovl_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int64_t U, int32_t row_words, uint8_t* rows,
+                   int32_t* len, void* stream) {
+    if (!ctx || !ascii || !offsets || !rows || !len) return fail(OVL_E_ARG, "ovl_pack_bytes: null argument");
+    if (U <= 0) return OVL_OK;
+    if (row_words < 4 || (row_words & 3)) return fail(OVL_E_ARG, "ovl_pack_bytes: row_words must be a positive multiple of 4");
+    pack_bytes_kernel<<<grid_for(U * row_words, 256), 256, 0, (cudaStream_t)stream>>>(ascii, offsets, U, row_words * 4, rows, len);
+    LAUNCH_CHECK("pack_bytes_kernel");
+    return OVL_OK;
+}
+
+int ovl_kmer_hashes8(ovl_ctx* ctx, const uint8_t* rows, int32_t row_words, const int32_t* len, int64_t U, int32_t k,
+                     uint64_t* prefix_hash, uint64_t* suffix_hash, void* stream) {
+    if (!ctx || !rows || !len || !prefix_hash || !suffix_hash) return fail(OVL_E_ARG, "ovl_kmer_hashes8: null argument");
+    if (k < 1) return fail(OVL_E_ARG, "ovl_kmer_hashes8: k must be positive");
+    if (U <= 0) return OVL_OK;
+    kmer_hash8_kernel<<<grid_for(U, 256), 256, 0, (cudaStream_t)stream>>>(rows, row_words * 4, len, U, k, prefix_hash, suffix_hash);
+    LAUNCH_CHECK("kmer_hash8_kernel");
+    return OVL_OK;
+}
+
+int ovl_join_count_verify8(ovl_ctx* ctx, const uint8_t* rows, int32_t row_words, const int32_t* len, int32_t k,
+                           const uint64_t* suffix_hash, int64_t a_begin, int64_t a_end, const uint64_t* sorted_hash,
+                           const uint32_t* sorted_uid, const int64_t* n_indexed, int64_t* pair_off, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+    if (!ctx || !rows || !len || !suffix_hash || !sorted_hash || !sorted_uid || !n_indexed || !pair_off || !workspace)
+        return fail(OVL_E_ARG, "ovl_join_count_verify8: null argument");
+    int64_t nA = a_end - a_begin;
+    if (nA < 0) return fail(OVL_E_ARG, "ovl_join_count_verify8: a_end < a_begin");
+    if (workspace_bytes < ovl_join_workspace_bytes(nA)) return fail(OVL_E_ARG, "ovl_join_count_verify8: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    int64_t* cnt = (int64_t*)ws;
+    void* sums = ws + align256((size_t)std::max<int64_t>(nA, 1) * sizeof(int64_t));
+    if (nA > 0) {
+        join_verify8_kernel<false><<<grid_for(nA, 256), 256, 0, st>>>(rows, row_words * 4, len, k, suffix_hash, nA, a_begin, sorted_hash,
+                                                                      sorted_uid, n_indexed, cnt, nullptr, 0, 0, nullptr, nullptr);
+        LAUNCH_CHECK("join_verify8_kernel<count>");
+    }
+    int nl = 0;
+    CUDA_TRY((exclusive_scan<LoadArray<int64_t>, int64_t>(LoadArray<int64_t>{cnt}, pair_off, nA, sums, st, &nl)));
+    ctx->launches += nl;
+    return OVL_OK;
+}
+
+int ovl_join_fill_verify8(ovl_ctx* ctx, const uint8_t* rows, int32_t row_words, const int32_t* len, int32_t k,
+                          const uint64_t* suffix_hash, int64_t a_begin, int64_t a_end, const uint64_t* sorted_hash,
+                          const uint32_t* sorted_uid, const int64_t* n_indexed, const int64_t* pair_off, int64_t p_begin,
+                          int64_t p_count, int32_t* pair_a, int32_t* pair_b, void* stream) {
+    if (!ctx || !rows || !len || !suffix_hash || !sorted_hash || !sorted_uid || !n_indexed || !pair_off || !pair_a || !pair_b)
+        return fail(OVL_E_ARG, "ovl_join_fill_verify8: null argument");
+    int64_t nA = a_end - a_begin;
+    if (nA <= 0 || p_count <= 0) return OVL_OK;
+    join_verify8_kernel<true><<<grid_for(nA, 256), 256, 0, (cudaStream_t)stream>>>(rows, row_words * 4, len, k, suffix_hash, nA, a_begin,
+                                                                                    sorted_hash, sorted_uid, n_indexed, nullptr,
+                                                                                    pair_off, p_begin, p_count, pair_a, pair_b);
+    LAUNCH_CHECK("join_verify8_kernel<fill>");
+    return OVL_OK;
 }
 
 // ---------------------------------------------------------------- K6

@@ -29,6 +29,7 @@ class ReadSet:
     row_words: int
     n_reads: int
     max_len: int
+    code_bits: int = 2            # 2: 2-bit packed A/C/G/T rows; 8: byte rows (any alphabet, general kernels)
 
 
 @dataclass
@@ -98,7 +99,7 @@ class OverlapEngine:
         return x.to(self.device, non_blocking=True)
 
     # ------------------------------------------------------------------ K0
-    def upload_reads(self, bases, offsets, max_len: Optional[int] = None) -> ReadSet:
+    def upload_reads(self, bases, offsets, max_len: Optional[int] = None, code_bits: int = 2) -> ReadSet:
         """bases: uint8[sum len] ASCII, offsets: int64[U+1] (NumPy or CPU/GPU torch tensors)."""
         off_host = None
         if isinstance(offsets, np.ndarray):
@@ -118,11 +119,21 @@ class OverlapEngine:
             src = self._from_numpy(bases) if isinstance(bases, np.ndarray) else bases
             ascii_dev[:total].copy_(src[:total], non_blocking=True)
         off_dev = self._to_device(offsets, torch.int64)
-        return self.pack_reads(ascii_dev, off_dev, U, max_len)
+        return self.pack_reads(ascii_dev, off_dev, U, max_len, code_bits)
 
-    def pack_reads(self, ascii_dev: torch.Tensor, off_dev: torch.Tensor, U: int, max_len: int) -> ReadSet:
+    def pack_reads(self, ascii_dev: torch.Tensor, off_dev: torch.Tensor, U: int, max_len: int,
+                   code_bits: int = 2) -> ReadSet:
         if max_len > nat.OVL_MAX_LONG_READ_LEN:
             raise nat.OvlUnsupported(f"read length {max_len} exceeds the supported maximum {nat.OVL_MAX_LONG_READ_LEN}")
+        if code_bits == 8:
+            # any alphabet: padded byte rows, general (slower) kernels downstream
+            row_words = max(4, ((max_len + 3) // 4 + 3) // 4 * 4)
+            rows = self._empty(U * row_words * 4 + 16, torch.uint8)
+            length = self._empty(U, torch.int32)
+            bad = torch.zeros(1, dtype=torch.int32, device=self.device)
+            nat.check(nat.lib.ovl_pack_bytes(self._ctx, _ptr(ascii_dev), _ptr(off_dev), U, row_words, _ptr(rows),
+                                             _ptr(length), self._stream()))
+            return ReadSet(rows, length, bad, row_words, U, max_len, 8)
         row_words = int(nat.lib.ovl_row_words(max_len))
         packed = self._empty(U * row_words * 4 + 16, torch.uint8)
         length = self._empty(U, torch.int32)
@@ -145,7 +156,7 @@ class OverlapEngine:
         with its read set; reads of different sets then never share a key."""
         if k < 1:
             raise ValueError("k must be positive for the k-mer index")
-        hashed = k > nat.OVL_MAX_K          # the k-mer does not fit a u64: index 64-bit hashes, verify in the join
+        hashed = k > nat.OVL_MAX_K or rs.code_bits == 8   # no u64 k-mer: index 64-bit hashes, verify in the join
         key_bits = 64 if hashed else 0
         if segments is not None and hashed:
             raise nat.OvlUnsupported(f"batched read sets with k={k} > {nat.OVL_MAX_K} are not supported")
@@ -157,7 +168,10 @@ class OverlapEngine:
         U = rs.n_reads
         pk = self._empty(U, torch.int64)
         sk = self._empty(U, torch.int64)
-        if hashed:
+        if rs.code_bits == 8:
+            nat.check(nat.lib.ovl_kmer_hashes8(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length), U, k,
+                                               _ptr(pk), _ptr(sk), self._stream()))
+        elif hashed:
             nat.check(nat.lib.ovl_kmer_hashes(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length), U, k,
                                               _ptr(pk), _ptr(sk), self._stream()))
         else:
@@ -204,7 +218,7 @@ class OverlapEngine:
                 nat.check(nat.lib.ovl_all_pairs_fill(self._ctx, U, 0, p_begin, P, _ptr(pair_a), _ptr(pair_b), st))
             return pair_a[:P], pair_b[:P], p_begin
         assert index is not None and index.k == k
-        if k > nat.OVL_MAX_K:
+        if k > nat.OVL_MAX_K or rs.code_bits == 8:
             return self._candidate_pairs_hashed(rs, index, k, shard)
         lo = self._empty(U, torch.int32)
         self_rank = self._empty(U, torch.int32)
@@ -234,7 +248,9 @@ class OverlapEngine:
         pair_off = self._empty(U + 1, torch.int64)
         ws_bytes = int(nat.lib.ovl_join_workspace_bytes(U))
         ws = self._empty(ws_bytes, torch.uint8)
-        nat.check(nat.lib.ovl_join_count_verify(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length), k,
+        count_fn = nat.lib.ovl_join_count_verify8 if rs.code_bits == 8 else nat.lib.ovl_join_count_verify
+        fill_fn = nat.lib.ovl_join_fill_verify8 if rs.code_bits == 8 else nat.lib.ovl_join_fill_verify
+        nat.check(count_fn(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length), k,
                                                 _ptr(index.suffix_key), 0, U, _ptr(index.sorted_key),
                                                 _ptr(index.sorted_uid), _ptr(index.n_indexed), _ptr(pair_off),
                                                 _ptr(ws), ws_bytes, st))
@@ -245,7 +261,7 @@ class OverlapEngine:
         pair_a = self._empty(P, torch.int32)
         pair_b = self._empty(P, torch.int32)
         if P:
-            nat.check(nat.lib.ovl_join_fill_verify(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length), k,
+            nat.check(fill_fn(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length), k,
                                                    _ptr(index.suffix_key), 0, U, _ptr(index.sorted_key),
                                                    _ptr(index.sorted_uid), _ptr(index.n_indexed), _ptr(pair_off),
                                                    p_begin, P, _ptr(pair_a), _ptr(pair_b), st))
@@ -264,12 +280,29 @@ class OverlapEngine:
             end = self._empty(P, torch.int32)
         else:
             score, end = out
-        if P:
+        if P and rs.code_bits == 8:
+            nat.check(nat.lib.ovl_overlap_dp8(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length),
+                                              _ptr(pair_a), _ptr(pair_b), P, rs.max_len,
+                                              int(match_score), int(mismatch), int(indel), _ptr(score), _ptr(end),
+                                              None, None, None, None, self._stream()))
+        elif P:
             nat.check(nat.lib.ovl_overlap_dp(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length),
                                              _ptr(pair_a), _ptr(pair_b), P, rs.max_len,
                                              int(match_score), int(mismatch), int(indel),
                                              _ptr(score), _ptr(end), mode, lanes, cols, self._stream()))
         return score[:P], end[:P]
+
+    def _dp_edges_call(self, rs: ReadSet, a_ptr, b_ptr, P: int, scoring, copies, node_off, off_ptr, out_ptr, st) -> None:
+        """One launch of the DP with the fused edge epilogue (2-bit packed or byte-coded reads)."""
+        match_score, mismatch, indel = scoring
+        if rs.code_bits == 8:
+            nat.check(nat.lib.ovl_overlap_dp8(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length), a_ptr, b_ptr, P,
+                                              rs.max_len, int(match_score), int(mismatch), int(indel), None, None,
+                                              _ptr(copies), _ptr(node_off), off_ptr, out_ptr, st))
+        else:
+            nat.check(nat.lib.ovl_overlap_dp_edges(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length), a_ptr, b_ptr,
+                                                   P, rs.max_len, int(match_score), int(mismatch), int(indel),
+                                                   _ptr(copies), _ptr(node_off), off_ptr, out_ptr, st))
 
     def overlap_edges_fused(self, rs: ReadSet, pair_a: torch.Tensor, pair_b: torch.Tensor,
                             copies: Optional[torch.Tensor] = None, node_off: Optional[torch.Tensor] = None,
@@ -302,10 +335,8 @@ class OverlapEngine:
             out_ptr = _ptr(edges)
         if events is not None:
             events[0].record()
-        nat.check(nat.lib.ovl_overlap_dp_edges(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length),
-                                               _ptr(pair_a), _ptr(pair_b), P, rs.max_len,
-                                               int(match_score), int(mismatch), int(indel),
-                                               _ptr(copies), _ptr(node_off), _ptr(edge_off), out_ptr, st))
+        self._dp_edges_call(rs, _ptr(pair_a), _ptr(pair_b), P, (match_score, mismatch, indel), copies, node_off,
+                            _ptr(edge_off), out_ptr, st)
         if events is not None:
             events[1].record()
         return None if edges is None else edges[:E * 4].view(E, 4)
@@ -361,10 +392,8 @@ class OverlapEngine:
             else:
                 off_ptr = ctypes.c_void_p(0)
                 out_ptr = ctypes.c_void_p(edges.data_ptr() + 16 * p0)
-            nat.check(nat.lib.ovl_overlap_dp_edges(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length),
-                                                   a_ptr, b_ptr, p1 - p0, rs.max_len,
-                                                   int(match_score), int(mismatch), int(indel),
-                                                   _ptr(copies), _ptr(node_off), off_ptr, out_ptr, st))
+            self._dp_edges_call(rs, a_ptr, b_ptr, p1 - p0, (match_score, mismatch, indel), copies, node_off,
+                                off_ptr, out_ptr, st)
             done = torch.cuda.Event()
             done.record(main)
             e0, e1 = int(e_bounds[c]), int(e_bounds[c + 1])
@@ -500,13 +529,13 @@ class OverlapEngine:
                       match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT,
                       stats: Optional[dict] = None, to_host: bool = True, reuse_host_buffer: bool = False,
                       min_weight: Optional[int] = None, pairs=None, segments=None, n_segments: int = 1,
-                      host_sink=None):
+                      host_sink=None, code_bits: int = 2):
         """HOST buffers in, HOST edge rows out: unique reads (ASCII bytes + offsets) and their
         multiplicities -> int32[E, 4] (node_a, node_b, weight, end_position) in the reference's
         insertion order.  This is the call the drop-in graph builder makes."""
         if k < 0:
             raise AssertionError("k-mer length must be non-negative")      # overlapGraphs.py:17
-        rs = self.upload_reads(bases, offsets)
+        rs = self.upload_reads(bases, offsets, code_bits=code_bits)
         copies = node_off = None
         if counts is not None:
             counts_np = counts if isinstance(counts, np.ndarray) else counts.numpy()

@@ -33,22 +33,21 @@ def _flatten(uniq):
     np.cumsum(lens, out=offsets[1:])
     joined = "".join(uniq)
     try:
-        raw = joined.encode("ascii")
+        raw = joined.encode("latin-1")            # one byte per character, so that offsets are character offsets
     except UnicodeEncodeError as exc:
-        raise _engine.nat.OvlUnsupported("reads contain non-ASCII characters; the 2-bit CUDA path "
-                                         "supports A, C, G, T only") from exc
+        raise _engine.nat.OvlUnsupported("reads contain characters above U+00FF; the CUDA builder works on "
+                                         "single-byte symbols") from exc
     bases = np.frombuffer(raw, dtype=np.uint8) if raw else np.zeros(0, np.uint8)
     return bases, offsets
 
 
 def _to_acgt(bases):
     """Re-letter a read set that uses at most four distinct symbols (lower case, RNA, ...) as A/C/G/T.
-    Keys and the DP only test symbols for equality, so any bijection leaves every result unchanged."""
+    Keys and the DP only test symbols for equality, so any bijection leaves every result unchanged.
+    Returns None when there are more than four symbols (byte-coded general kernels take over)."""
     symbols = np.unique(bases)
     if symbols.size > 4:
-        raise _engine.nat.OvlUnsupported(
-            f"reads use {symbols.size} distinct symbols ({bytes(symbols[:8]).decode('latin-1')!r}...); the 2-bit CUDA "
-            "path covers alphabets of at most four symbols")
+        return None
     lut = np.zeros(256, dtype=np.uint8)
     lut[symbols] = np.frombuffer(b"ACGT", dtype=np.uint8)[:symbols.size]
     return lut[bases]
@@ -76,8 +75,15 @@ def overlap_edge_rows(reads, k=5, _reuse_host_buffer=False, min_weight=None):
     except _engine.nat.OvlUnsupported as exc:
         if "other than A, C, G, T" not in str(exc):
             raise
-        edges = eng.overlap_edges(_to_acgt(bases), offsets, counts, k, reuse_host_buffer=_reuse_host_buffer,
-                                  min_weight=min_weight)
+        relettered = _to_acgt(bases)
+        if relettered is not None:
+            edges = eng.overlap_edges(relettered, offsets, counts, k, reuse_host_buffer=_reuse_host_buffer,
+                                      min_weight=min_weight)
+        else:
+            # more than four symbols (e.g. reads with N): byte-coded rows and the general kernels -- the
+            # reference compares arbitrary characters (aligners.py:35), so does this path
+            edges = eng.overlap_edges(bases, offsets, counts, k, reuse_host_buffer=_reuse_host_buffer,
+                                      min_weight=min_weight, code_bits=8)
     return read_copies, uniq, counts, edges
 
 

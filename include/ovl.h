@@ -146,6 +146,31 @@ int ovl_overlap_dp_edges(ovl_ctx *ctx, const uint32_t *packed, int32_t row_words
 int ovl_overlap_dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_t indel,
                         int32_t mode, int32_t out[3]);
 
+/* Byte-coded reads: read sets with more than four distinct symbols cannot be 2-bit packed (the
+ * reference compares arbitrary characters, aligners.py:35).  They are kept as padded byte rows
+ * (row_words*4 bytes per read) and take the general route: hashed keys + byte-wise verified join and
+ * the CTA-per-pair anti-diagonal DP.  Same results, lower throughput.  ovl_overlap_dp8 writes
+ * score/end when edges == NULL, else the fused edge rows (as ovl_overlap_dp_edges). */
+int ovl_pack_bytes(ovl_ctx *ctx, const uint8_t *ascii, const int64_t *offsets, int64_t U,
+                   int32_t row_words, uint8_t *rows, int32_t *len, void *stream);
+int ovl_kmer_hashes8(ovl_ctx *ctx, const uint8_t *rows, int32_t row_words, const int32_t *len,
+                     int64_t U, int32_t k, uint64_t *prefix_hash, uint64_t *suffix_hash, void *stream);
+int ovl_join_count_verify8(ovl_ctx *ctx, const uint8_t *rows, int32_t row_words, const int32_t *len,
+                           int32_t k, const uint64_t *suffix_hash, int64_t a_begin, int64_t a_end,
+                           const uint64_t *sorted_hash, const uint32_t *sorted_uid,
+                           const int64_t *n_indexed, int64_t *pair_off, void *workspace,
+                           size_t workspace_bytes, void *stream);
+int ovl_join_fill_verify8(ovl_ctx *ctx, const uint8_t *rows, int32_t row_words, const int32_t *len,
+                          int32_t k, const uint64_t *suffix_hash, int64_t a_begin, int64_t a_end,
+                          const uint64_t *sorted_hash, const uint32_t *sorted_uid,
+                          const int64_t *n_indexed, const int64_t *pair_off, int64_t p_begin,
+                          int64_t p_count, int32_t *pair_a, int32_t *pair_b, void *stream);
+int ovl_overlap_dp8(ovl_ctx *ctx, const uint8_t *rows, int32_t row_words, const int32_t *len,
+                    const int32_t *pair_a, const int32_t *pair_b, int64_t P, int32_t max_len,
+                    int64_t match, int64_t mismatch, int64_t indel, int32_t *score, int32_t *end,
+                    const int32_t *copies, const int64_t *node_off, const int64_t *edge_off,
+                    int32_t *edges, void *stream);
+
 /* K6: edge expansion, overlapGraphs.py:55-60.  Edge row = int32[4] (node_a, node_b, weight,
  * end_position); node id = node_off[uid] + copy; order = pair order, copy_a, copy_b.
  * ovl_expand_count writes the exclusive scan edge_off[P+1] of copies[a]*copies[b]. */

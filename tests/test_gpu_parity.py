@@ -158,13 +158,18 @@ def test_pack_rejects_non_acgt(eng, nat):
             eng.check_alphabet(rs)
     g = load_pkg("overlapGraphs")
     with pytest.raises(nat.OvlUnsupported):
-        g.construct_overlap_graph_nx_k(["ACGTN", "GTNAC"], k=2)          # five symbols
-    # at most four distinct symbols of any kind are re-lettered on the host and give the exact graph
-    for reads in (["acgtac", "gtacgg", "acggta"], ["ACGUAC", "GUACGG", "ACGGUA"], ["xyxxy", "xxyxy", "yxyxx", "xyxxy"]):
-        G, rc = g.construct_overlap_graph_nx_k(reads, k=2)
-        nodes, edges, rc2 = orc.construct_overlap_graph(reads, 2)
-        assert list(rc.items()) == list(rc2.items()) and list(G.nodes) == nodes
-        assert list(G.edges(data=True)) == list(orc.to_networkx(nodes, edges).edges(data=True))
+        g.construct_overlap_graph_nx_k(["ACGT\u0394", "GT\u0394AC"], k=2)    # beyond one byte per symbol
+    # up to four distinct symbols of any kind are re-lettered on the host; more (reads with N, IUPAC codes,
+    # mixed case) go through the byte-coded general kernels -- both give the exact graph
+    rng = random.Random(12)
+    with_n = ["".join(ch if rng.random() > 0.03 else "N" for ch in r) for r in overlapping_reads(rng, 400, 300, 40, 0.01)]
+    for reads in (["acgtac", "gtacgg", "acggta"], ["ACGUAC", "GUACGG", "ACGGUA"], ["xyxxy", "xxyxy", "yxyxx", "xyxxy"],
+                  ["ACGTN", "GTNAC", "TNACG"], with_n, with_n + ["acgtRYKM", "KMacgtRY"]):
+        for k in (2, 5, 0) if len(reads) < 50 else (4, 9):
+            G, rc = g.construct_overlap_graph_nx_k(reads, k=k)
+            nodes, edges, rc2 = orc.construct_overlap_graph(reads, k)
+            assert list(rc.items()) == list(rc2.items()) and list(G.nodes) == nodes
+            assert list(G.edges(data=True)) == list(orc.to_networkx(nodes, edges).edges(data=True))
 
 
 @pytest.mark.parametrize("k", [1, 3, 5, 8, 15, 16, 17, 31, 32])
