@@ -135,9 +135,13 @@ def construct_overlap_graphs_batch(read_lists, k=5):
     counts_all = np.concatenate(all_counts)
     bases, offsets = _flatten(all_uniq)
     eng = _engine.get_engine()
-    # counts are always passed so that node ids are offsets into the concatenated copy list
-    edges = eng.overlap_edges(bases, offsets, np.maximum(counts_all, 1) if counts_all.max() > 1 else None, k,
-                              reuse_host_buffer=True, segments=np.concatenate(seg), n_segments=len(read_lists))
+    try:
+        # counts are always passed so that node ids are offsets into the concatenated copy list
+        edges = eng.overlap_edges(bases, offsets, np.maximum(counts_all, 1) if counts_all.max() > 1 else None, k,
+                                  reuse_host_buffer=True, segments=np.concatenate(seg), n_segments=len(read_lists))
+    except _engine.nat.OvlUnsupported:
+        # what the one-job path does not cover (k > 31, symbols other than A/C/G/T): one build per read set
+        return [construct_overlap_graph_nx_k(reads, k) for reads in read_lists]
     node_base = np.zeros(len(per_set) + 1, dtype=np.int64)
     if counts_all.max() > 1:
         np.cumsum([int(c.sum()) for _, _, c in per_set], out=node_base[1:])
