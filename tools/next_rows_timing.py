@@ -43,3 +43,25 @@ for k in (5, 10, 15):
     torch.cuda.synchronize(); t_bat = time.perf_counter() - t0
     assert all(list(a[0].edges(data=True)) == list(b[0].edges(data=True)) for a, b in zip(one, bat))
     print(f"k={k}: {len(sets)} graph builds one by one {t_one:.2f} s, as one batch {t_bat:.2f} s, edges {sum(x[0].number_of_edges() for x in bat)}")
+
+# general kernels: long reads (> 2,432 bases) and byte-coded alphabets
+engine = importlib.import_module(PKG + ".engine")
+eng = engine.get_engine()
+def rate(bases, offsets, k, code_bits, label):
+    ub, uo, counts, _ = synth.dedup(bases, offsets)
+    rs = eng.upload_reads(ub, uo, code_bits=code_bits)
+    idx = eng.kmer_index(rs, k)
+    pa, pb, _ = eng.candidate_pairs(rs, idx, k)
+    lens = rs.length[:rs.n_reads].to(torch.int64)
+    cells = int((lens[pa.long()] * lens[pb.long()]).sum().item())
+    eng.overlap_scores(rs, pa, pb); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); eng.overlap_scores(rs, pa, pb); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"{label}: {pa.shape[0]} pairs, {cells:.3e} cells, DP {ms:.2f} ms = {cells/ms/1e6:.0f} GCUPS ({eng.dp_plan(rs.max_len)['mode'] if code_bits == 2 else 'byte-coded long-read kernel'})")
+g = synth.random_genome(400_000, 3)
+b, o = synth.simulate_reads(g, 4000, 4000, 0.02, seed=5)
+rate(b, o, 12, 2, "l=4000 (anti-diagonal CTA-per-pair kernel)")
+b, o = synth.simulate_reads(synth.phix_like_genome(), 20000, 150, 0.01, seed=6)
+rate(b, o, 5, 2, "PhiX-like N=20000 l=150, 2-bit packed")
+rate(b, o, 5, 8, "same reads, byte-coded general kernels")
