@@ -110,6 +110,11 @@ __device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t one, uint32_t c
 __device__ __forceinline__ uint32_t base_code(const uint32_t* row, int i) {
     return (row[i >> 4] >> ((i & 15) * 2)) & 3u;
 }
+// BITS = 2: 2-bit packed rows (16 bases per word); BITS = 8: byte rows (any alphabet)
+template <int BITS>
+__device__ __forceinline__ uint32_t read_symbol(const uint32_t* row, int i) {
+    return BITS == 2 ? base_code(row, i) : (uint32_t)reinterpret_cast<const uint8_t*>(row)[i];
+}
 __device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; }
 __device__ __forceinline__ constexpr bool dp_form2(int c) {
     return OVL_DP_F2_NUM > 0 && (c * OVL_DP_F2_NUM) % OVL_DP_F2_DEN < OVL_DP_F2_NUM;
@@ -142,7 +147,10 @@ __host__ __device__ inline int dp_lut_rows(int max_len) {
 }
 
 // PK = true : two pairs per group (unsigned 16-bit halves).  PK = false: one pair per group (s32).
-template <int G, int T, bool PK>
+// BITS = 8 (byte-coded reads, any alphabet; packed mode only): the diagonal cost comes from
+// XOR + min(.,1) + multiply-add (LOP3, VIMNMX.U16x2, IMAD) instead of the 4-entry PRMT table;
+// requires eqc == 0 (match >= mismatch).
+template <int G, int T, bool PK, int BITS = 2>
 __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : OVL_DP_MINB)) overlap_dp_kernel(
     const uint32_t* __restrict__ packed, int row_words, const int32_t* __restrict__ len,
     const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b, int64_t P, int lut_rows,
@@ -202,7 +210,7 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : OVL_DP_MINB)) overla
     }
     while (!mbar_try_wait(bar, 0)) { }                      // the rows have landed (phase 0 completes once)
     const int nmax = PK ? max(n[0], n[PAIRS - 1]) : n[0];
-    const int max_col = row_words * 16 - 1;
+    const int max_col = row_words * (BITS == 2 ? 16 : 4) - 1;
 
     // ---- per-row tables: lut.x / lut.y = bytes {cost of s[i] vs code 0..3} for pair 0 / 1
     uint2* lut = smem_lut + (size_t)gib * lut_rows;
@@ -210,9 +218,10 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : OVL_DP_MINB)) overla
         const uint32_t nec4 = (uint32_t)prm.nec * 0x01010101u;
         const uint32_t flip = (uint32_t)(prm.eqc ^ prm.nec);
         for (int i = r; i < nmax; i += G) {
-            uint32_t ca = base_code(srow[0], min(i, max_col));
-            uint32_t cb = base_code(srow[PAIRS - 1], min(i, max_col));
-            lut[i] = PK ? make_uint2(nec4 ^ (flip << (8 * ca)), nec4 ^ (flip << (8 * cb))) : make_uint2(ca, 0u);
+            uint32_t ca = read_symbol<BITS>(srow[0], min(i, max_col));
+            uint32_t cb = read_symbol<BITS>(srow[PAIRS - 1], min(i, max_col));
+            if (BITS == 8)      lut[i] = make_uint2(PK ? (ca | (cb << 16)) : ca, 0u);     // the two query symbols
+            else                lut[i] = PK ? make_uint2(nec4 ^ (flip << (8 * ca)), nec4 ^ (flip << (8 * cb))) : make_uint2(ca, 0u);
         }
     }
     __syncwarp();
@@ -229,10 +238,10 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : OVL_DP_MINB)) overla
 #pragma unroll
     for (int c = 0; c < T; ++c) {
         int j = min(r * T + c, max_col);
-        uint32_t ca = base_code(trow[0], j);
+        uint32_t ca = read_symbol<BITS>(trow[0], j);
         if (PK) {
-            uint32_t cb = base_code(trow[PAIRS - 1], j);
-            sel[c] = ca | 0x80u | ((4u + cb) << 8) | 0x8000u;
+            uint32_t cb = read_symbol<BITS>(trow[PAIRS - 1], j);
+            sel[c] = BITS == 8 ? (ca | (cb << 16)) : (ca | 0x80u | ((4u + cb) << 8) | 0x8000u);
         } else {
             sel[c] = ca;
         }
@@ -279,8 +288,14 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : OVL_DP_MINB)) overla
             for (int c = 0; c < T; ++c) {
                 uint32_t g;
                 if (PK) {
-                    uint32_t dc = prmt(lu.x, lu.y, sel[c]);
-                    uint32_t a1 = fma_add(dc, one, diag);
+                    uint32_t a1;
+                    if (BITS == 8) {
+                        uint32_t ne = __vminu2(sel[c] ^ lu.x, 0x00010001u);      // 1 per half where the symbols differ
+                        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a1) : "r"(ne), "r"((uint32_t)prm.nec), "r"(diag));
+                    } else {
+                        uint32_t dc = prmt(lu.x, lu.y, sel[c]);
+                        a1 = fma_add(dc, one, diag);
+                    }
                     if (dp_form2(c)) {
                         uint32_t a2 = fma_add(up[c], one, gu2);
                         uint32_t a3 = fma_add(left, one, gl2);
@@ -367,13 +382,6 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : OVL_DP_MINB)) overla
 // recurrence, same first-minimum rule).  Slower per cell than the packed kernel, any length whose
 // diagonals fit shared memory (3 * (n+1) ints).
 constexpr int kDpLongThreads = 256;
-
-// BITS = 2: 2-bit packed rows (row_words words per read); BITS = 8: byte rows (row_words*4 bytes per
-// read, any alphabet -- the route for read sets with more than four distinct symbols)
-template <int BITS>
-__device__ __forceinline__ uint32_t read_symbol(const uint32_t* row, int i) {
-    return BITS == 2 ? base_code(row, i) : (uint32_t)reinterpret_cast<const uint8_t*>(row)[i];
-}
 
 template <int BITS>
 __global__ void __launch_bounds__(kDpLongThreads) overlap_dp_long_kernel(

@@ -382,7 +382,7 @@ bool dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_t indel, in
     return false;
 }
 
-template <int G, int T, bool PK>
+template <int G, int T, bool PK, int BITS = 2>
 int launch_dp(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, const int32_t* pair_a, const int32_t* pair_b,
               int64_t P, int32_t max_len, const DpParams& prm, int32_t* score, int32_t* end, const DpEdgeOut& eo, cudaStream_t st) {
     constexpr int PAIRS = PK ? 2 : 1;
@@ -395,16 +395,19 @@ int launch_dp(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int
                 + (size_t)GROUPS_PER_CTA * lut_rows * sizeof(uint2)                       // per-row score tables
                 + (kDpThreads / 32) * sizeof(uint64_t);                                   // one mbarrier per warp
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(overlap_dp_kernel<G, T, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(overlap_dp_kernel<G, T, PK, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(OVL_E_CUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));
     }
-    overlap_dp_kernel<G, T, PK><<<(unsigned)grid, kDpThreads, smem, st>>>(packed, row_words, len, pair_a, pair_b, P, lut_rows, prm, score, end, eo);
+    overlap_dp_kernel<G, T, PK, BITS><<<(unsigned)grid, kDpThreads, smem, st>>>(packed, row_words, len, pair_a, pair_b, P, lut_rows, prm, score, end, eo);
     LAUNCH_CHECK("overlap_dp_kernel");
     return OVL_OK;
 }
 
 #define DP_CASE(G_, T_, PK_) \
     if (plan.G == G_ && plan.T == T_) return launch_dp<G_, T_, PK_>(ctx, packed, row_words, len, pair_a, pair_b, P, max_len, plan.prm, score, end, eo, st);
+#define DP_CASE8(G_, T_) \
+    if (plan.G == G_ && plan.T == T_) return launch_dp<G_, T_, true, 8>(ctx, packed, row_words, len, pair_a, pair_b, P, max_len, plan.prm, score, end, eo, st);
+#define DP_CASES8_T(T_) DP_CASE8(1, T_) DP_CASE8(2, T_) DP_CASE8(4, T_) DP_CASE8(8, T_) DP_CASE8(16, T_) DP_CASE8(32, T_)
 #define DP_CASES_T(T_, PK_) \
     DP_CASE(1, T_, PK_) DP_CASE(2, T_, PK_) DP_CASE(4, T_, PK_) DP_CASE(8, T_, PK_) DP_CASE(16, T_, PK_) DP_CASE(32, T_, PK_)
 
@@ -443,8 +446,18 @@ static int dp_dispatch(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, 
         return fail(OVL_E_ARG, "%s: row_words=%d does not hold max_len=%d", who, row_words, max_len);
     if (max_len > OVL_MAX_LONG_READ_LEN)
         return fail(OVL_E_UNSUPPORTED, "%s: read length %d exceeds the supported maximum %d", who, max_len, OVL_MAX_LONG_READ_LEN);
+    if (code_bits == 8 && max_len <= 32 * 38 && mode != 2) {
+        // byte-coded reads: the packed wavefront kernel with XOR/min/IMAD costs, when the scores fit 16 bits
+        DpPlan plan;
+        if (dp_plan(max_len, match, mismatch, indel, 1, group_lanes, cols_per_lane, &plan) && plan.T != 19 && plan.T != 76 &&
+            plan.prm.eqc == 0) {
+            cudaStream_t st = (cudaStream_t)stream;
+            DP_CASES8_T(25) DP_CASES8_T(32) DP_CASES8_T(38)
+        }
+    }
     if (max_len > OVL_MAX_READ_LEN || code_bits == 8) {
-        // longer than the register wavefront, or byte-coded reads: CTA-per-pair anti-diagonal kernel (int32 cost space)
+        // longer than the register wavefront, or byte-coded reads the packed kernel cannot take:
+        // CTA-per-pair anti-diagonal kernel (int32 cost space)
         DpParams prm;
         if (mode == 1 || !dp_params(match, mismatch, indel, max_len, max_len, false, &prm))
             return fail(OVL_E_UNSUPPORTED, "%s: no kernel for (match=%lld, mismatch=%lld, indel=%lld, len=%d, mode=%d)",

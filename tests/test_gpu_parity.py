@@ -294,6 +294,32 @@ def test_batch_dp_long_reads_use_the_anti_diagonal_kernel(eng):
     assert list(G.edges(data=True)) == list(orc.to_networkx(nodes, edges).edges(data=True))
 
 
+@pytest.mark.parametrize("max_len", [12, 30, 100, 150, 400, 1000, 1500])
+def test_byte_coded_dp_equals_oracle(eng, max_len):
+    """Byte-coded reads (any alphabet): packed wavefront kernel with XOR/min/IMAD costs when the scores
+    fit 16 bits, the anti-diagonal kernel otherwise -- both against the oracle."""
+    import torch
+    rng = random.Random(1000 + max_len)
+    alphabet = "ACGTNRYacgt"
+    g = "".join(rng.choice(alphabet) for _ in range(3 * max_len + 20))
+    reads = []
+    for _ in range(80):
+        st = rng.randrange(len(g))
+        reads.append("".join(ch if rng.random() > 0.03 else rng.choice(alphabet) for ch in g[st:st + max_len]))
+    reads += ["", "N", "ACGTN"]
+    bases, offsets = orc.concat_reads(reads)
+    rs = eng.upload_reads(bases[:int(offsets[-1])], offsets, code_bits=8)
+    n_pairs = 201 if max_len > 400 else 1501
+    pa = np.array([rng.randrange(len(reads)) for _ in range(n_pairs)], dtype=np.int32)
+    pb = np.array([rng.randrange(len(reads)) for _ in range(n_pairs)], dtype=np.int32)
+    ta, tb = torch.from_numpy(pa).to(eng.device), torch.from_numpy(pb).to(eng.device)
+    wide = (10, -1000000, -2 ** 31) if max_len <= 400 else (10, -100000, -2 ** 31)     # int32 route, must stay < 2^30
+    for prm in [(10, -1, -2 ** 31), (10, -1, -2), (2, -3, -2), (-1, 10, -2), wide]:
+        s, e = eng.overlap_scores(rs, ta, tb, *prm)
+        ws, we = orc.overlap_pairs(bases, offsets, pa, pb, *prm)
+        assert np.array_equal(s.cpu().numpy(), ws) and np.array_equal(e.cpu().numpy(), we), (max_len, prm)
+
+
 def test_batch_dp_wide_scores_use_int32_kernel(eng):
     rng = random.Random(5)
     reads = overlapping_reads(rng, 100, 400, 120, 0.05)

@@ -58,10 +58,10 @@ def rate(bases, offsets, k, code_bits, label):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); eng.overlap_scores(rs, pa, pb); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(f"{label}: {pa.shape[0]} pairs, {cells:.3e} cells, DP {ms:.2f} ms = {cells/ms/1e6:.0f} GCUPS ({eng.dp_plan(rs.max_len)['mode'] if code_bits == 2 else 'byte-coded long-read kernel'})")
+    print(f"{label}: {pa.shape[0]} pairs, {cells:.3e} cells, DP {ms:.2f} ms = {cells/ms/1e6:.0f} GCUPS ({eng.dp_plan(rs.max_len)['mode'] if code_bits == 2 else 'byte-coded'})")
 g = synth.random_genome(400_000, 3)
 b, o = synth.simulate_reads(g, 4000, 4000, 0.02, seed=5)
 rate(b, o, 12, 2, "l=4000 (anti-diagonal CTA-per-pair kernel)")
 b, o = synth.simulate_reads(synth.phix_like_genome(), 20000, 150, 0.01, seed=6)
 rate(b, o, 5, 2, "PhiX-like N=20000 l=150, 2-bit packed")
-rate(b, o, 5, 8, "same reads, byte-coded general kernels")
+rate(b, o, 5, 8, "same reads, byte-coded (8-bit symbols in the packed wavefront kernel)")
