@@ -105,3 +105,57 @@ def test_long_reads_sample_vs_oracle():
     pa_h, pb_h = pa.cpu().numpy()[sel], pb.cpu().numpy()[sel]
     ws, we = orc.overlap_pairs(ub, uo, pa_h, pb_h)
     assert np.array_equal(score.cpu().numpy()[sel], ws) and np.array_equal(end.cpu().numpy()[sel], we)
+
+
+def test_config2_one_million_reads_properties():
+    """BASELINE.json configs[2] at full size (1 M reads x 150 bp, k = 5): size-independent properties of the
+    index / join on all 9.3e8 pairs, and oracle parity of the DP on random samples of them."""
+    import torch
+    synth = load_pkg("synth")
+    eng = load_pkg("engine").get_engine()
+    bases, offsets = synth.make_workload("ecoli_n1m_l150")
+    ub, uo, counts, _ = synth.dedup(bases, offsets)
+    U = len(counts)
+    rs = eng.upload_reads(ub, uo)
+    eng.check_alphabet(rs)
+    k = 5
+    idx = eng.kmer_index(rs, k)
+    pa, pb, _ = eng.candidate_pairs(rs, idx, k)
+    P = int(pa.shape[0])
+    # (1) the pair count equals an independent NumPy join on the host
+    lens = (uo[1:] - uo[:-1])
+    valid = np.nonzero(lens >= k)[0]
+    code = np.zeros(256, np.int64)
+    code[np.frombuffer(b"ACGT", np.uint8)] = np.arange(4)
+    pk = sum(code[ub[uo[valid] + i]] * 4 ** i for i in range(k))
+    sk = sum(code[ub[uo[valid + 1] - k + i]] * 4 ** i for i in range(k))
+    hist = np.bincount(pk, minlength=4 ** k)
+    assert P == int(hist[sk].sum() - (pk == sk).sum())
+    # (2) ordered by (a, b), no self pairs -- checked on the device over all pairs
+    a64, b64 = pa.to(torch.int64), pb.to(torch.int64)
+    key = a64 * U + b64
+    assert bool((key[1:] > key[:-1]).all())
+    assert bool((pa != pb).all())
+    del key, a64, b64
+    # (3) suffix_k(a) == prefix_k(b) for every pair, via the device keys
+    assert bool((idx.suffix_key[:U][pa.long()] == idx.prefix_key[:U][pb.long()]).all())
+    # (4) sharded slices tile the list exactly
+    q = [eng.candidate_pairs(rs, idx, k, (r, 8)) for r in (0, 3, 7)]
+    assert q[0][2] == 0 and q[1][2] == P * 3 // 8 and q[2][2] == P * 7 // 8
+    assert torch.equal(q[1][0], pa[P * 3 // 8:P * 4 // 8]) and torch.equal(q[2][1], pb[P * 7 // 8:])
+    del q
+    # (5) DP parity on random samples of the real pair list, default and finite indel
+    g = torch.Generator(device="cpu").manual_seed(7)
+    sel = torch.randint(0, P, (6000,), generator=g).to(eng.device)
+    sa, sb = pa[sel].contiguous(), pb[sel].contiguous()
+    for prm in [(10, -1, -2 ** 31), (10, -1, -2)]:
+        s, e = eng.overlap_scores(rs, sa, sb, *prm)
+        ws, we = orc.overlap_pairs(ub, uo, sa.cpu().numpy(), sb.cpu().numpy(), *prm)
+        assert np.array_equal(s.cpu().numpy(), ws) and np.array_equal(e.cpu().numpy(), we)
+    # (6) score bounds over a 20 M-pair slice: 10*k <= score <= 10*min(len), 0 <= end <= len(b)
+    n = min(P, 20_000_000)
+    s, e = eng.overlap_scores(rs, pa[:n].contiguous(), pb[:n].contiguous())
+    ld = rs.length[:U]
+    la, lb = ld[pa[:n].long()], ld[pb[:n].long()]
+    assert bool((s >= 10 * k).all()) and bool((s <= 10 * torch.minimum(la, lb)).all())
+    assert bool((e >= 0).all()) and bool((e <= lb).all())
