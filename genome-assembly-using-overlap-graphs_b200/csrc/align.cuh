@@ -147,4 +147,81 @@ __global__ void __launch_bounds__(kAlignThreads) local_align_kernel(const int32_
     }
 }
 
+// K8, row-per-thread variant for queries up to 1,024 symbols (reads and typical contigs): thread t owns
+// query row i = t + 1 for the whole sweep.  On diagonal d it computes cell (i, j = d - i); its "left"
+// H[i][j-1] is its own previous output, its "up" H[i-1][j] is the left neighbour's previous output (one
+// __shfl_up_sync) and its "diag" H[i-1][j-1] the one before that.  Only warp boundaries go through
+// shared memory, double buffered, so a diagonal costs one block barrier (none for a single warp).
+// tb is diagonal-major here: byte (d, i) at tb[d*(n+1) + i] -- consecutive threads, consecutive bytes.
+__global__ void __launch_bounds__(kAlignThreads) local_align_rows_kernel(const int32_t* __restrict__ q, int n,
+                                                                         const int32_t* __restrict__ ref, int m,
+                                                                         int64_t match, int64_t mismatch, int64_t indel,
+                                                                         int8_t* __restrict__ tb,
+                                                                         int32_t* __restrict__ result, uint8_t* __restrict__ ops) {
+    __shared__ int32_t edge[2][kAlignThreads / 32];
+    __shared__ int32_t s_best[kAlignThreads / 32], s_bi[kAlignThreads / 32], s_bj[kAlignThreads / 32];
+    const int t = threadIdx.x, i = t + 1, wid = t >> 5;
+    const unsigned lane = lane_id();
+    const bool row_ok = i <= n;
+    const int S = n + 1;
+    const int32_t qi = row_ok ? q[i - 1] : -1;
+    int32_t out_prev = 0;        // my cell on the previous diagonal  (H[i][j-1], 0 outside the matrix)
+    int32_t up_prev = 0;         // the neighbour's cell two diagonals ago (H[i-1][j-1])
+    int32_t best = 0, bj = 0;
+    if (t < kAlignThreads / 32) { edge[0][t] = 0; edge[1][t] = 0; s_best[t] = 0; s_bi[t] = 0; s_bj[t] = 0; }
+    __syncthreads();
+    for (int d = 2; d <= n + m; ++d) {
+        int32_t up = __shfl_up_sync(kFull, out_prev, 1);
+        if (lane == 0) up = wid == 0 ? 0 : edge[(d - 1) & 1][wid - 1];     // row i-1 lives in the previous warp (or is row 0)
+        const int j = d - i;
+        int32_t v = 0;
+        if (row_ok && j >= 1 && j <= m) {
+            int64_t dg = (int64_t)up_prev + (qi == ref[j - 1] ? match : mismatch);
+            int64_t u = (int64_t)up + indel;
+            int64_t lf = (int64_t)out_prev + indel;
+            int8_t dir;
+            if (dg >= u && dg >= lf && dg >= 0) { v = (int32_t)dg; dir = 1; }
+            else if (u >= lf && u >= 0)         { v = (int32_t)u;  dir = 2; }
+            else if (lf >= 0)                   { v = (int32_t)lf; dir = 3; }
+            else                                { v = 0;           dir = 0; }
+            tb[(size_t)d * S + i] = (int8_t)(dir | (v > 0 ? 4 : 0));
+            if (v > best) { best = v; bj = j; }            // j ascends along my row: first strict maximum
+        }
+        up_prev = up;
+        out_prev = v;
+        if (lane == 31) edge[d & 1][wid] = v;
+        if (blockDim.x > 32) __syncthreads();
+    }
+    // block arg-max: value, then smaller i, then smaller j (row-major first maximum, aligners.py:135-137)
+    int32_t bi = i;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        int32_t ob = __shfl_xor_sync(kFull, best, off), oi = __shfl_xor_sync(kFull, bi, off), oj = __shfl_xor_sync(kFull, bj, off);
+        if (ob > best || (ob == best && ob > 0 && (oi < bi || (oi == bi && oj < bj)))) { best = ob; bi = oi; bj = oj; }
+    }
+    if (lane == 0) { s_best[wid] = best; s_bi[wid] = bi; s_bj[wid] = bj; }
+    __syncthreads();
+    if (t == 0) {
+        for (int w = 1; w < kAlignThreads / 32; ++w) {
+            int32_t ob = s_best[w], oi = s_bi[w], oj = s_bj[w];
+            if (ob > best || (ob == best && ob > 0 && (oi < bi || (oi == bi && oj < bj)))) { best = ob; bi = oi; bj = oj; }
+        }
+        if (best == 0) { bi = 0; bj = 0; }                 // nothing beat the initial (0, 0), aligners.py:113-114
+        int ii = bi, jj = bj, L = 0;
+        while (ii > 0 && jj > 0) {
+            int8_t x = tb[(size_t)(ii + jj) * S + ii];
+            if (!(x & 4)) break;
+            int dir = x & 3;
+            if (dir == 0) break;
+            ops[L++] = (uint8_t)dir;
+            if (dir == 1) { --ii; --jj; } else if (dir == 2) { --ii; } else { --jj; }
+        }
+        result[0] = best;
+        result[1] = jj;
+        result[2] = bj;
+        result[3] = L;
+        result[4] = bi;
+    }
+}
+
 }  // namespace ovl

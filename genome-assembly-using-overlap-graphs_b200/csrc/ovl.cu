@@ -688,7 +688,8 @@ int ovl_align_pair(ovl_ctx* ctx, const int32_t* s, int32_t n, const int32_t* t, 
 size_t ovl_local_align_workspace_bytes(int32_t n, int32_t m) {
     if (n < 0) n = 0;
     if (m < 0) m = 0;
-    return align256((size_t)3 * (n + 1) * sizeof(int32_t)) + align256((size_t)(n + 1) * (m + 1)) + 256;
+    // the row-per-thread kernel stores its traceback diagonal-major: (n + m + 1) diagonals of n + 1 bytes
+    return align256((size_t)3 * (n + 1) * sizeof(int32_t)) + align256((size_t)(n + 1) * (n + m + 2)) + 256;
 }
 
 int ovl_local_align(ovl_ctx* ctx, const int32_t* query, int32_t n, const int32_t* reference, int32_t m, int64_t match,
@@ -700,6 +701,13 @@ int ovl_local_align(ovl_ctx* ctx, const int32_t* query, int32_t n, const int32_t
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     int32_t* diag = (int32_t*)ws;
     int8_t* tb = (int8_t*)(ws + align256((size_t)3 * (n + 1) * sizeof(int32_t)));
+    if (n >= 1 && n <= kAlignThreads) {
+        // row-per-thread sweep: neighbours exchange cells with shuffles, one barrier per diagonal
+        local_align_rows_kernel<<<1, ((n + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(query, n, reference, m, match, mismatch, indel,
+                                                                                    tb, result, ops);
+        LAUNCH_CHECK("local_align_rows_kernel");
+        return OVL_OK;
+    }
     // as many threads as the longest anti-diagonal needs (a block barrier per diagonal: fewer warps, cheaper barrier)
     int threads = std::min(kAlignThreads, std::max(32, ((std::min(n, m) + 31) / 32) * 32));
     size_t smem = (size_t)3 * (n + 1) * sizeof(int32_t);
