@@ -35,7 +35,7 @@
 // Per column (2 cells) the kernel issues either
 //     form 1:  PRMT, IMAD, VIADDMNMX, VIADDMNMX          (3 ALU + 1 FMA)
 //     form 2:  PRMT, IMAD, IMAD, IMAD, VIMNMX3           (2 ALU + 3 FMA)
-// mixed OVL_DP_F2_NUM : OVL_DP_F2_DEN to balance the two pipes.
+// mixed: OVL_DP_F2_NUM columns out of every OVL_DP_F2_DEN use form 2 (default 1 in 3, measured best).
 //
 // A 32-bit variant (one pair per group, s32 DPX ops, compare+select for dc) covers scoring
 // schemes or read lengths whose range does not fit 16 bits.
@@ -52,8 +52,8 @@ struct DpParams {
     int32_t gu;         // effective cost of an up move   (maxs - indel), clamped
     int32_t gl;         // effective cost of a left move  (-indel), clamped
     uint32_t one;       // == 1, a runtime value so the adds stay IMADs
-    // the same constants pre-packed for the kernel (both 16-bit halves in packed mode), so that
-    // they reach the instructions as uniform/constant operands and cost no register-file reads
+    // the same constants pre-packed on the host (both 16-bit halves in packed mode); only read with
+    // OVL_DP_PREPACK=1, which was measured slower than packing them in the kernel prologue
     uint32_t gu2, gl2, maxs2, beta2;
 };
 
