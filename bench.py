@@ -5,21 +5,24 @@
     python bench.py --impl reference ...      # the CPU arm (oracle port on the host cores)
 
 A step = one pass of the hot path over the workload: pack -> k-mer keys -> prefix index ->
-candidate join -> overlap DP -> edge expansion (-> edge gather when N > 1).
+candidate join -> overlap DP -> edge expansion (-> edge exchange when N > 1).
   value  GCUPS = sum over candidate pairs of len(a)*len(b) (cells as the reference fills them,
          aligners.py:33-34) / step time, inputs resident in HBM.
   e2e    the same through the host-buffer call (engine.overlap_edges): H2D of the reads and
          D2H of the edge rows inside the timed region.
-Prints ONE JSON line on rank 0.
+Prints ONE JSON line on rank 0.  At N = 1 the line also carries `configs_extra`: the other
+BASELINE.json configs (PhiX N=1000 / N=50,000, the l=1000 long-read set at k=8 and k=5, and the
+experiments.py parameter sweep as one batched job), each measured the same way in the same run.
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
 import importlib
+import io
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -34,13 +37,29 @@ PKG = "genome-assembly-using-overlap-graphs_b200"
 METRIC = "overlap_gcups"
 UNIT = "GCUPS"
 OPS_PER_CELL = 7        # compare, select, 3 adds, 2 max
+SCORING = "match 10, mismatch -1, indel -2^31 (reference defaults)"
+L2_NOTE = "GPU arm: flushed between timed iterations (256 MiB memset)"
 
 
-def load_workload(name, seed):
-    synth = importlib.import_module(PKG + ".synth")
-    bases, offsets = synth.make_workload(name, seed)
-    ub, uo, counts, _ = synth.dedup(bases, offsets)           # host part of the builder (read_copies)
-    return ub, uo, counts, len(offsets) - 1
+class Workload:
+    """Host side of one workload: the unique reads (the host part of the builder, read_copies)."""
+
+    def __init__(self, name, seed, k):
+        synth = importlib.import_module(PKG + ".synth")
+        bases, offsets = synth.make_workload(name, seed)
+        self.name, self.seed, self.k = name, seed, k
+        self.n_reads = len(offsets) - 1
+        self.ub, self.uo, self.counts, _ = synth.dedup(bases, offsets)
+        self.U = len(self.counts)
+        self.total_bases = int(self.uo[-1])
+        self.max_len = int((self.uo[1:] - self.uo[:-1]).max())
+        self.has_dups = bool(self.counts.max() > 1)
+
+    def shared_config(self, pairs=None):
+        """The keys both arms print (the driver compares them)."""
+        return {"workload": self.name, "k": self.k, "seed": self.seed, "reads": self.n_reads,
+                "unique_reads": self.U, "max_read_len": self.max_len, "candidate_pairs": pairs, "scoring": SCORING,
+                "l2": L2_NOTE}
 
 
 def peaks():
@@ -133,7 +152,11 @@ def cpu_arm(ub, uo, pair_a, pair_b, target_s=12.0, nthreads=0, total_pairs=None)
     lens = (uo[1:] - uo[:-1]).astype(np.int64)
     rng = np.random.Generator(np.random.PCG64(99))
     P = len(pair_a)
-    probe = min(P, 256 * cores)
+    if P == 0:
+        return {"value": 0.0, "unit": UNIT, "cores": cores, "kind": "port", "sample": "no candidate pairs",
+                "seconds": 0.0, "pairs": 0, "cells": 0}
+    cells_per_pair = float((lens[pair_a[:4096]] * lens[pair_b[:4096]]).mean())
+    probe = min(P, max(2 * cores, int(256 * cores * 22500 / max(cells_per_pair, 1.0))))
     sel = rng.choice(P, size=probe, replace=False) if P > probe else np.arange(P)
     t0 = time.perf_counter()
     orc.overlap_pairs(ub, uo, pair_a[sel], pair_b[sel], full=True, nthreads=cores)
@@ -156,7 +179,6 @@ def host_candidate_pairs(ub, uo, k, max_pairs=None):
     reads is expanded (all their candidates), so memory stays bounded on the big workloads.
     Returns (pair_a, pair_b, total_pairs)."""
     lens = (uo[1:] - uo[:-1]).astype(np.int64)
-    U = len(lens)
     code = np.zeros(256, np.uint64)
     for i, ch in enumerate(b"ACGT"):
         code[ch] = i
@@ -187,83 +209,144 @@ def host_candidate_pairs(ub, uo, k, max_pairs=None):
     return a[keep].astype(np.int32), b[keep].astype(np.int32), total
 
 
+def numba_reference_sample(wl, pair_a, pair_b, seconds=8.0):
+    """The LIVE, unmodified Numba reference (aligners.overlap_alignment) on a small sample of the same
+    pairs -- only where a reference checkout is importable (the build container; the GPU box has none)."""
+    try:
+        from oracle import ref_loader
+        if not ref_loader.available():
+            return None
+        ref_al, _ = ref_loader.load()
+    except Exception:                      # noqa: BLE001  (numba missing, ...)
+        return None
+    buf = wl.ub.tobytes().decode("ascii")
+    off = wl.uo.tolist()
+    ref_al.overlap_alignment("ACGT", "ACGT")                # JIT warm-up (not timed)
+    n, cells = 0, 0
+    t0 = time.perf_counter()
+    for a, b in zip(pair_a.tolist(), pair_b.tolist()):
+        s, t = buf[off[a]:off[a + 1]], buf[off[b]:off[b + 1]]
+        ref_al.overlap_alignment(s, t)
+        n += 1
+        cells += len(s) * len(t)
+        if time.perf_counter() - t0 > seconds:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": cells / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "reference (live Numba, build container only)",
+            "sample": f"{n} candidate pairs ({cells:.3e} cells) in {dt:.2f} s, aligners.overlap_alignment, 1 process"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ub, uo, counts, n_reads = load_workload(args.workload, args.seed)
-    pa, pb, total_pairs = host_candidate_pairs(ub, uo, args.k, max_pairs=8_000_000)
+    wl = Workload(args.workload, args.seed, args.k)
+    pa, pb, total_pairs = host_candidate_pairs(wl.ub, wl.uo, args.k, max_pairs=8_000_000)
     per_step = max(2.0, min(20.0, 60.0 / max(args.steps + args.warmup, 1)))
     vals, secs = [], []
     last = None
     for it in range(args.warmup + args.steps):
-        last = cpu_arm(ub, uo, pa, pb, target_s=per_step, total_pairs=total_pairs)
+        last = cpu_arm(wl.ub, wl.uo, pa, pb, target_s=per_step, total_pairs=total_pairs)
         if it >= args.warmup:
             vals.append(last["value"]); secs.append(last["seconds"])
     v = float(np.mean(vals))
+    lens = (wl.uo[1:] - wl.uo[:-1]).astype(np.int64)
+    config = wl.shared_config(int(total_pairs))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": args.workload, "k": args.k, "seed": args.seed, "unique_reads": int(len(counts)),
-                       "candidate_pairs": int(total_pairs)},
+            "config": config,
             "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0,
+            "reference_arm_note": (f"each step = the CPU port over a random sample of the candidate pairs "
+                                   f"(~{per_step:.0f} s of work); ms_per_step is that sample's duration, not a workload step")}
     line["cpu_baseline"]["value"] = v
+    numba = numba_reference_sample(wl, pa[:4000], pb[:4000])
+    if numba is not None:
+        line["cpu_baseline_numba"] = numba
     print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------------------- GPU arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    engine_mod = importlib.import_module(PKG + ".engine")
-    par = importlib.import_module(PKG + ".parallel")
-    eng = engine_mod.get_engine(local_rank)
-    dev = eng.device
+class Env:
+    """Process-wide bench state: torch, the engine, ranks, the L2 flush buffer, the integer probe."""
 
-    ub, uo, counts, n_reads = load_workload(args.workload, args.seed)
-    U = len(counts)
-    total_bases = int(uo[-1])
-    max_len = int((uo[1:] - uo[:-1]).max())
-    has_dups = bool(counts.max() > 1)
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.engine_mod = importlib.import_module(PKG + ".engine")
+        self.par = importlib.import_module(PKG + ".parallel")
+        self.nat = importlib.import_module(PKG + "._native")
+        self.eng = self.engine_mod.get_engine(self.local_rank)
+        self.dev = self.eng.device
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)       # > 126 MB L2
+        self._probe = None
+
+    def ev(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def probe(self):
+        """Integer-pipe issue rates measured on this GPU in this run (G lane-instructions / s)."""
+        if self._probe is None:
+            import ctypes
+            names = {0: "iadd3", 1: "imad", 2: "vimnmx_s32", 3: "viaddmnmx_s16x2", 4: "dp_mix", 5: "prmt", 6: "lop3",
+                     7: "lop3_imad_pair", 8: "vimnmx3_imad_distinct_regs", 9: "dp_form1_column"}
+            out = {}
+            for kind, nm in names.items():
+                g, ms = ctypes.c_double(), ctypes.c_double()
+                self.nat.check(self.nat.lib.ovl_int_peak_probe(self.eng._ctx, kind, 2000, ctypes.byref(g), ctypes.byref(ms)))
+                out[nm] = round(g.value, 1)
+            self._probe = out
+        return self._probe
+
+
+def measure(env, wl, steps, warmup, cpu_seconds, use_peer=True, with_cpu=True, sample_clocks=True):
+    """One workload through the value leg (device-resident inputs), the e2e leg (host buffers) and the
+    CPU arm; returns the JSON line as a dict (rank 0) or None."""
+    torch, dist, eng, par, dev = env.torch, env.dist, env.eng, env.par, env.dev
+    rank, world = env.rank, env.world
+    U, k = wl.U, wl.k
 
     # pinned host buffers (the e2e leg copies from these every step)
-    h_bases = torch.from_numpy(ub[:total_bases].copy()).pin_memory()
-    h_off = torch.from_numpy(uo.copy()).pin_memory()
-    h_counts = torch.from_numpy(counts.copy()).pin_memory()
+    h_bases = torch.from_numpy(wl.ub[:wl.total_bases].copy()).pin_memory()
+    h_off = torch.from_numpy(wl.uo.copy()).pin_memory()
+    h_counts = torch.from_numpy(wl.counts.copy()).pin_memory()
     node_off_np = np.zeros(U + 1, np.int64)
-    np.cumsum(counts, out=node_off_np[1:])
+    np.cumsum(wl.counts, out=node_off_np[1:])
 
     # device-resident inputs for the `value` leg
-    d_ascii = torch.empty(total_bases + 64, dtype=torch.uint8, device=dev)
-    d_ascii[:total_bases].copy_(h_bases)
+    d_ascii = torch.empty(wl.total_bases + 64, dtype=torch.uint8, device=dev)
+    d_ascii[:wl.total_bases].copy_(h_bases)
     d_off = h_off.to(dev)
-    d_copies = h_counts.to(dev) if has_dups else None
-    d_node_off = torch.from_numpy(node_off_np).to(dev) if has_dups else None
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    d_copies = h_counts.to(dev) if wl.has_dups else None
+    d_node_off = torch.from_numpy(node_off_np).to(dev) if wl.has_dups else None
 
     shard = (rank, world)
-    ev = lambda: torch.cuda.Event(enable_timing=True)
     peer = None          # set after the first (NCCL-gather) pass, when the total edge count is known
     exchange = "none (1 GPU)"
 
     def device_step(record=None):
-        rs = eng.pack_reads(d_ascii, d_off, U, max_len)
-        index = eng.kmer_index(rs, args.k) if args.k > 0 else None
-        pa, pb, _ = eng.candidate_pairs(rs, index, args.k, shard)
+        rs = eng.pack_reads(d_ascii, d_off, U, wl.max_len)
+        index = eng.kmer_index(rs, k) if k > 0 else None
+        pa, pb, p_begin = eng.candidate_pairs(rs, index, k, shard)
         if record is not None:
             record["k1"].record()           # end of the k-mer stages (K0-K3)
-        # K6 is fused into the DP epilogue; with duplicate reads a scan of the per-pair edge counts
-        # (and one host read of the total) comes first
+        # K6 is fused into the DP epilogue; with duplicate reads the per-pair edge offsets come first
         edges = eng.overlap_edges_fused(rs, pa, pb, d_copies, d_node_off,
                                         events=(record["dp0"], record["dp1"]) if record is not None else None,
                                         sink=peer.slot if peer is not None else None)
@@ -271,35 +354,35 @@ def run_ours(args):
             # the DP epilogue has stored this rank's rows straight into rank 0's buffer over NVLink
             peer.barrier()
             return rs, pa, pb, None, peer.result()
-        if world > 1:
-            edges_all = par.gather_edges(edges, 0)
-        else:
-            edges_all = edges
+        edges_all = par.gather_edges(edges, 0) if world > 1 else edges
         return rs, pa, pb, edges, edges_all
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def list_hash(edges_all):
+        """Order-sensitive fingerprint of the complete list (rank 0), as an unsigned 64-bit int."""
+        if rank != 0 or edges_all is None:
+            return 0
+        return int(eng.edge_hash(edges_all).item()) & 0xFFFFFFFFFFFFFFFF
 
     # ---- untimed: workload statistics (cells as the reference fills them)
     rs, pa, pb, edges, edges_all = device_step()
     torch.cuda.synchronize()
-    eng.check_alphabet(rs)
     lens_d = rs.length[:U].to(torch.int64)
     cells_local = int((lens_d[pa.long()] * lens_d[pb.long()]).sum().item()) if pa.numel() else 0
     pairs_local = int(pa.shape[0])
     edges_local = int(edges.shape[0])
     stat = torch.tensor([cells_local, pairs_local, edges_local], dtype=torch.int64, device=dev)
+    stat_max = torch.tensor([pairs_local, cells_local], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(stat)
+        dist.all_reduce(stat_max, op=dist.ReduceOp.MAX)
     cells, pairs, n_edges = (int(x) for x in stat.cpu().tolist())
-    checksum = int(edges_all.to(torch.int64).sum().item()) if (rank == 0 and edges_all is not None) else 0
-    plan = eng.dp_plan(max_len)
-    del rs, pa, pb, edges, edges_all
+    pairs_rank_max, cells_rank_max = (int(x) for x in stat_max.cpu().tolist())
+    edge_hash = list_hash(edges_all)
+    plan = eng.dp_plan(wl.max_len)
+    del rs, pa, pb, edges, edges_all, lens_d
     if world > 1:
         exchange = "NCCL send/recv gather of the per-rank edge slices"
-        if not args.no_peer_stores:
+        if use_peer:
             err = None
             try:
                 peer = par.PeerEdgeBuffer(n_edges, dev)
@@ -312,44 +395,45 @@ def run_ours(args):
                 if rank == 0:
                     print(f"[bench] peer-memory path unavailable ({err}); using the NCCL gather", file=sys.stderr)
             else:
-                # self-check: the peer-store path must reproduce the gathered list
+                # self-check: the peer-store path must reproduce the gathered list row for row
                 _, _, _, _, chk_all = device_step()
-                ok = torch.tensor([1 if (rank != 0 or int(chk_all.to(torch.int64).sum().item()) == checksum) else 0],
-                                  device=dev)
+                ok = torch.tensor([1 if (rank != 0 or list_hash(chk_all) == edge_hash) else 0], device=dev)
                 dist.all_reduce(ok, op=dist.ReduceOp.MIN)
                 if int(ok.item()) != 1:
                     raise SystemExit("peer-store edge list differs from the gathered one")
                 exchange = "DP epilogue stores edge rows directly into rank 0's HBM (NVLink peer memory)"
 
     # ---- value leg: inputs resident in HBM
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    for _ in range(args.warmup):
+    sampler = ClockSampler(env.local_rank) if sample_clocks else None
+    if sampler:
+        sampler.start()
+    for _ in range(warmup):
         device_step()
-        flush.zero_()
-    barrier()
+        env.flush.zero_()
+    env.barrier()
     t_begin = time.time()
-    step_ms, dp_ms, kmer_ms = [], [], []
+    step_ms, dp_ms, kmer_ms, off_ms = [], [], [], []
     launches0 = eng.launches
-    for _ in range(args.steps):
-        flush.zero_()                                   # flush L2 between timed iterations
-        rec = {"dp0": ev(), "dp1": ev(), "k1": ev()}
-        e0, e1 = ev(), ev()
-        barrier()
+    for _ in range(steps):
+        env.flush.zero_()                               # flush L2 between timed iterations
+        rec = {"dp0": env.ev(), "dp1": env.ev(), "k1": env.ev()}
+        e0, e1 = env.ev(), env.ev()
+        env.barrier()
         e0.record()
         device_step(rec)
         e1.record()
-        barrier()
+        env.barrier()
         step_ms.append(e0.elapsed_time(e1))
         dp_ms.append(rec["dp0"].elapsed_time(rec["dp1"]))
         kmer_ms.append(e0.elapsed_time(rec["k1"]))
+        off_ms.append(rec["k1"].elapsed_time(rec["dp0"]))
     launches = eng.launches - launches0
-    clocks = sampler.stop(t_begin, time.time())
-    t = torch.tensor([sum(step_ms), sum(dp_ms), sum(kmer_ms)], dtype=torch.float64, device=dev)
+    clocks = sampler.stop(t_begin, time.time()) if sampler else None
+    t = torch.tensor([sum(step_ms), sum(dp_ms), sum(kmer_ms), sum(off_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)        # max over ranks
-    total_ms, dp_total_ms, kmer_total_ms = (float(x) for x in t.cpu().tolist())
-    ms_per_step = total_ms / args.steps
+    total_ms, dp_total_ms, kmer_total_ms, off_total_ms = (float(x) for x in t.cpu().tolist())
+    ms_per_step = total_ms / steps
     value = cells / (ms_per_step * 1e-3) / 1e9
 
     # ---- e2e leg: host buffers in, host edge rows out, every step
@@ -357,118 +441,305 @@ def run_ours(args):
 
     def e2e_step():
         if world == 1:
-            return eng.overlap_edges(h_bases, h_off, h_counts if has_dups else None, args.k, shard, reuse_host_buffer=True)
+            return eng.overlap_edges(h_bases, h_off, h_counts if wl.has_dups else None, k, shard, reuse_host_buffer=True)
         # every rank copies its slice over its own PCIe link into one shared, page-locked host buffer;
         # after the barrier rank 0 holds the complete ordered edge list in host memory
-        eng.overlap_edges(h_bases, h_off, h_counts if has_dups else None, args.k, shard, host_sink=sink)
+        eng.overlap_edges(h_bases, h_off, h_counts if wl.has_dups else None, k, shard, host_sink=sink)
         dist.barrier()
         return sink.rows()
 
-    for _ in range(max(1, min(args.warmup, 2))):      # at least one: the first call allocates the pinned result buffer
+    for _ in range(max(1, min(warmup, 2))):           # at least one: the first call allocates the pinned result buffer
         e2e_step()
     e2e_ms = []
     d2h_bytes = 0
-    for _ in range(args.steps):
-        flush.zero_()
-        barrier()
+    out = None
+    for _ in range(steps):
+        env.flush.zero_()
+        env.barrier()
         t0 = time.perf_counter()
         out = e2e_step()
         torch.cuda.synchronize()
         e2e_ms.append((time.perf_counter() - t0) * 1e3)
         d2h_bytes = out.nbytes + 16
-    # untimed: the host result of the last e2e step must be the same edge list as the device-resident step's
-    e2e_ok = bool(int(out.sum(dtype=np.int64)) == checksum and out.shape[0] == n_edges) if rank == 0 else None
+    # untimed: the host result of the last e2e step must be, row for row, the device-resident step's edge list
+    e2e_ok = bool(out.shape[0] == n_edges and eng.edge_hash_host(out) == edge_hash) if rank == 0 else None
     te = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_per_step = float(te.item()) / args.steps
-    h2d_bytes = total_bases + h_off.numel() * 8 + (h_counts.numel() * 4 + (U + 1) * 8 if has_dups else 0)
+    e2e_per_step = float(te.item()) / steps
+    h2d_bytes = wl.total_bases + h_off.numel() * 8 + (h_counts.numel() * 4 + (U + 1) * 8 if wl.has_dups else 0)
 
+    line = None
     if rank == 0:
-        # ---- roofline of the dominant kernel (the DP): integer pipe, not HBM
-        probe = {}
-        names = {0: "iadd3", 1: "imad", 2: "vimnmx_s32", 3: "viaddmnmx_s16x2", 4: "dp_mix", 5: "prmt", 6: "lop3",
-                 7: "lop3_imad_pair", 8: "vimnmx3_imad_distinct_regs", 9: "dp_form1_column"}
-        import ctypes
-        nat = importlib.import_module(PKG + "._native")
-        for kind, nm in names.items():
-            g, ms = ctypes.c_double(), ctypes.c_double()
-            nat.check(nat.lib.ovl_int_peak_probe(eng._ctx, kind, 2000, ctypes.byref(g), ctypes.byref(ms)))
-            probe[nm] = round(g.value, 1)
-        dp_ms_avg = dp_total_ms / args.steps
-        cells_per_launch = cells / world                       # each rank launches the DP on its slice
+        # ---- roofline of the dominant kernel (the DP): integer pipes, not HBM
+        probe = env.probe()
+        dp_ms_avg = dp_total_ms / steps
+        cells_per_launch = cells_rank_max                      # the slowest rank's slice (max-over-ranks time)
         achieved = cells_per_launch * OPS_PER_CELL / (dp_ms_avg * 1e-3) / 1e12
         # Peak of the integer pipes for this op class, measured in this run: the ALU pipe issues
         # VIADDMNMX.U16x2 at `viaddmnmx_s16x2` G lane-instr/s, each doing 4 algorithmic 16-bit ops
         # (2 halves x (add + min)); the FMA pipe co-issues IMAD at `imad` G lane-instr/s, each a
         # packed add = 2 algorithmic ops.
-        peak = (probe["viaddmnmx_s16x2"] * 4 + probe["imad"] * 2) / 1e3 if plan["mode"] == "packed16" \
+        packed = plan["mode"] == "packed16"
+        peak = (probe["viaddmnmx_s16x2"] * 4 + probe["imad"] * 2) / 1e3 if packed \
             else (probe["viaddmnmx_s16x2"] * 2 + probe["imad"]) / 1e3
-        peak_int32 = probe["lop3"] / 1e3            # int32 lanes x clock (one op per lane-instr)
+        # SURVEY 8(d)'s own denominator: plain int32 lanes x clock, one algorithmic op per lane-instruction, at the
+        # rate the min/max instruction issues (VIMNMX.S32: 128 lanes/clk/SM).  Packed DPX does two 16-bit cells per
+        # lane-instruction, so this fraction exceeds 1 by design; it is reported, not used as the ceiling.
+        peak_int32 = probe["vimnmx_s32"] / 1e3
         pk, pk_kind = peaks()
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "dp_traffic.json")) as fh:
-                ent = json.load(fh).get(f"{args.workload}:k{args.k}:gpus{world}")
+                ent = json.load(fh).get(f"{wl.name}:k{k}:gpus{world}")
             if ent:
                 traffic = ent["dram_bytes_read"] + ent["dram_bytes_write"]      # one ncu capture, per launch
-        except Exception:
+        except Exception:                                  # noqa: BLE001
             traffic = None
-        roofline = {"bound": "int-pipe (ALU DPX + FMA IMAD)",
-                    "kernel": f"overlap_dp_kernel<{plan['lanes']},{plan['cols']},{plan['mode']}>",
+        kernel = {"packed16": f"overlap_dp_kernel<{plan['lanes']},{plan['cols']},packed16>",
+                  "int32": f"overlap_dp_kernel<{plan['lanes']},{plan['cols']},int32>",
+                  "long-read": "overlap_dp_long_kernel"}[plan["mode"]]
+        roofline = {"bound": "int-pipe (ALU DPX + FMA IMAD)", "kernel": kernel,
                     "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak if peak else None,
                     "traffic": traffic, "ops_per_cell": OPS_PER_CELL,
                     "dp_gcups": cells_per_launch / (dp_ms_avg * 1e-3) / 1e9, "dp_ms": dp_ms_avg,
                     "peak_source": "ovl_int_peak_probe in this run: 4 ops x VIADDMNMX.16x2 rate + 2 ops x IMAD rate",
                     "frac_vs_int32_lanes": achieved / peak_int32, "peak_int32_lanes": peak_int32,
+                    "peak_int32_lanes_source": "VIMNMX.S32 issue rate measured in this run (SURVEY 8d's denominator)",
                     # what a pure stream of the kernel's own form-1 columns (PRMT, IMAD, 2x VIADDMNMX on distinct
                     # registers, no loop overhead) sustains on this GPU: 2 cells per 4 lane-instructions
                     "same_mix_stream_gcups": probe["dp_form1_column"] / 4 * 2,
                     "int_probe_gops": probe, "hbm_peak_gbs": pk.get("hbm_gbs"), "hbm_peak_source": pk_kind}
-        # ---- the k-mer stages (K0-K3) and edge expansion (K6): HBM-bound; algorithmic bytes per SURVEY 8(d)
-        passes = (2 * args.k + 7) // 8
-        kb = (total_bases + total_bases / 4) + 48 * U + 12 * (1 + 2 * passes) * U + 16 * U + 12 * pairs
-        k_ms = kmer_total_ms / args.steps
+        # ---- the k-mer stages (K0-K3) and edge expansion (K6): HBM-bound; algorithmic bytes per SURVEY 8(d).
+        # Every rank packs / indexes / counts all reads (replicated) and fills ITS slice of the pair list.
+        passes = (2 * k + 7) // 8
+        kb = (wl.total_bases + wl.total_bases / 4) + 48 * U + 12 * (1 + 2 * passes) * U + 16 * U + 12 * pairs_rank_max
+        k_ms = kmer_total_ms / steps
+        o_ms = off_total_ms / steps
+        hbm = pk.get("hbm_gbs")
+        k6_bytes = 16 * pairs_rank_max + 16 * (n_edges / world)
         kmer = {"algorithmic_bytes_k0_k3": int(kb), "ms": k_ms,
-                "k0_k3_gbs": kb / (k_ms * 1e-3) / 1e9,
-                "hbm_peak_gbs": pk.get("hbm_gbs"), "k0_k3_frac": kb / (k_ms * 1e-3) / 1e9 / pk.get("hbm_gbs"),
-                "note": "pack + keys + radix index + join (count, scan, fill), timed with CUDA events inside the step; "
-                        "includes one host round trip for the pair count; K6 is fused into the DP epilogue"}
+                "k0_k3_gbs": kb / (k_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm,
+                "k0_k3_frac": kb / (k_ms * 1e-3) / 1e9 / hbm,
+                "k6": {"edge_offset_stage_ms": o_ms, "algorithmic_bytes": int(k6_bytes),
+                       "note": "the edge rows are written by the DP epilogue (their time is inside dp_ms); "
+                               "edge_offset_stage_ms is what precedes the DP when reads have copies"},
+                "k0_k3_plus_k6_offsets_frac": kb / ((k_ms + o_ms) * 1e-3) / 1e9 / hbm,
+                "per_rank": world > 1,
+                "note": "pack + keys + index + join (count, scan, fill), timed with CUDA events inside the step; "
+                        "includes the host round trip for the pair count"}
         # ---- CPU baseline on this box's host cores (bounded sample)
-        cpu = None
-        if not args.no_cpu_baseline and world == 1:
+        cpu = numba = None
+        if with_cpu and world == 1 and pairs > 0:
             # a bounded random sample of the SAME candidate list the GPU just processed
             rs_, pa_, pb_, _, _ = device_step()
             n_s = min(pairs, 4_000_000)
             idx = torch.randperm(pairs, device=dev)[:n_s] if pairs > n_s else torch.arange(pairs, device=dev)
             pa_h, pb_h = pa_[idx].cpu().numpy(), pb_[idx].cpu().numpy()
             del rs_, pa_, pb_, idx
-            cpu = cpu_arm(ub, uo, pa_h, pb_h, target_s=args.cpu_seconds, total_pairs=pairs)
-            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "int16x2" if plan["mode"] == "packed16" else "int32",
-                "data": "synthetic",
-                "config": {"workload": args.workload, "k": args.k, "seed": args.seed, "reads": n_reads,
-                           "unique_reads": U, "max_read_len": max_len, "candidate_pairs": pairs, "edges": n_edges,
-                           "cells": cells, "edge_checksum": checksum, "sharding": f"pair-range x{world}", "exchange": exchange,
-                           "l2": "flushed between timed iterations (256 MiB memset)",
-                           "scoring": "match 10, mismatch -1, indel -2^31 (reference defaults)"},
-                "pairs_per_s": pairs / (kmer_total_ms / args.steps * 1e-3),
-                "stage_ms": {"kmer_index_join": kmer_total_ms / args.steps, "overlap_dp_fused_expand": dp_total_ms / args.steps,
-                             "edge_count_scan_and_gather": ms_per_step - (kmer_total_ms + dp_total_ms) / args.steps},
+            cpu = cpu_arm(wl.ub, wl.uo, pa_h, pb_h, target_s=cpu_seconds, total_pairs=pairs)
+            cpu = {kk: cpu[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+            numba = numba_reference_sample(wl, pa_h[:4000], pb_h[:4000], seconds=min(cpu_seconds, 8.0))
+        config = wl.shared_config(pairs)            # identical keys and values in the reference arm's line
+        stats = {"edges": n_edges, "cells": cells, "edge_list_hash": f"{edge_hash:016x}",
+                 "sharding": f"pair-range x{world}", "exchange": exchange}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "int16x2" if packed else "int32", "data": "synthetic",
+                "config": config, "workload_stats": stats,
+                "pairs_per_s": pairs_rank_max / (k_ms * 1e-3) * world,
+                "stage_ms": {"kmer_index_join": k_ms, "edge_offsets": o_ms, "overlap_dp_fused_expand": dp_ms_avg,
+                             "exchange_and_rest": ms_per_step - k_ms - o_ms - dp_ms_avg},
                 "kmer_stages": kmer,
                 "e2e": {"value": cells / (e2e_per_step * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_per_step,
                         "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
-                        "checksum_matches_device_path": e2e_ok,
+                        "edge_list_hash_matches_device_path": e2e_ok,
                         "path": "engine.overlap_edges: pinned host reads in, host edge rows out, D2H overlapped with the DP"
                                 + ("; each rank writes its slice into one shared page-locked host buffer" if world > 1 else "")},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        if numba is not None:
+            line["cpu_baseline_numba"] = numba
     if world > 1:
         sink.close()
         dist.barrier()
-        dist.destroy_process_group()
+    return line
+
+
+# --------------------------------------------------------------------------------------- the other configs
+def _brief(line):
+    """The part of a measured line that configs_extra keeps."""
+    r = line["roofline"]
+    return {"value": line["value"], "unit": UNIT, "ms_per_step": line["ms_per_step"], "steps": line["steps"],
+            "warmup": line["warmup"], "dtype": line["dtype"],
+            "config": {**{kk: line["config"][kk] for kk in ("workload", "k", "reads", "unique_reads", "max_read_len",
+                                                            "candidate_pairs")},
+                       **{kk: line["workload_stats"][kk] for kk in ("edges", "cells", "edge_list_hash")}},
+            "e2e": {kk: line["e2e"][kk] for kk in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step",
+                                                   "edge_list_hash_matches_device_path")},
+            "stage_ms": line["stage_ms"],
+            "k0_k3_frac": line["kmer_stages"]["k0_k3_frac"],
+            "roofline": {kk: r[kk] for kk in ("kernel", "bound", "achieved", "peak", "unit", "frac", "dp_gcups", "dp_ms")},
+            "cpu_baseline": line["cpu_baseline"], "gpu_launches": line["gpu_launches"]}
+
+
+def dropin_wall(env, wl, reps=3):
+    """The true drop-in call: list[str] -> (nx.DiGraph, read_copies), wall clock (host dedup, H2D, kernels,
+    D2H, NetworkX construction)."""
+    synth = importlib.import_module(PKG + ".synth")
+    og = importlib.import_module(PKG + ".overlapGraphs")
+    bases, offsets = synth.make_workload(wl.name, wl.seed)
+    reads = synth.to_strings(bases, offsets)
+    og.construct_overlap_graph_nx_k(reads, k=wl.k)                    # warm-up
+    ts = []
+    G = None
+    for _ in range(reps):
+        env.torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        G, rc = og.construct_overlap_graph_nx_k(reads, k=wl.k)
+        ts.append(time.perf_counter() - t0)
+    return {"call": "construct_overlap_graph_nx_k(list[str], k) -> (nx.DiGraph, read_copies)",
+            "wall_ms": min(ts) * 1e3, "wall_ms_median": statistics.median(ts) * 1e3, "reps": reps,
+            "nodes": G.number_of_nodes(), "edges": G.number_of_edges()}
+
+
+def sweep_sets(iterations, seed0=1000):
+    """The experiments.py:49-53 grid (N x l x p), `iterations` read sets per point, on the PhiX-like genome."""
+    synth = importlib.import_module(PKG + ".synth")
+    g = synth.phix_like_genome()
+    sets, meta = [], []
+    i = 0
+    for it in range(iterations):
+        for n in (100, 316, 1000, 3162, 10000):
+            for l in (50, 100, 150):
+                for p in (0.001, 0.01, 0.1):
+                    b, o = synth.simulate_reads(g, n, l, p, seed=seed0 + i)
+                    i += 1
+                    sets.append(synth.to_strings(b, o))
+                    meta.append((n, l, p, it))
+    return sets, meta
+
+
+def _sweep_cpu_worker(job):
+    from oracle import overlap_oracle as orc
+    reads, k = job
+    if reads is None:                       # pool warm-up: load the oracle library in this worker
+        orc.overlap_alignment("ACGT", "CGTA")
+        return 0
+    nodes, edges, rc = orc.construct_overlap_graph(reads, k, nthreads=1, full=True)
+    return len(edges)
+
+
+def sweep_extra(env, iterations=10, cpu_seconds=20.0):
+    """BASELINE.json configs[4]: every graph build of the reference's parameter sweep (experiments.py:49-53:
+    N x l x p x k x 10 iterations) as ONE batched GPU job per k, against the CPU port run the reference's way --
+    one process per core over the parameter sets (experiments.py:537)."""
+    import multiprocessing as mp
+    og = importlib.import_module(PKG + ".overlapGraphs")
+    torch = env.torch
+    sets, meta = sweep_sets(iterations)
+    n_reads = sum(len(s) for s in sets)
+    out = {"grid": "N in {100,316,1000,3162,10000} x l in {50,100,150} x p in {0.001,0.01,0.1} x k in {5,10,15} "
+                   f"x {iterations} iterations (experiments.py:49-53), PhiX-like genome",
+           "read_sets_per_k": len(sets), "reads_per_k": n_reads, "per_k": {}}
+    one_iter = [s for s, m in zip(sets, meta) if m[3] == 0]
+    cores = os.cpu_count() or 1
+    total_gpu_s = total_graph_s = 0.0
+    cpu_s_one_iter = 0.0
+    # worker processes are spawned (CUDA and OpenMP state must not be forked) and warmed before any clock starts
+    pool = mp.get_context("spawn").Pool(cores)
+    pool.map(_sweep_cpu_worker, [(None, 0)] * (4 * cores), chunksize=1)
+    for k in (5, 10, 15):
+        og.overlap_edge_rows_batch(sets[:8], k)                        # warm-up
+        launches0 = env.eng.launches
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rows = og.overlap_edge_rows_batch(sets, k)                     # list[str] sets in, host edge rows per set out
+        torch.cuda.synchronize()
+        t_rows = time.perf_counter() - t0
+        launches = env.eng.launches - launches0
+        n_edges = int(sum(r[3].shape[0] for r in rows))
+        del rows
+        t0 = time.perf_counter()
+        graphs = og.construct_overlap_graphs_batch(one_iter, k)        # the full drop-in result for one iteration
+        t_graph = time.perf_counter() - t0
+        g_edges = int(sum(g.number_of_edges() for g, _ in graphs))
+        del graphs
+        # CPU arm: the oracle builder, one process per core over the sets of ONE iteration (bounded sample)
+        jobs = sorted(((s, k) for s in one_iter), key=lambda j: -len(j[0]))     # largest first: balanced tail
+        t0 = time.perf_counter()
+        cpu_edges = sum(pool.imap_unordered(_sweep_cpu_worker, jobs, chunksize=1))
+        t_cpu = time.perf_counter() - t0
+        assert cpu_edges == g_edges, (cpu_edges, g_edges)
+        out["per_k"][str(k)] = {"gpu_edge_rows_all_sets_s": t_rows, "edges_all_sets": n_edges, "gpu_launches": int(launches),
+                                "gpu_graphs_one_iteration_s": t_graph, "edges_one_iteration": g_edges,
+                                "cpu_port_one_iteration_s": t_cpu}
+        total_gpu_s += t_rows
+        total_graph_s += t_graph
+        cpu_s_one_iter += t_cpu
+    pool.close()
+    pool.join()
+    out["gpu_job_s"] = total_gpu_s
+    out["gpu_job_note"] = ("construct-ready host edge rows for all read sets of the sweep (3 batched jobs, one per k): host "
+                          "dedup + H2D + kernels + D2H, wall clock")
+    out["gpu_graphs_one_iteration_s"] = total_graph_s
+    out["cpu_baseline"] = {"value": cpu_s_one_iter * iterations, "unit": "s (extrapolated: measured one iteration x "
+                           f"{iterations})", "measured_one_iteration_s": cpu_s_one_iter, "cores": cores, "kind": "port",
+                           "sample": "oracle construct_overlap_graph (C DP, full matrices + traceback) over the "
+                                     f"{len(one_iter)} read sets of one iteration per k, one process per core (spawned pool, warm), "
+                                     "edge count checked against the GPU graphs"}
+    return out
+
+
+def configs_extra(env, args):
+    extra = {}
+    t_all = time.perf_counter()
+    plan = [("configs[0]", "phix_n1000_l100", 5, 5, 3, 3.0, True),
+            ("configs[1]", "phix_n50000_l150", 5, 5, 3, 5.0, True),
+            ("configs[3]_k8", "ecoli_n200k_l1000", 8, 3, 3, 5.0, False),
+            ("configs[3]_k5", "ecoli_n200k_l1000", 5, 2, 3, 6.0, False)]
+    for key, name, k, steps, warmup, cpu_s, dropin in plan:
+        t0 = time.perf_counter()
+        try:
+            wl = Workload(name, args.seed, k)
+            line = measure(env, wl, steps, warmup, cpu_s, sample_clocks=False)
+            ent = _brief(line)
+            if dropin:
+                ent["dropin"] = dropin_wall(env, wl)
+                if key == "configs[0]":
+                    ent["dropin"]["reference_numba_s"] = 1.29      # BASELINE.md section 2 (survey container, 1 core)
+            if "cpu_baseline_numba" in line:
+                ent["cpu_baseline_numba"] = line["cpu_baseline_numba"]
+            ent["bench_seconds"] = time.perf_counter() - t0
+            extra[key] = ent
+            del wl
+        except Exception as exc:                           # noqa: BLE001  -- an extra must never lose the headline line
+            extra[key] = {"error": f"{type(exc).__name__}: {exc}"}
+        env.torch.cuda.empty_cache()
+    try:
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            extra["configs[4]_sweep"] = sweep_extra(env, iterations=args.sweep_iterations)
+        extra["configs[4]_sweep"]["bench_seconds"] = time.perf_counter() - t0
+    except Exception as exc:                               # noqa: BLE001
+        extra["configs[4]_sweep"] = {"error": f"{type(exc).__name__}: {exc}"}
+    extra["bench_seconds"] = time.perf_counter() - t_all
+    return extra
+
+
+def run_ours(args):
+    env = Env()
+    wl = Workload(args.workload, args.seed, args.k)
+    line = measure(env, wl, args.steps, args.warmup, args.cpu_seconds, use_peer=not args.no_peer_stores,
+                   with_cpu=not args.no_cpu_baseline)
+    del wl
+    if env.rank == 0 and env.world == 1 and not args.no_extras:
+        env.torch.cuda.empty_cache()
+        line["configs_extra"] = configs_extra(env, args)
+    if env.rank == 0:
+        print(json.dumps(line), flush=True)
+    if env.world > 1:
+        env.dist.barrier()
+        env.dist.destroy_process_group()
 
 
 def main():
@@ -479,12 +750,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     # BASELINE.json quotes the metric "at 1/2/4/8 B200" on configs[2] (4.6 Mb genome, 1M reads, l=150,
     # p=0.005, sharded by read-ID range); it fits one GPU (~32 GB), so it is the workload at every N.
-    # configs[1] is --workload phix_n50000_l150 (numbers in DESIGN.md).
+    # The other configs are measured in the same run into `configs_extra` (N = 1).
     ap.add_argument("--workload", default="ecoli_n1m_l150")
     ap.add_argument("--k", type=int, default=5)
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip configs_extra (the other BASELINE configs)")
+    ap.add_argument("--sweep-iterations", type=int, default=10)
     ap.add_argument("--no-peer-stores", action="store_true", help="N>1: gather with NCCL instead of peer-memory stores")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -28,6 +28,11 @@ class OvlUnsupported(OvlError, NotImplementedError):
     """Valid input for the reference that the CUDA kernels do not cover."""
 
 
+class OvlBadAlphabet(OvlUnsupported):
+    """The 2-bit packed kernels were handed reads with symbols other than A, C, G, T (the graph
+    builder catches this and re-letters or byte-codes the read set)."""
+
+
 if not os.path.isfile(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -83,6 +88,7 @@ _SIGS = {
     "ovl_align_pair": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp, _vp, _vp]),
     "ovl_local_align_workspace_bytes": (_sz, [_i32, _i32]),
     "ovl_local_align": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp, _vp, _vp]),
+    "ovl_edge_list_hash": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "ovl_int_peak_probe": (ctypes.c_int, [_vp, _i32, _i32, ctypes.POINTER(ctypes.c_double),
                                           ctypes.POINTER(ctypes.c_double)]),
 }

@@ -3,8 +3,8 @@
 Same name, same keyword arguments, same 5-tuple; the DP, the last-row arg-max and the
 traceback run on the GPU (kernel K7, csrc/align.cuh) -- there is no CPU fallback.
 Every other symbol of the reference's ``aligners`` module (local_alignment, ...) is outside
-the accelerated path and is forwarded to the reference module when its checkout is present
-(``OVL_REFERENCE_DIR``, default /root/reference).
+the accelerated path and is forwarded to the reference module when ``OVL_REFERENCE_DIR`` names
+its checkout (opt-in).
 """
 from __future__ import annotations
 
@@ -106,6 +106,8 @@ def align_read_or_contig_to_reference(read_or_contig, reference_genome, read_len
 
 
 def __getattr__(name):
+    if name.startswith("__") and name.endswith("__"):
+        raise AttributeError(name)
     ref = _engine.reference_module("aligners")
     if ref is not None and hasattr(ref, name):
         return getattr(ref, name)

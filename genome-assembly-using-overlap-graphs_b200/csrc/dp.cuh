@@ -208,7 +208,10 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : OVL_DP_MINB)) overla
         srow[h] = grp_rows + (size_t)(2 * h) * row_words;
         trow[h] = grp_rows + (size_t)(2 * h + 1) * row_words;
     }
-    while (!mbar_try_wait(bar, 0)) { }                      // the rows have landed (phase 0 completes once)
+    // the rows have landed (phase 0 completes once); a copy that never completes (bad pointer) traps
+    // instead of hanging the GPU
+    for (uint32_t spins = 0; !mbar_try_wait(bar, 0); )
+        if (++spins > (1u << 20)) __trap();
     const int nmax = PK ? max(n[0], n[PAIRS - 1]) : n[0];
     const int max_col = row_words * (BITS == 2 ? 16 : 4) - 1;
 

@@ -13,6 +13,7 @@
 #include "dp.cuh"
 #include "probe.cuh"
 #include "align.cuh"
+#include "check.cuh"
 
 using namespace ovl;
 
@@ -49,6 +50,21 @@ static int fail(int code, const char* fmt, ...) {
             return fail(OVL_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
     } while (0)
 
+// Every entry point that takes a context runs on the context's device and leaves the calling
+// thread's current device as it found it (PyTorch owns that state).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(const ovl_ctx* ctx) {
+        if (ctx && cudaGetDevice(&prev) == cudaSuccess && prev != ctx->device)
+            switched = cudaSetDevice(ctx->device) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define ON_CTX_DEVICE(ctx) DeviceGuard device_guard__(ctx)
+
 static inline unsigned grid_for(int64_t n, int per_block) {
     int64_t g = (n + per_block - 1) / per_block;
     return (unsigned)(g > 0 ? g : 1);
@@ -64,11 +80,10 @@ int ovl_ctx_create(int device, ovl_ctx** out) {
     int count = 0;
     CUDA_TRY(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count) return fail(OVL_E_ARG, "ovl_ctx_create: no CUDA device %d (have %d)", device, count);
-    CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10)
-        return fail(OVL_E_UNSUPPORTED, "ovl_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));       // does not change the current device
+    if (prop.major != 10)
+        return fail(OVL_E_UNSUPPORTED, "ovl_ctx_create: device %d is sm_%d%d; this library holds sm_100a code only",
                     device, prop.major, prop.minor);
     ovl_ctx* c = new ovl_ctx();
     c->device = device;
@@ -81,6 +96,7 @@ int ovl_ctx_create(int device, ovl_ctx** out) {
 
 int ovl_ctx_destroy(ovl_ctx* ctx) {
     if (!ctx) return OVL_OK;
+    ON_CTX_DEVICE(ctx);
     if (ctx->probe_sink) cudaFree(ctx->probe_sink);
     delete ctx;
     return OVL_OK;
@@ -98,6 +114,7 @@ int32_t ovl_row_words(int32_t max_len) {
 // ---------------------------------------------------------------- K0 / K1
 int ovl_pack_reads(ovl_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int64_t U, int32_t row_words,
                    uint32_t* packed, int32_t* len, int32_t* bad_count, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !ascii || !offsets || !packed || !len || !bad_count) return fail(OVL_E_ARG, "ovl_pack_reads: null argument");
     if (U <= 0) return OVL_OK;
     if (row_words < 4 || (row_words & 3)) return fail(OVL_E_ARG, "ovl_pack_reads: row_words must be a positive multiple of 4");
@@ -110,6 +127,7 @@ int ovl_pack_reads(ovl_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, i
 
 int ovl_kmer_keys(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, int64_t U, int32_t k,
                   const int32_t* segment, uint64_t* prefix_key, uint64_t* suffix_key, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !packed || !len || !prefix_key || !suffix_key) return fail(OVL_E_ARG, "ovl_kmer_keys: null argument");
     if (k < 1 || k > OVL_MAX_K) return fail(OVL_E_UNSUPPORTED, "ovl_kmer_keys: k=%d outside 1..%d", k, OVL_MAX_K);
     if (U <= 0) return OVL_OK;
@@ -121,6 +139,7 @@ int ovl_kmer_keys(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const
 
 int ovl_kmer_hashes(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, int64_t U, int32_t k,
                     uint64_t* prefix_key, uint64_t* suffix_key, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !packed || !len || !prefix_key || !suffix_key) return fail(OVL_E_ARG, "ovl_kmer_hashes: null argument");
     if (k < 1) return fail(OVL_E_ARG, "ovl_kmer_hashes: k must be positive");
     if (U <= 0) return OVL_OK;
@@ -146,6 +165,7 @@ size_t ovl_index_workspace_bytes(int64_t U) {
 
 int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len, int64_t U, int32_t k, int32_t key_bits, uint64_t* sorted_key,
                     uint32_t* sorted_uid, int64_t* n_indexed, void* workspace, size_t workspace_bytes, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !prefix_key || !len || !sorted_key || !sorted_uid || !n_indexed || !workspace) return fail(OVL_E_ARG, "ovl_index_build: null argument");
     if (k < 1) return fail(OVL_E_ARG, "ovl_index_build: k must be positive");
     if (k > OVL_MAX_K && key_bits != 64) return fail(OVL_E_ARG, "ovl_index_build: k=%d > %d needs hashed keys (key_bits = 64)", k, OVL_MAX_K);
@@ -206,6 +226,7 @@ int ovl_join_count(ovl_ctx* ctx, const uint64_t* suffix_key, const uint64_t* pre
                    int64_t a_begin, int64_t a_end,
                    const uint64_t* sorted_key, const uint32_t* sorted_uid, const int64_t* n_indexed, int32_t* bucket_lo,
                    int32_t* self_rank, int64_t* pair_off, void* workspace, size_t workspace_bytes, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !suffix_key || !prefix_key || !len || !sorted_key || !sorted_uid || !n_indexed || !bucket_lo || !self_rank || !pair_off || !workspace)
         return fail(OVL_E_ARG, "ovl_join_count: null argument");
     int64_t nA = a_end - a_begin;
@@ -229,6 +250,7 @@ int ovl_join_count(ovl_ctx* ctx, const uint64_t* suffix_key, const uint64_t* pre
 int ovl_join_fill(ovl_ctx* ctx, const int64_t* pair_off, int64_t a_begin, int64_t a_end, const int32_t* bucket_lo,
                   const int32_t* self_rank, const uint32_t* sorted_uid, int64_t p_begin, int64_t p_count, int64_t total_hint,
                   int32_t* pair_a, int32_t* pair_b, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !pair_off || !bucket_lo || !self_rank || !sorted_uid || !pair_a || !pair_b) return fail(OVL_E_ARG, "ovl_join_fill: null argument");
     if (p_count <= 0) return OVL_OK;
     int64_t nA = a_end - a_begin;
@@ -249,6 +271,7 @@ int ovl_join_count_verify(ovl_ctx* ctx, const uint32_t* packed, int32_t row_word
                           const uint64_t* suffix_hash, int64_t a_begin, int64_t a_end, const uint64_t* sorted_hash,
                           const uint32_t* sorted_uid, const int64_t* n_indexed, int64_t* pair_off, void* workspace,
                           size_t workspace_bytes, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !packed || !len || !suffix_hash || !sorted_hash || !sorted_uid || !n_indexed || !pair_off || !workspace)
         return fail(OVL_E_ARG, "ovl_join_count_verify: null argument");
     int64_t nA = a_end - a_begin;
@@ -273,6 +296,7 @@ int ovl_join_fill_verify(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words
                          const uint64_t* suffix_hash, int64_t a_begin, int64_t a_end, const uint64_t* sorted_hash,
                          const uint32_t* sorted_uid, const int64_t* n_indexed, const int64_t* pair_off, int64_t p_begin,
                          int64_t p_count, int32_t* pair_a, int32_t* pair_b, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !packed || !len || !suffix_hash || !sorted_hash || !sorted_uid || !n_indexed || !pair_off || !pair_a || !pair_b)
         return fail(OVL_E_ARG, "ovl_join_fill_verify: null argument");
     int64_t nA = a_end - a_begin;
@@ -286,6 +310,7 @@ int ovl_join_fill_verify(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words
 
 int ovl_all_pairs_fill(ovl_ctx* ctx, int64_t U, int64_t a_begin, int64_t p_begin, int64_t p_count, int32_t* pair_a,
                        int32_t* pair_b, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !pair_a || !pair_b) return fail(OVL_E_ARG, "ovl_all_pairs_fill: null argument");
     if (p_count <= 0) return OVL_OK;
     if (U < 2) return fail(OVL_E_ARG, "ovl_all_pairs_fill: need at least two reads");
@@ -497,6 +522,7 @@ extern "C" {
 int ovl_overlap_dp(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, const int32_t* pair_a,
                    const int32_t* pair_b, int64_t P, int32_t max_len, int64_t match, int64_t mismatch, int64_t indel,
                    int32_t* score, int32_t* end, int32_t mode, int32_t group_lanes, int32_t cols_per_lane, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (P > 0 && (!score || !end)) return fail(OVL_E_ARG, "ovl_overlap_dp: null output");
     DpEdgeOut eo{nullptr, nullptr, nullptr, nullptr};
     return dp_dispatch(ctx, packed, row_words, len, pair_a, pair_b, P, max_len, match, mismatch, indel, score, end, eo,
@@ -507,6 +533,7 @@ int ovl_overlap_dp8(ovl_ctx* ctx, const uint8_t* rows, int32_t row_words, const 
                     const int32_t* pair_b, int64_t P, int32_t max_len, int64_t match, int64_t mismatch, int64_t indel,
                     int32_t* score, int32_t* end, const int32_t* copies, const int64_t* node_off, const int64_t* edge_off,
                     int32_t* edges, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (P > 0 && !edges && (!score || !end)) return fail(OVL_E_ARG, "ovl_overlap_dp8: null output");
     if ((uintptr_t)edges & 15) return fail(OVL_E_ARG, "ovl_overlap_dp8: edges must be 16-byte aligned");
     if (copies && (!node_off || !edge_off)) return fail(OVL_E_ARG, "ovl_overlap_dp8: copies given without node_off / edge_off");
@@ -519,6 +546,7 @@ int ovl_overlap_dp_edges(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words
                          const int32_t* pair_b, int64_t P, int32_t max_len, int64_t match, int64_t mismatch, int64_t indel,
                          const int32_t* copies, const int64_t* node_off, const int64_t* edge_off, int32_t* edges,
                          void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (P > 0 && !edges) return fail(OVL_E_ARG, "ovl_overlap_dp_edges: null output");
     if ((uintptr_t)edges & 15) return fail(OVL_E_ARG, "ovl_overlap_dp_edges: edges must be 16-byte aligned");
     if (copies && (!node_off || !edge_off)) return fail(OVL_E_ARG, "ovl_overlap_dp_edges: copies given without node_off / edge_off");
@@ -530,6 +558,7 @@ int ovl_overlap_dp_edges(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words
 // ---------------------------------------------------------------- byte-coded reads (any alphabet)
 int ovl_pack_bytes(ovl_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int64_t U, int32_t row_words, uint8_t* rows,
                    int32_t* len, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !ascii || !offsets || !rows || !len) return fail(OVL_E_ARG, "ovl_pack_bytes: null argument");
     if (U <= 0) return OVL_OK;
     if (row_words < 4 || (row_words & 3)) return fail(OVL_E_ARG, "ovl_pack_bytes: row_words must be a positive multiple of 4");
@@ -540,6 +569,7 @@ int ovl_pack_bytes(ovl_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, i
 
 int ovl_kmer_hashes8(ovl_ctx* ctx, const uint8_t* rows, int32_t row_words, const int32_t* len, int64_t U, int32_t k,
                      uint64_t* prefix_hash, uint64_t* suffix_hash, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !rows || !len || !prefix_hash || !suffix_hash) return fail(OVL_E_ARG, "ovl_kmer_hashes8: null argument");
     if (k < 1) return fail(OVL_E_ARG, "ovl_kmer_hashes8: k must be positive");
     if (U <= 0) return OVL_OK;
@@ -552,6 +582,7 @@ int ovl_join_count_verify8(ovl_ctx* ctx, const uint8_t* rows, int32_t row_words,
                            const uint64_t* suffix_hash, int64_t a_begin, int64_t a_end, const uint64_t* sorted_hash,
                            const uint32_t* sorted_uid, const int64_t* n_indexed, int64_t* pair_off, void* workspace,
                            size_t workspace_bytes, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !rows || !len || !suffix_hash || !sorted_hash || !sorted_uid || !n_indexed || !pair_off || !workspace)
         return fail(OVL_E_ARG, "ovl_join_count_verify8: null argument");
     int64_t nA = a_end - a_begin;
@@ -576,6 +607,7 @@ int ovl_join_fill_verify8(ovl_ctx* ctx, const uint8_t* rows, int32_t row_words, 
                           const uint64_t* suffix_hash, int64_t a_begin, int64_t a_end, const uint64_t* sorted_hash,
                           const uint32_t* sorted_uid, const int64_t* n_indexed, const int64_t* pair_off, int64_t p_begin,
                           int64_t p_count, int32_t* pair_a, int32_t* pair_b, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !rows || !len || !suffix_hash || !sorted_hash || !sorted_uid || !n_indexed || !pair_off || !pair_a || !pair_b)
         return fail(OVL_E_ARG, "ovl_join_fill_verify8: null argument");
     int64_t nA = a_end - a_begin;
@@ -595,6 +627,7 @@ size_t ovl_expand_workspace_bytes(int64_t P) {
 
 int ovl_expand_count(ovl_ctx* ctx, const int32_t* pair_a, const int32_t* pair_b, const int32_t* copies, int64_t P,
                      int64_t* edge_off, void* workspace, size_t workspace_bytes, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !edge_off || !workspace || (P > 0 && (!pair_a || !pair_b || !copies))) return fail(OVL_E_ARG, "ovl_expand_count: null argument");
     if (workspace_bytes < ovl_expand_workspace_bytes(P)) return fail(OVL_E_ARG, "ovl_expand_count: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
@@ -609,6 +642,7 @@ int ovl_expand_count(ovl_ctx* ctx, const int32_t* pair_a, const int32_t* pair_b,
 int ovl_expand_fill(ovl_ctx* ctx, const int64_t* edge_off, int64_t P, const int32_t* pair_a, const int32_t* pair_b,
                     const int32_t* score, const int32_t* end, const int32_t* copies, const int64_t* node_off,
                     int64_t e_begin, int64_t e_count, int32_t* edges, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !edge_off || !pair_a || !pair_b || !score || !end || !copies || !node_off || !edges) return fail(OVL_E_ARG, "ovl_expand_fill: null argument");
     if (e_count <= 0) return OVL_OK;
     if ((uintptr_t)edges & 15) return fail(OVL_E_ARG, "ovl_expand_fill: edges must be 16-byte aligned");
@@ -620,6 +654,7 @@ int ovl_expand_fill(ovl_ctx* ctx, const int64_t* edge_off, int64_t P, const int3
 
 int ovl_expand_unit(ovl_ctx* ctx, const int32_t* pair_a, const int32_t* pair_b, const int32_t* score, const int32_t* end,
                     int64_t P, int32_t* edges, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !pair_a || !pair_b || !score || !end || !edges) return fail(OVL_E_ARG, "ovl_expand_unit: null argument");
     if (P <= 0) return OVL_OK;
     if ((uintptr_t)edges & 15) return fail(OVL_E_ARG, "ovl_expand_unit: edges must be 16-byte aligned");
@@ -636,6 +671,7 @@ size_t ovl_filter_workspace_bytes(int64_t E) {
 
 int ovl_filter_count(ovl_ctx* ctx, const int32_t* edges, int64_t E, int32_t min_weight, int64_t* keep_off, void* workspace,
                      size_t workspace_bytes, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !keep_off || !workspace || (E > 0 && !edges)) return fail(OVL_E_ARG, "ovl_filter_count: null argument");
     if (workspace_bytes < ovl_filter_workspace_bytes(E)) return fail(OVL_E_ARG, "ovl_filter_count: workspace too small");
     void* sums = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
@@ -647,6 +683,7 @@ int ovl_filter_count(ovl_ctx* ctx, const int32_t* edges, int64_t E, int32_t min_
 
 int ovl_filter_fill(ovl_ctx* ctx, const int32_t* edges, const int64_t* keep_off, int64_t E, int32_t min_weight, int32_t* out,
                     void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || (E > 0 && (!edges || !keep_off || !out))) return fail(OVL_E_ARG, "ovl_filter_fill: null argument");
     if (E <= 0) return OVL_OK;
     filter_edges_kernel<<<grid_for(E, 256), 256, 0, (cudaStream_t)stream>>>((const int4*)edges, keep_off, E, min_weight, (int4*)out);
@@ -664,6 +701,7 @@ size_t ovl_align_pair_workspace_bytes(int32_t n, int32_t m) {
 
 int ovl_align_pair(ovl_ctx* ctx, const int32_t* s, int32_t n, const int32_t* t, int32_t m, int64_t match, int64_t mismatch,
                    int64_t indel, void* workspace, size_t workspace_bytes, int32_t* result, uint8_t* ops, void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !workspace || !result || !ops || (n > 0 && !s) || (m > 0 && !t)) return fail(OVL_E_ARG, "ovl_align_pair: null argument");
     if (n < 0 || m < 0) return fail(OVL_E_ARG, "ovl_align_pair: negative length");
     if (workspace_bytes < ovl_align_pair_workspace_bytes(n, m)) return fail(OVL_E_ARG, "ovl_align_pair: workspace too small");
@@ -695,6 +733,7 @@ size_t ovl_local_align_workspace_bytes(int32_t n, int32_t m) {
 int ovl_local_align(ovl_ctx* ctx, const int32_t* query, int32_t n, const int32_t* reference, int32_t m, int64_t match,
                     int64_t mismatch, int64_t indel, void* workspace, size_t workspace_bytes, int32_t* result, uint8_t* ops,
                     void* stream) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !workspace || !result || !ops || (n > 0 && !query) || (m > 0 && !reference)) return fail(OVL_E_ARG, "ovl_local_align: null argument");
     if (n < 0 || m < 0) return fail(OVL_E_ARG, "ovl_local_align: negative length");
     if (workspace_bytes < ovl_local_align_workspace_bytes(n, m)) return fail(OVL_E_ARG, "ovl_local_align: workspace too small");
@@ -719,6 +758,18 @@ int ovl_local_align(ovl_ctx* ctx, const int32_t* query, int32_t n, const int32_t
         local_align_kernel<false><<<1, threads, 0, (cudaStream_t)stream>>>(query, n, reference, m, match, mismatch, indel, diag, tb, result, ops);
     }
     LAUNCH_CHECK("local_align_kernel");
+    return OVL_OK;
+}
+
+// ---------------------------------------------------------------- edge-list fingerprint
+int ovl_edge_list_hash(ovl_ctx* ctx, const int32_t* edges, int64_t E, int64_t first_row, uint64_t* accum, void* stream) {
+    ON_CTX_DEVICE(ctx);
+    if (!ctx || !accum || (E > 0 && !edges)) return fail(OVL_E_ARG, "ovl_edge_list_hash: null argument");
+    if (E <= 0) return OVL_OK;
+    if ((uintptr_t)edges & 15) return fail(OVL_E_ARG, "ovl_edge_list_hash: edges must be 16-byte aligned");
+    unsigned grid = (unsigned)std::min<int64_t>((E + 255) / 256, (int64_t)ctx->sm_count * 16);
+    edge_hash_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const int4*)edges, E, first_row, (unsigned long long*)accum);
+    LAUNCH_CHECK("edge_hash_kernel");
     return OVL_OK;
 }
 
@@ -751,6 +802,7 @@ static int run_probe(ovl_ctx* ctx, int iters, double* gops, double* ms_out) {
 extern "C" {
 
 int ovl_int_peak_probe(ovl_ctx* ctx, int32_t kind, int32_t iters, double* h_gops, double* h_ms) {
+    ON_CTX_DEVICE(ctx);
     if (!ctx || !h_gops) return fail(OVL_E_ARG, "ovl_int_peak_probe: null argument");
     if (iters < 1) iters = 1;
     switch (kind) {

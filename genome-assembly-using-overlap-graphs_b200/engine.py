@@ -9,6 +9,7 @@ expansion).  PyTorch is used for device buffers, streams and host<->device copie
 from __future__ import annotations
 
 import ctypes
+import threading
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -60,6 +61,9 @@ class OverlapEngine:
         self.sm_count = int(nat.lib.ovl_ctx_sm_count(ctx))
         self._total_mem = int(torch.cuda.get_device_properties(self.device).total_memory)
         self._pinned_out = None    # reusable pinned host buffer for edge rows (D2H at full PCIe rate)
+        # one engine per device is shared by the whole process and hands out views of ONE pinned result
+        # buffer: callers that consume such a view (the graph builders) hold this lock while they do
+        self.lock = threading.RLock()
 
     @property
     def launches(self) -> int:
@@ -145,9 +149,19 @@ class OverlapEngine:
     def check_alphabet(self, rs: ReadSet) -> None:
         """The reference compares arbitrary characters; the 2-bit kernels cover A/C/G/T only
         and refuse anything else instead of mis-scoring it (host sync)."""
-        if int(rs.bad.item()) != 0:
-            raise nat.OvlUnsupported("reads contain characters other than A, C, G, T; "
+        if rs.code_bits == 2 and int(rs.bad.item()) != 0:
+            raise nat.OvlBadAlphabet("reads contain characters other than A, C, G, T; "
                                      "the 2-bit CUDA path does not support them")
+
+    def _total_and_alphabet(self, rs: ReadSet, total_dev: torch.Tensor) -> int:
+        """ONE host sync for the two scalars the host needs before it can size the pair list: the pair
+        count, and whether the 2-bit packing met a symbol it cannot code (then nothing downstream of
+        the mis-coded rows is allocated or run)."""
+        both = torch.stack((total_dev.reshape(()).to(torch.int64), rs.bad.reshape(()).to(torch.int64))).cpu()
+        if rs.code_bits == 2 and int(both[1]) != 0:
+            raise nat.OvlBadAlphabet("reads contain characters other than A, C, G, T; "
+                                     "the 2-bit CUDA path does not support them")
+        return int(both[0])
 
     # ------------------------------------------------------------------ K1 + K2
     def kmer_index(self, rs: ReadSet, k: int, segments: Optional[torch.Tensor] = None,
@@ -208,6 +222,7 @@ class OverlapEngine:
         rank, world = shard
         st = self._stream()
         if k == 0:
+            self.check_alphabet(rs)                            # before U*(U-1) pairs are sized
             total = U * (U - 1) if U > 1 else 0
             p_begin, p_end = total * rank // world, total * (rank + 1) // world
             P = p_end - p_begin
@@ -229,7 +244,7 @@ class OverlapEngine:
                                          _ptr(rs.length), k, 0, U,
                                          _ptr(index.sorted_key), _ptr(index.sorted_uid), _ptr(index.n_indexed),
                                          _ptr(lo), _ptr(self_rank), _ptr(pair_off), _ptr(ws), ws_bytes, st))
-        total = int(pair_off[U].item())                      # host sync: the output size
+        total = self._total_and_alphabet(rs, pair_off[U])    # host sync: the output size
         p_begin, p_end = total * rank // world, total * (rank + 1) // world
         P = p_end - p_begin
         self._check_fits(P, f"k = {k}")
@@ -254,7 +269,7 @@ class OverlapEngine:
                                                 _ptr(index.suffix_key), 0, U, _ptr(index.sorted_key),
                                                 _ptr(index.sorted_uid), _ptr(index.n_indexed), _ptr(pair_off),
                                                 _ptr(ws), ws_bytes, st))
-        total = int(pair_off[U].item())
+        total = self._total_and_alphabet(rs, pair_off[U])
         p_begin, p_end = total * rank // world, total * (rank + 1) // world
         P = p_end - p_begin
         self._check_fits(P, f"k = {k}")
@@ -496,6 +511,41 @@ class OverlapEngine:
         nat.check(nat.lib.ovl_filter_fill(self._ctx, _ptr(edges), _ptr(keep_off), E, int(min_weight), _ptr(out), st))
         return out[:kept * 4].view(kept, 4)
 
+    # ------------------------------------------------------------------ edge-list fingerprint
+    def edge_hash(self, edges: torch.Tensor, first_row: int = 0, accum: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Order-sensitive fingerprint of device edge rows (csrc/check.cuh): returns the int64[1] device
+        accumulator (bit pattern of the u64 sum); shards hashed with their global `first_row` add up."""
+        if accum is None:
+            accum = torch.zeros(1, dtype=torch.int64, device=self.device)
+        E = int(edges.shape[0])
+        if E:
+            nat.check(nat.lib.ovl_edge_list_hash(self._ctx, _ptr(edges), E, int(first_row), _ptr(accum), self._stream()))
+        return accum
+
+    def edge_hash_host(self, rows: np.ndarray, first_row: int = 0, chunk_rows: int = 1 << 25) -> int:
+        """The same fingerprint of HOST edge rows: uploaded chunk by chunk and hashed by the same kernel."""
+        accum = torch.zeros(1, dtype=torch.int64, device=self.device)
+        E = int(rows.shape[0])
+        for r0 in range(0, E, chunk_rows):
+            part = self._from_numpy(rows[r0:r0 + chunk_rows]).to(self.device, non_blocking=True)
+            self.edge_hash(part, first_row + r0, accum)
+        return int(accum.item()) & 0xFFFFFFFFFFFFFFFF
+
+    @staticmethod
+    def edge_hash_numpy(rows: np.ndarray, first_row: int = 0) -> int:
+        """Host mirror of csrc/check.cuh (wrapping u64 arithmetic), for tests and small lists."""
+        r = np.ascontiguousarray(rows, dtype=np.int32).view(np.uint32).astype(np.uint64)
+        n = r.shape[0]
+        with np.errstate(over="ignore"):
+            z = (np.arange(n, dtype=np.uint64) + np.uint64(first_row)) * np.uint64(0x9E3779B97F4A7C15) \
+                + np.uint64(0x632BE59BD9B4E019)
+            z ^= r[:, 0] | (r[:, 1] << np.uint64(32))
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z ^= r[:, 2] | (r[:, 3] << np.uint64(32))
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z ^= z >> np.uint64(31)
+            return int(z.sum(dtype=np.uint64))
+
     # ------------------------------------------------------------------ whole path
     def overlap_edges_device(self, rs: ReadSet, k: int, copies: Optional[torch.Tensor] = None,
                              node_off: Optional[torch.Tensor] = None, shard: Tuple[int, int] = (0, 1),
@@ -545,6 +595,7 @@ class OverlapEngine:
                 copies = self._to_device(counts_np, torch.int32)
                 node_off = self._to_device(no, torch.int64)
         if pairs is not None:        # caller-supplied unique-read index pairs instead of the k-mer join
+            self.check_alphabet(rs)
             pa = self._to_device(pairs[0], torch.int32)
             pb = self._to_device(pairs[1], torch.int32)
             edges = self.overlap_edges_fused(rs, pa, pb, copies, node_off, match_score, mismatch, indel)
@@ -556,7 +607,6 @@ class OverlapEngine:
                                                     host_sink=host_sink)
             if stats is not None:
                 stats["pairs"], stats["edges"] = int(pa.shape[0]), int(host.shape[0])
-            self.check_alphabet(rs)
             return host if (reuse_host_buffer or host_sink is not None) else host.copy()
         else:
             seg_dev = self._to_device(segments, torch.int32) if segments is not None else None
@@ -564,7 +614,6 @@ class OverlapEngine:
                                               seg_dev, n_segments)
         if min_weight is not None:
             edges = self.filter_edges(edges, min_weight)
-        self.check_alphabet(rs)
         if not to_host:
             return edges
         host = self.to_pinned_host(edges)
@@ -591,25 +640,34 @@ _REF_MODULES = {}
 
 
 def reference_module(name: str):
-    """The reference's own module `name` (for the symbols outside the accelerated path), or
-    None when no checkout is available.  The reference's functions that call the builder look
-    it up in their module globals (overlapGraphs.py:167), so the forwarded module gets the
-    GPU builder / aligner patched in."""
+    """The reference's own module `name` (for the symbols outside the accelerated path), or None.
+
+    Forwarding is opt-in: it happens only when ``OVL_REFERENCE_DIR`` names a checkout of the
+    reference.  The reference's functions that call the builder look it up in their module globals
+    (overlapGraphs.py:167), so the forwarded module gets the GPU builder / aligner patched in.
+    Optional imports of the reference that are not on the accelerated path (Bio, matplotlib) are
+    stubbed only while the module executes; sys.modules is left as it was found."""
     import importlib.util
     import os
     import sys
     from unittest.mock import MagicMock
     if name in _REF_MODULES:
         return _REF_MODULES[name]
-    ref_dir = os.environ.get("OVL_REFERENCE_DIR", "/root/reference")
+    ref_dir = os.environ.get("OVL_REFERENCE_DIR")
+    if not ref_dir:
+        return None
     path = os.path.join(ref_dir, name + ".py")
     mod = None
     if os.path.isfile(path):
+        stubbed = []
         for m in ("Bio", "Bio.Align", "matplotlib", "matplotlib.pyplot"):   # not on the hot path, may be absent
+            if m in sys.modules:
+                continue
             try:
                 __import__(m)
             except Exception:
-                sys.modules.setdefault(m, MagicMock())
+                sys.modules[m] = MagicMock()
+                stubbed.append(m)
         spec = importlib.util.spec_from_file_location(f"_ovl_reference_{name}", path)
         mod = importlib.util.module_from_spec(spec)
         saved_path = list(sys.path)
@@ -617,12 +675,16 @@ def reference_module(name: str):
         sys.path.insert(0, ref_dir)
         try:
             spec.loader.exec_module(mod)
+        except ImportError:
+            mod = None                          # e.g. numba missing: the caller turns this into AttributeError
         finally:
             sys.path[:] = saved_path
             for m, was in had.items():          # do not leave the reference registered under
                 if not was:                     # the drop-in's module names
                     sys.modules.pop(m, None)
-        if name == "overlapGraphs":
+            for m in stubbed:                   # a later `import matplotlib` must not get a mock
+                sys.modules.pop(m, None)
+        if mod is not None and name == "overlapGraphs":
             from . import overlapGraphs as dropin
             from . import aligners as dropin_al
             mod.construct_overlap_graph_nx_k = dropin.construct_overlap_graph_nx_k

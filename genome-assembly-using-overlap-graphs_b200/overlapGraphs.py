@@ -6,8 +6,13 @@ What stays on the host is what the return value itself is made of: the ``read_co
 (overlapGraphs.py:18-20), the node-name strings and the NetworkX container.  The prefix
 index, the candidate lookup, the overlap DP and the copy x copy edge expansion
 (overlapGraphs.py:30-60) run on the GPU.  Other symbols of the reference module
-(assemble_contigs_using_overlap_graphs, ...) are forwarded to the reference checkout when it
-is present; they call this builder through the module global, as in overlapGraphs.py:167.
+(assemble_contigs_using_overlap_graphs, ...) are forwarded to the reference checkout named by
+``OVL_REFERENCE_DIR`` (opt-in); they call this builder through the module global, as in
+overlapGraphs.py:167.
+
+Thread safety: the process-wide engine hands out views of one pinned result buffer, so the
+builders hold ``engine.lock`` from the GPU call until the rows are consumed; concurrent calls
+from several threads serialise on it.
 """
 from __future__ import annotations
 
@@ -58,23 +63,15 @@ def overlap_edge_rows(reads, k=5, _reuse_host_buffer=False, min_weight=None):
     is int32[E, 4] = (node_a, node_b, weight, end_position) in insertion order and node ids
     number the copies in (uid, copy) order.  min_weight keeps only rows with weight >= it."""
     assert k >= 0, "k-mer length must be non-negative"               # overlapGraphs.py:17
-    read_copies = {}
-    for read in reads:                                               # overlapGraphs.py:18-20
-        read_copies[read] = read_copies.get(read, 0) + 1
-    uniq = list(read_copies.keys())
-    for r in uniq:
-        if not isinstance(r, str):
-            raise TypeError("reads must be str")
-    counts = np.fromiter(read_copies.values(), dtype=np.int32, count=len(uniq))
+    read_copies, uniq, counts = _dedup(reads)
     if len(uniq) == 0:
         return read_copies, uniq, counts, np.zeros((0, 4), np.int32)
     bases, offsets = _flatten(uniq)
     eng = _engine.get_engine()
     try:
         edges = eng.overlap_edges(bases, offsets, counts, k, reuse_host_buffer=_reuse_host_buffer, min_weight=min_weight)
-    except _engine.nat.OvlUnsupported as exc:
-        if "other than A, C, G, T" not in str(exc):
-            raise
+    except _engine.nat.OvlBadAlphabet:
+        # raised right after the pack + count stages, before any pair list is built on the mis-coded rows
         relettered = _to_acgt(bases)
         if relettered is not None:
             edges = eng.overlap_edges(relettered, offsets, counts, k, reuse_host_buffer=_reuse_host_buffer,
@@ -101,67 +98,88 @@ def _graph_from_rows(uniq, counts, edges):
 
 def construct_overlap_graph_nx_k(reads, k=5):
     """Construct the overlap graph -- see overlapGraphs.py:5-16 for the contract."""
-    read_copies, uniq, counts, edges = overlap_edge_rows(reads, k, _reuse_host_buffer=True)   # consumed right below
-    return _graph_from_rows(uniq, counts, edges), read_copies
+    assert k >= 0, "k-mer length must be non-negative"               # overlapGraphs.py:17
+    with _engine.get_engine().lock:           # the rows are a view of the engine's pinned buffer: consumed right below
+        read_copies, uniq, counts, edges = overlap_edge_rows(reads, k, _reuse_host_buffer=True)
+        return _graph_from_rows(uniq, counts, edges), read_copies
+
+
+def _dedup(reads):
+    read_copies = {}
+    for read in reads:                                               # overlapGraphs.py:18-20
+        read_copies[read] = read_copies.get(read, 0) + 1
+    uniq = list(read_copies.keys())
+    for r in uniq:
+        if not isinstance(r, str):
+            raise TypeError("reads must be str")
+    counts = np.fromiter(read_copies.values(), dtype=np.int32, count=len(uniq))
+    return read_copies, uniq, counts
+
+
+def overlap_edge_rows_batch(read_lists, k=5):
+    """Many independent read sets in ONE GPU job: returns, per read set, (read_copies, uniq, counts, edges)
+    exactly as overlap_edge_rows(reads, k) would -- same rows, same order -- but with one pack / index /
+    join / DP pass over all sets: every read is tagged with its set number in the key bits above the
+    k-mer, so reads of different sets never become candidates.  (Not in the reference: this is the
+    graph-build step of its parameter sweep, experiments.py:451-539, which the reference runs as one
+    process per parameter set.)  The returned rows are copies (they outlive the next engine call)."""
+    assert k >= 0, "k-mer length must be non-negative"
+    per_set = [_dedup(reads) for reads in read_lists]
+    if k == 0 or len(read_lists) <= 1:
+        return [overlap_edge_rows(reads, k) for reads in read_lists]
+    all_uniq = [r for _, uniq, _ in per_set for r in uniq]
+    if not all_uniq:
+        return [(rc, uniq, counts, np.zeros((0, 4), np.int32)) for rc, uniq, counts in per_set]
+    counts_all = np.concatenate([c for _, _, c in per_set])
+    seg = np.concatenate([np.full(len(u), s_id, dtype=np.int32) for s_id, (_, u, _) in enumerate(per_set)])
+    bases, offsets = _flatten(all_uniq)
+    has_dups = bool(counts_all.max() > 1)
+    eng = _engine.get_engine()
+    with eng.lock:
+        def job(b):
+            # counts are passed when any read repeats, so that node ids are offsets into the concatenated copy list
+            return eng.overlap_edges(b, offsets, counts_all if has_dups else None, k, reuse_host_buffer=True,
+                                     segments=seg, n_segments=len(read_lists))
+        try:
+            try:
+                edges = job(bases)
+            except _engine.nat.OvlBadAlphabet:
+                relettered = _to_acgt(bases)             # at most four distinct symbols over ALL sets: exact re-lettering
+                if relettered is None:
+                    raise
+                edges = job(relettered)
+        except _engine.nat.OvlUnsupported:
+            # what the one-job path does not cover (segment tag + 2k > 64 key bits, more than four symbols):
+            # one build per read set
+            return [overlap_edge_rows(reads, k) for reads in read_lists]
+        node_base = np.zeros(len(per_set) + 1, dtype=np.int64)
+        if has_dups:
+            np.cumsum([int(c.sum()) for _, _, c in per_set], out=node_base[1:])
+        else:
+            np.cumsum([len(u) for _, u, _ in per_set], out=node_base[1:])
+        bounds = np.searchsorted(edges[:, 0], node_base, side="left") if edges.shape[0] else np.zeros(len(per_set) + 1, np.int64)
+        out = []
+        for s_id, (read_copies, uniq, counts) in enumerate(per_set):
+            rows = edges[bounds[s_id]:bounds[s_id + 1]].copy()
+            rows[:, 0] -= int(node_base[s_id])
+            rows[:, 1] -= int(node_base[s_id])
+            out.append((read_copies, uniq, counts, rows))
+    return out
 
 
 def construct_overlap_graphs_batch(read_lists, k=5):
-    """Many independent read sets in ONE GPU job (not in the reference: this is the graph-build step
-    of its parameter sweep, experiments.py:451-539, which the reference runs as one process per
-    parameter set).  Returns [construct_overlap_graph_nx_k(reads, k) for reads in read_lists] --
-    same graphs, same order -- but with one pack / index / join / DP pass over all sets: every read
-    is tagged with its set number in the key bits above the k-mer, so reads of different sets never
-    become candidates."""
-    assert k >= 0, "k-mer length must be non-negative"
-    if k == 0 or len(read_lists) <= 1:
-        return [construct_overlap_graph_nx_k(reads, k) for reads in read_lists]
-    per_set = []
-    all_uniq, seg, all_counts = [], [], []
-    for s_id, reads in enumerate(read_lists):
-        read_copies = {}
-        for read in reads:
-            read_copies[read] = read_copies.get(read, 0) + 1
-        uniq = list(read_copies.keys())
-        for r in uniq:
-            if not isinstance(r, str):
-                raise TypeError("reads must be str")
-        counts = np.fromiter(read_copies.values(), dtype=np.int32, count=len(uniq))
-        per_set.append((read_copies, uniq, counts))
-        all_uniq.extend(uniq)
-        all_counts.append(counts)
-        seg.append(np.full(len(uniq), s_id, dtype=np.int32))
-    if not all_uniq:
-        return [(nx.DiGraph(), rc) for rc, _, _ in per_set]
-    counts_all = np.concatenate(all_counts)
-    bases, offsets = _flatten(all_uniq)
-    eng = _engine.get_engine()
-    try:
-        # counts are always passed so that node ids are offsets into the concatenated copy list
-        edges = eng.overlap_edges(bases, offsets, np.maximum(counts_all, 1) if counts_all.max() > 1 else None, k,
-                                  reuse_host_buffer=True, segments=np.concatenate(seg), n_segments=len(read_lists))
-    except _engine.nat.OvlUnsupported:
-        # what the one-job path does not cover (k > 31, symbols other than A/C/G/T): one build per read set
-        return [construct_overlap_graph_nx_k(reads, k) for reads in read_lists]
-    node_base = np.zeros(len(per_set) + 1, dtype=np.int64)
-    if counts_all.max() > 1:
-        np.cumsum([int(c.sum()) for _, _, c in per_set], out=node_base[1:])
-    else:
-        np.cumsum([len(u) for _, u, _ in per_set], out=node_base[1:])
-    bounds = np.searchsorted(edges[:, 0], node_base, side="left") if edges.shape[0] else np.zeros(len(per_set) + 1, np.int64)
-    out = []
-    for s_id, (read_copies, uniq, counts) in enumerate(per_set):
-        rows = edges[bounds[s_id]:bounds[s_id + 1]].copy()
-        rows[:, 0] -= int(node_base[s_id])
-        rows[:, 1] -= int(node_base[s_id])
-        out.append((_graph_from_rows(uniq, counts, rows), read_copies))
-    return out
+    """[construct_overlap_graph_nx_k(reads, k) for reads in read_lists] -- same graphs, same order -- from
+    ONE GPU job over all read sets (overlap_edge_rows_batch)."""
+    return [(_graph_from_rows(uniq, counts, rows), read_copies)
+            for read_copies, uniq, counts, rows in overlap_edge_rows_batch(read_lists, k)]
 
 
 def construct_overlap_graph_string(reads):
     """Drop-in for overlapGraphs.py:196-232: every ordered pair of distinct reads is aligned and
     edges are kept only for score > 0 (same node naming and copy expansion as the k-mer builder)."""
-    read_copies, uniq, counts, edges = overlap_edge_rows(reads, 0, _reuse_host_buffer=True, min_weight=1)
-    return _graph_from_rows(uniq, counts, edges), read_copies
+    with _engine.get_engine().lock:
+        read_copies, uniq, counts, edges = overlap_edge_rows(reads, 0, _reuse_host_buffer=True, min_weight=1)
+        return _graph_from_rows(uniq, counts, edges), read_copies
 
 
 def construct_string_graph(reads):
@@ -206,8 +224,9 @@ def construct_string_graph(reads):
     if pa.size:
         bases, offsets = _flatten(order)
         eng = _engine.get_engine()
-        rows = eng.overlap_edges(bases, offsets, None, 0, pairs=(pa, pb), min_weight=1, reuse_host_buffer=True)
-        cols = rows.T.tolist()
+        with eng.lock:
+            rows = eng.overlap_edges(bases, offsets, None, 0, pairs=(pa, pb), min_weight=1, reuse_host_buffer=True)
+            cols = rows.T.tolist()
         graph.add_edges_from((order[u], order[v], {"weight": w, "end_position": e})
                              for u, v, w, e in zip(cols[0], cols[1], cols[2], cols[3]))
     print(f"graph: {graph.edges}")                                   # overlapGraphs.py:350
@@ -215,6 +234,8 @@ def construct_string_graph(reads):
 
 
 def __getattr__(name):
+    if name.startswith("__") and name.endswith("__"):
+        raise AttributeError(name)
     ref = _engine.reference_module("overlapGraphs")
     if ref is not None and hasattr(ref, name):
         return getattr(ref, name)

@@ -215,6 +215,13 @@ int ovl_local_align(ovl_ctx *ctx, const int32_t *query, int32_t n, const int32_t
                     int64_t match, int64_t mismatch, int64_t indel, void *workspace,
                     size_t workspace_bytes, int32_t *result, uint8_t *ops, void *stream);
 
+/* Order-sensitive fingerprint of an edge list: adds, into *accum (device u64, zeroed by the caller),
+ * the sum over rows of mix(first_row + i, row i) mod 2^64.  Shards hashed with their global row
+ * offset add up to the fingerprint of the whole list; any misplaced or reordered row changes it.
+ * Self-check of the multi-GPU exchange paths (no counterpart in the reference). */
+int ovl_edge_list_hash(ovl_ctx *ctx, const int32_t *edges, int64_t E, int64_t first_row,
+                       uint64_t *accum, void *stream);
+
 /* Roofline denominator for the DP: runs a dependency-free instruction stream on every SM and
  * returns lane-operations per second (1e9/s).  kind: 0 IADD3, 1 IMAD, 2 VIMNMX.S32,
  * 3 VIADDMNMX.S16x2, 4 the DP inner-loop mix (PRMT, IMAD, 2x VIADDMNMX.S16x2), 5 PRMT, 6 LOP3,

@@ -159,3 +159,55 @@ def test_config2_one_million_reads_properties():
     la, lb = ld[pa[:n].long()], ld[pb[:n].long()]
     assert bool((s >= 10 * k).all()) and bool((s <= 10 * torch.minimum(la, lb)).all())
     assert bool((e >= 0).all()) and bool((e <= lb).all())
+
+
+def test_config3_long_reads_full_size():
+    """BASELINE.json configs[3] at full size (200,000 reads x 1,000 bp, p = 0.02, 4.6 Mb genome): the pair lists
+    at k = 5 (3.9e7 pairs) and k = 8 against an independent NumPy join, their order, and oracle parity of the
+    32-lane DP instantiation on random samples (default and finite indel) plus the whole k = 8 list's bounds."""
+    import torch
+    synth = load_pkg("synth")
+    eng = load_pkg("engine").get_engine()
+    bases, offsets = synth.make_workload("ecoli_n200k_l1000")
+    ub, uo, counts, _ = synth.dedup(bases, offsets)
+    U = len(counts)
+    rs = eng.upload_reads(ub, uo)
+    eng.check_alphabet(rs)
+    assert rs.max_len == 1000 and eng.dp_plan(rs.max_len) == {"mode": "packed16", "lanes": 32, "cols": 32}
+    lens = (uo[1:] - uo[:-1])
+    code = np.zeros(256, np.int64)
+    code[np.frombuffer(b"ACGT", np.uint8)] = np.arange(4)
+    for k, n_oracle in ((5, 2000), (8, 2000)):
+        idx = eng.kmer_index(rs, k)
+        pa, pb, _ = eng.candidate_pairs(rs, idx, k)
+        P = int(pa.shape[0])
+        # (1) pair count == independent host join
+        valid = np.nonzero(lens >= k)[0]
+        pk = sum(code[ub[uo[valid] + i]] * 4 ** i for i in range(k))
+        sk = sum(code[ub[uo[valid + 1] - k + i]] * 4 ** i for i in range(k))
+        hist = np.bincount(pk, minlength=4 ** k)
+        assert P == int(hist[sk].sum() - (pk == sk).sum())
+        assert P > (30_000_000 if k == 5 else 400_000)
+        # (2) ordered by (a, b), no self pairs; (3) key equality for every pair
+        key = pa.to(torch.int64) * U + pb.to(torch.int64)
+        assert bool((key[1:] > key[:-1]).all()) and bool((pa != pb).all())
+        del key
+        assert bool((idx.suffix_key[:U][pa.long()] == idx.prefix_key[:U][pb.long()]).all())
+        # (4) DP parity on random samples of the real list: default scoring and a finite indel
+        g = torch.Generator(device="cpu").manual_seed(100 + k)
+        sel = torch.randint(0, P, (n_oracle,), generator=g).to(eng.device)
+        sa, sb = pa[sel].contiguous(), pb[sel].contiguous()
+        for prm in [(10, -1, -2 ** 31), (10, -1, -2)]:
+            s, e = eng.overlap_scores(rs, sa, sb, *prm)
+            ws, we = orc.overlap_pairs(ub, uo, sa.cpu().numpy(), sb.cpu().numpy(), *prm)
+            assert np.array_equal(s.cpu().numpy(), ws) and np.array_equal(e.cpu().numpy(), we)
+        if k == 8:
+            # (5) the whole list: score / end bounds, and the fused edge rows equal (a, b, score, end)
+            s, e = eng.overlap_scores(rs, pa, pb)
+            ld = rs.length[:U]
+            la, lb = ld[pa.long()], ld[pb.long()]
+            assert bool((s >= 10 * k).all()) and bool((s <= 10 * torch.minimum(la, lb)).all())
+            assert bool((e >= 0).all()) and bool((e <= lb).all())
+            rows = eng.overlap_edges_fused(rs, pa, pb)
+            assert torch.equal(rows, torch.stack((pa, pb, s, e), dim=1))
+        del pa, pb, idx

@@ -498,3 +498,30 @@ def test_sharded_edges_concatenate(eng):
     whole = eng.overlap_edges(ub, uo, counts, k=6)
     parts = [eng.overlap_edges(ub, uo, counts, k=6, shard=(r, 4)) for r in range(4)]
     assert np.array_equal(np.concatenate(parts), whole)
+
+
+def test_edge_list_hash_matches_host_mirror_and_sees_order(eng):
+    import torch
+    rng = np.random.default_rng(11)
+    rows = rng.integers(-2 ** 31, 2 ** 31 - 1, size=(100_003, 4), dtype=np.int64).astype(np.int32)
+    d = torch.from_numpy(rows).to(eng.device)
+    h = int(eng.edge_hash(d).item()) & 0xFFFFFFFFFFFFFFFF
+    assert h == eng.edge_hash_numpy(rows)
+    assert eng.edge_hash_host(rows, chunk_rows=7777) == h
+    # shards hashed with their global row offset add up (mod 2^64)
+    cut = 41_234
+    parts = (eng.edge_hash_numpy(rows[:cut]) + eng.edge_hash_numpy(rows[cut:], first_row=cut)) & 0xFFFFFFFFFFFFFFFF
+    assert parts == h
+    acc = eng.edge_hash(d[:cut])
+    eng.edge_hash(d[cut:], first_row=cut, accum=acc)
+    assert int(acc.item()) & 0xFFFFFFFFFFFFFFFF == h
+    # a sum of fields cannot see these; the fingerprint must: two rows swapped, one row duplicated over its neighbour
+    swapped = rows.copy()
+    swapped[[10, 20]] = swapped[[20, 10]]
+    assert swapped.astype(np.int64).sum() == rows.astype(np.int64).sum()
+    assert int(eng.edge_hash(torch.from_numpy(swapped).to(eng.device)).item()) & 0xFFFFFFFFFFFFFFFF != h
+    comp = rows.copy()
+    comp[5, 2] += 1
+    comp[6, 2] -= 1                                     # compensating errors
+    assert int(eng.edge_hash(torch.from_numpy(comp).to(eng.device)).item()) & 0xFFFFFFFFFFFFFFFF != h
+    assert int(eng.edge_hash(d[:0]).item()) == 0

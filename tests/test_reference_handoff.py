@@ -61,8 +61,12 @@ def test_rebuilt_graph_gives_identical_contigs(k):
     assert len(got) > 0
 
 
-def test_forwarding_module_is_patched_with_the_drop_ins():
+def test_forwarding_module_is_patched_with_the_drop_ins(monkeypatch):
+    import sys
+    monkeypatch.setenv("OVL_REFERENCE_DIR", ref_loader.REFERENCE_DIR)      # forwarding is opt-in
     eng = load_pkg("engine")
+    eng._REF_MODULES.clear()
+    had_mpl = "matplotlib" in sys.modules
     og = load_pkg("overlapGraphs")
     al = load_pkg("aligners")
     ref = eng.reference_module("overlapGraphs")
@@ -72,3 +76,17 @@ def test_forwarding_module_is_patched_with_the_drop_ins():
     # symbols outside the accelerated path resolve through the drop-in module
     assert og.remove_cycles_from_graph is ref.remove_cycles_from_graph
     assert og.assemble_contigs_using_overlap_graphs is ref.assemble_contigs_using_overlap_graphs
+    # dunder probes never reach the forwarding, and the import stubs do not outlive the module load
+    assert not hasattr(og, "__wrapped__")
+    assert ("matplotlib" in sys.modules) == had_mpl
+    eng._REF_MODULES.clear()
+
+
+def test_no_forwarding_without_opt_in(monkeypatch):
+    monkeypatch.delenv("OVL_REFERENCE_DIR", raising=False)
+    eng = load_pkg("engine")
+    eng._REF_MODULES.clear()
+    og = load_pkg("overlapGraphs")
+    assert eng.reference_module("overlapGraphs") is None
+    with pytest.raises(AttributeError):
+        og.remove_cycles_from_graph
