@@ -341,21 +341,21 @@ def measure(env, wl, steps, warmup, cpu_seconds, use_peer=True, with_cpu=True, s
     exchange = "none (1 GPU)"
 
     def device_step(record=None):
-        rs = eng.pack_reads(d_ascii, d_off, U, wl.max_len)
-        index = eng.kmer_index(rs, k) if k > 0 else None
-        pa, pb, p_begin = eng.candidate_pairs(rs, index, k, shard)
+        # K0-K3 as one library call + one host sync (the pair / edge totals), then the pair fill
+        cand = eng.build_candidates(d_ascii, d_off, U, wl.max_len, k, d_copies, d_node_off, shard)
+        pa, pb = eng.fill_pairs(cand)
         if record is not None:
             record["k1"].record()           # end of the k-mer stages (K0-K3)
-        # K6 is fused into the DP epilogue; with duplicate reads the per-pair edge offsets come first
-        edges = eng.overlap_edges_fused(rs, pa, pb, d_copies, d_node_off,
-                                        events=(record["dp0"], record["dp1"]) if record is not None else None,
-                                        sink=peer.slot if peer is not None else None)
+        # K6 is fused into the DP epilogue; with duplicate reads the row offsets come from the join index
+        edges = eng.candidate_edges(cand, pa, pb,
+                                    events=(record["dp0"], record["dp1"]) if record is not None else None,
+                                    sink=peer.slot if peer is not None else None)
         if peer is not None:
             # the DP epilogue has stored this rank's rows straight into rank 0's buffer over NVLink
             peer.barrier()
-            return rs, pa, pb, None, peer.result()
+            return cand.rs, pa, pb, None, peer.result()
         edges_all = par.gather_edges(edges, 0) if world > 1 else edges
-        return rs, pa, pb, edges, edges_all
+        return cand.rs, pa, pb, edges, edges_all
 
     def list_hash(edges_all):
         """Order-sensitive fingerprint of the complete list (rank 0), as an unsigned 64-bit int."""
@@ -512,8 +512,10 @@ def measure(env, wl, steps, warmup, cpu_seconds, use_peer=True, with_cpu=True, s
                     "int_probe_gops": probe, "hbm_peak_gbs": pk.get("hbm_gbs"), "hbm_peak_source": pk_kind}
         # ---- the k-mer stages (K0-K3) and edge expansion (K6): HBM-bound; algorithmic bytes per SURVEY 8(d).
         # Every rank packs / indexes / counts all reads (replicated) and fills ITS slice of the pair list.
-        passes = (2 * k + 7) // 8
-        kb = (wl.total_bases + wl.total_bases / 4) + 48 * U + 12 * (1 + 2 * passes) * U + 16 * U + 12 * pairs_rank_max
+        # K0 pack: ASCII in + packed out; K1 (fused into K0): 16 B of keys out; K2: 12 B x (1 + 2 x passes) with
+        # 10-bit digits (one pass for k <= 5); K3: 16 B per read + 12 B per pair
+        passes = (2 * k + 9) // 10
+        kb = (wl.total_bases + wl.total_bases / 4) + 16 * U + 12 * (1 + 2 * passes) * U + 16 * U + 12 * pairs_rank_max
         k_ms = kmer_total_ms / steps
         o_ms = off_total_ms / steps
         hbm = pk.get("hbm_gbs")
@@ -526,8 +528,8 @@ def measure(env, wl, steps, warmup, cpu_seconds, use_peer=True, with_cpu=True, s
                                "edge_offset_stage_ms is what precedes the DP when reads have copies"},
                 "k0_k3_plus_k6_offsets_frac": kb / ((k_ms + o_ms) * 1e-3) / 1e9 / hbm,
                 "per_rank": world > 1,
-                "note": "pack + keys + index + join (count, scan, fill), timed with CUDA events inside the step; "
-                        "includes the host round trip for the pair count"}
+                "note": "pack+keys, index (+ bucket table), join count / scan / totals (one library call), the host sync on "
+                        "the totals, pair fill; timed with CUDA events inside the step"}
         # ---- CPU baseline on this box's host cores (bounded sample)
         cpu = numba = None
         if with_cpu and world == 1 and pairs > 0:

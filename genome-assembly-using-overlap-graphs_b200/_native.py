@@ -45,6 +45,16 @@ _i32 = ctypes.c_int32
 _i64 = ctypes.c_int64
 _sz = ctypes.c_size_t
 
+class CandLayout(ctypes.Structure):
+    """ovl_cand_layout (include/ovl.h): byte offsets of every array of the K0-K3 job inside its arena."""
+    _fields_ = [(n, ctypes.c_size_t) for n in (
+        "packed", "len", "bad", "n_indexed", "prefix_key", "suffix_key", "sorted_key", "sorted_uid", "table", "pos_of",
+        "bucket_lo", "self_rank", "pair_off", "edge_base", "cum", "scratch", "scratch_bytes", "total_bytes")] + \
+        [(n, ctypes.c_int32) for n in ("row_words", "key_bits", "table_bits", "has_copies")]
+
+
+_lay_p = ctypes.POINTER(CandLayout)
+
 _SIGS = {
     "ovl_last_error": (ctypes.c_char_p, []),
     "ovl_version": (ctypes.c_int, []),
@@ -60,9 +70,18 @@ _SIGS = {
     "ovl_join_fill_verify": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i64,
                                             _vp, _vp, _vp]),
     "ovl_index_workspace_bytes": (_sz, [_i64]),
-    "ovl_index_build": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ovl_pack_reads_keys": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ovl_index_table_bits": (_i32, [_i64, _i32]),
+    "ovl_index_build": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
     "ovl_join_workspace_bytes": (_sz, [_i64]),
-    "ovl_join_count": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ovl_join_count": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _vp, _vp, _sz, _vp]),
+    "ovl_totals_len": (_i32, []),
+    "ovl_join_finalize": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "ovl_candidates_layout": (ctypes.c_int, [_i64, _i32, _i32, _i32, _i32, _lay_p]),
+    "ovl_candidates_build": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _lay_p, _vp, _vp]),
+    "ovl_overlap_dp_edges_join": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _i64, _vp, _vp, _vp,
+                                                 _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "ovl_join_fill": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "ovl_all_pairs_fill": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "ovl_overlap_dp": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _i64, _vp, _vp,

@@ -41,6 +41,7 @@
 // schemes or read lengths whose range does not fit 16 bits.
 #pragma once
 #include "common.cuh"
+#include "joinidx.cuh"
 
 namespace ovl {
 
@@ -62,8 +63,16 @@ struct DpEdgeOut {
     int4* edges;                 // int32[E][4] rows, or null
     const int32_t* copies;       // multiplicity per unique read, or null when every read occurs once
     const int64_t* node_off;     // exclusive scan of copies
-    const int64_t* edge_off;     // exclusive scan of copies[a]*copies[b] over the pair list
+    const int64_t* edge_off;     // explicit row offsets: exclusive scan of copies[a]*copies[b] over the pair list, or null
+    JoinEdgeIndex join;          // implicit row offsets of a k-mer join (join.pair_off != null), see joinidx.cuh
 };
+
+// first edge row of pair p (local index) = (a, b) when reads have copies
+__device__ __forceinline__ int4* dp_edge_dst(const DpEdgeOut& eo, int64_t p, int32_t a) {
+    if (eo.join.pair_off != nullptr)
+        return eo.edges + (join_edge_offset(eo.join, eo.copies, eo.join.p_begin + p, a) - eo.join.e_begin);
+    return eo.edges + eo.edge_off[p];
+}
 
 #ifndef OVL_DP_THREADS
 #define OVL_DP_THREADS 128
@@ -370,7 +379,7 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : OVL_DP_MINB)) overla
                 } else {
                     const int32_t ca = eo.copies[a], cb = eo.copies[b];
                     const int32_t na = (int32_t)eo.node_off[a], nb = (int32_t)eo.node_off[b];
-                    int4* dst = eo.edges + eo.edge_off[p];
+                    int4* dst = dp_edge_dst(eo, p, a);
                     for (int32_t ia = 0; ia < ca; ++ia)
                         for (int32_t ib = 0; ib < cb; ++ib) *dst++ = make_int4(na + ia, nb + ib, score, bestj[h]);
                 }
@@ -451,7 +460,7 @@ __global__ void __launch_bounds__(kDpLongThreads) overlap_dp_long_kernel(
         } else {
             const int32_t ca = eo.copies[a], cb = eo.copies[b];
             const int32_t na = (int32_t)eo.node_off[a], nb = (int32_t)eo.node_off[b];
-            int4* dst = eo.edges + eo.edge_off[p];
+            int4* dst = dp_edge_dst(eo, p, a);
             for (int32_t ia = 0; ia < ca; ++ia)
                 for (int32_t ib = 0; ib < cb; ++ib) *dst++ = make_int4(na + ia, nb + ib, score, bestj);
         }

@@ -1,8 +1,7 @@
 // k-mer stages of the overlap graph builder (replaces overlapGraphs.py:30-52, 55-60):
 //   K0 pack_reads      ASCII -> 2-bit packed rows (+ length, non-ACGT detection)
 //   K1 kmer_keys       prefix / suffix k-mer of every read as a 2k-bit integer
-//   K2 radix passes    stable LSD sort of (prefix_key, uid)  == the reference's prefix_index
-//   K3 join_count/fill suffix_key[a] == prefix_key[b], a != b  -> ordered candidate pairs
+//   (K2 index and K3 join live in index.cuh)
 //   K6 expand_*        (a, b, score, end) -> copy_a x copy_b edge rows
 // All of these are HBM-bound byte/integer work: coalesced, 128-bit where the layout allows.
 #pragma once
@@ -39,21 +38,43 @@ __device__ __forceinline__ uint32_t pack16(const uint32_t r[4], int nvalid, uint
     return out;
 }
 
+// bits [o, o + 64) of the word array w[0..7] (o < 192), without dynamic register indexing
+__device__ __forceinline__ uint64_t window64(const uint32_t (&w)[8], int o) {
+    const int wi = o >> 5, sh = o & 31;
+    uint32_t a = 0, b = 0, c = 0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+        if (wi == j) { a = w[j]; b = w[j + 1]; c = w[j + 2]; }
+    return ((uint64_t)__funnelshift_r(b, c, sh) << 32) | __funnelshift_r(a, b, sh);
+}
+
+// KEYS: K1 fused into K0 -- the thread that packs a read's first 64 bases holds its prefix k-mer, the
+// thread that packs its last bases holds (with one shuffle from its left neighbour when the k-mer
+// straddles two 64-base groups) its suffix k-mer, so the keys cost no further pass over the rows.
+template <bool KEYS>
 __global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t* __restrict__ ascii,
                                                          const int64_t* __restrict__ offsets,
                                                          int64_t U, int row_words,
                                                          uint32_t* __restrict__ packed,
                                                          int32_t* __restrict__ len_out,
-                                                         int32_t* __restrict__ bad_count) {
+                                                         int32_t* __restrict__ bad_count,
+                                                         int k, const int32_t* __restrict__ segment,
+                                                         uint64_t* __restrict__ prefix_key,
+                                                         uint64_t* __restrict__ suffix_key) {
     const int quads = row_words >> 2;                // 16-byte groups per row
-    int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= U * quads) return;
-    int64_t u = slot / quads;
-    int q = (int)(slot - u * quads);
-    int64_t o0 = offsets[u];
-    int len = (int)(offsets[u + 1] - o0);
-    if (q == 0) len_out[u] = len;
-    int nvalid = len - 64 * q;                       // bases this thread holds
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = slot < U * quads;
+    if (!KEYS && !active) return;
+    const int64_t u = active ? slot / quads : 0;
+    const int q = active ? (int)(slot - u * quads) : 0;
+    int64_t o0 = 0;
+    int len = 0;
+    if (active) {
+        o0 = offsets[u];
+        len = (int)(offsets[u + 1] - o0);
+        if (q == 0) len_out[u] = len;
+    }
+    const int nvalid = len - 64 * q;                 // bases this thread holds
     uint4 outv = make_uint4(0u, 0u, 0u, 0u);
     if (nvalid > 0) {
         int64_t addr = o0 + 64 * (int64_t)q;         // byte index of the first base
@@ -82,7 +103,33 @@ __global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t* __restri
         outv.w = pack16(r + 12, nvalid - 48, bad);
         if (bad) atomicAdd(bad_count, 1);
     }
-    reinterpret_cast<uint4*>(packed)[slot] = outv;
+    if (active) reinterpret_cast<uint4*>(packed)[slot] = outv;
+    if (KEYS) {
+        // bases 32..63 of the left neighbour's group (the same read's previous group when q > 0)
+        const uint32_t pz = __shfl_up_sync(kFull, outv.z, 1), pw = __shfl_up_sync(kFull, outv.w, 1);
+        if (!active) return;
+        const uint64_t mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+        const uint64_t tag = segment != nullptr ? (uint64_t)(uint32_t)segment[u] << (2 * k) : 0ull;
+        if (q == 0)                                                       // overlapGraphs.py:33-37: prefix = read[:k]
+            prefix_key[u] = len >= k ? (((((uint64_t)outv.y << 32) | outv.x) & mask) | tag) : kInvalidKey;
+        if (q == (len > 0 ? (len - 1) >> 6 : 0)) {                        // :44-47: suffix = read[-k:]
+            uint64_t sk = kInvalidKey;
+            if (len >= k) {
+                const int s_local = len - k - 64 * q;                     // first base of the k-mer, relative to my group (>= -31)
+                if (s_local >= 0 || lane_id() != 0) {
+                    const uint32_t w[8] = {pz, pw, outv.x, outv.y, outv.z, outv.w, 0u, 0u};
+                    sk = window64(w, 64 + 2 * s_local);
+                } else {
+                    // the k-mer starts in a group packed by another warp: take it from the ASCII bytes (L1/L2 hits)
+                    sk = 0;
+                    const uint8_t* p = ascii + o0 + (len - k);
+                    for (int i = 0; i < k; ++i) sk |= (uint64_t)((p[i] >> 1) & 3u) << (2 * i);
+                }
+                sk = (sk & mask) | tag;
+            }
+            suffix_key[u] = sk;
+        }
+    }
 }
 
 // ------------------------------------------------------------------ K1 kmer_keys
@@ -285,207 +332,6 @@ __global__ void __launch_bounds__(256) join_verify8_kernel(const uint8_t* __rest
         }
     }
     if (!FILL) cnt_out[i] = cnt;
-}
-
-// ------------------------------------------------------------------ K2 radix sort (stable, LSD, 8-bit digits)
-// Each warp owns kSortChunk consecutive elements; a pass is: per-warp digit histogram ->
-// exclusive scan over (digit-major, warp-minor) -> per-warp stable scatter.  Stability keeps
-// uids ascending inside a bucket, which is the reference's bucket-append order
-// (overlapGraphs.py:38-40).  Pass 0 reads (prefix_key, uid = index) straight from K1's
-// output and drops reads shorter than k.
-constexpr int kSortChunk = 512;          // elements per warp
-constexpr int kSortWarps = 8;            // warps per CTA
-constexpr int kSortThreads = kSortWarps * 32;
-
-template <bool FIRST>
-__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint64_t* __restrict__ keys,
-                                                                  const int32_t* __restrict__ len, int k,
-                                                                  const int64_t* __restrict__ n_ptr, int64_t n_static,
-                                                                  int shift, int64_t W, int32_t* __restrict__ hist) {
-    __shared__ int32_t cnt[kSortWarps][256];
-    int wib = threadIdx.x >> 5;
-    int64_t warp = (int64_t)blockIdx.x * kSortWarps + wib;
-    for (int i = lane_id(); i < 256; i += 32) cnt[wib][i] = 0;
-    __syncwarp();
-    int64_t n = FIRST ? n_static : *n_ptr;
-    int64_t base = warp * kSortChunk;
-    if (warp < W) {
-        // all loads of the chunk are issued before the first atomic (16 independent requests per lane)
-        constexpr int R = kSortChunk / 32;
-        uint64_t key[R];
-        bool live[R];
-#pragma unroll
-        for (int it = 0; it < R; ++it) {
-            int64_t idx = base + it * 32 + lane_id();
-            live[it] = idx < n;
-            key[it] = live[it] ? keys[idx] : 0;
-            if (FIRST && live[it]) live[it] = len[idx] >= k;
-        }
-#pragma unroll
-        for (int it = 0; it < R; ++it)
-            if (live[it]) atomicAdd(&cnt[wib][(int)((key[it] >> shift) & 255u)], 1);
-        __syncwarp();
-        for (int d = lane_id(); d < 256; d += 32) hist[(int64_t)d * W + warp] = cnt[wib][d];
-    }
-}
-
-template <bool FIRST>
-__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint64_t* __restrict__ keys_in,
-                                                                     const uint32_t* __restrict__ uid_in,
-                                                                     const int32_t* __restrict__ len, int k,
-                                                                     const int64_t* __restrict__ n_ptr, int64_t n_static,
-                                                                     int shift, int64_t W,
-                                                                     const int32_t* __restrict__ hist_scanned,
-                                                                     uint64_t* __restrict__ keys_out,
-                                                                     uint32_t* __restrict__ uid_out,
-                                                                     int64_t* __restrict__ n_out) {
-    __shared__ int32_t off[kSortWarps][256];
-    int wib = threadIdx.x >> 5;
-    int64_t warp = (int64_t)blockIdx.x * kSortWarps + wib;
-    if (warp >= W) return;
-    for (int d = lane_id(); d < 256; d += 32) off[wib][d] = hist_scanned[(int64_t)d * W + warp];
-    __syncwarp();
-    int64_t n = FIRST ? n_static : *n_ptr;
-    int64_t base = warp * kSortChunk;
-    constexpr int R = kSortChunk / 32;
-    uint64_t key[R];
-    uint32_t uid[R];
-    bool live[R];
-#pragma unroll
-    for (int it = 0; it < R; ++it) {                 // issue every load of the chunk up front
-        int64_t idx = base + it * 32 + lane_id();
-        live[it] = idx < n;
-        key[it] = live[it] ? keys_in[idx] : 0;
-        uid[it] = FIRST ? (uint32_t)idx : (live[it] ? uid_in[idx] : 0u);
-        if (FIRST && live[it]) live[it] = len[idx] >= k;
-    }
-#pragma unroll
-    for (int it = 0; it < R; ++it) {
-        unsigned d = live[it] ? (unsigned)((key[it] >> shift) & 255u) : 256u + lane_id();  // dead lanes match nobody
-        unsigned peers = __match_any_sync(kFull, d);
-        int rank = __popc(peers & lanemask_lt());
-        int pos = 0;
-        if (live[it]) pos = off[wib][d] + rank;
-        __syncwarp();
-        if (live[it] && rank == 0) off[wib][d] += __popc(peers);
-        __syncwarp();
-        if (live[it]) { keys_out[pos] = key[it]; uid_out[pos] = uid[it]; }
-    }
-    if (FIRST && n_out != nullptr && warp == W - 1 && lane_id() == 0) {
-        // after the last warp's chunk, digit 255's running offset is the number of survivors
-        *n_out = (int64_t)off[wib][255];
-    }
-}
-
-// ------------------------------------------------------------------ K3 join
-// One thread per source read a (overlapGraphs.py:43-52): equal range of suffix_key[a] in
-// the sorted prefix keys.  `self_rank` is a's own position inside its bucket (or -1): the
-// reference skips read_b == read_a (:52) and reads are unique, so that is the only skip.
-__global__ void __launch_bounds__(256) join_count_kernel(const uint64_t* __restrict__ suffix_key,
-                                                         const uint64_t* __restrict__ prefix_key,
-                                                         const int32_t* __restrict__ len, int k,
-                                                         int64_t a_begin, int64_t a_end,
-                                                         const uint64_t* __restrict__ sorted_key,
-                                                         const uint32_t* __restrict__ sorted_uid,
-                                                         const int64_t* __restrict__ n_indexed,
-                                                         int32_t* __restrict__ lo_out, int32_t* __restrict__ self_rank,
-                                                         int64_t* __restrict__ cnt_out) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t a = a_begin + i;
-    if (a >= a_end) return;
-    uint64_t key = suffix_key[a];
-    int64_t cnt = 0;
-    int32_t lo32 = 0, sr = -1;
-    if (len[a] >= k) {
-        int64_t n = *n_indexed;
-        int64_t lo = lower_bound<uint64_t>(sorted_key, 0, n, key);
-        int64_t hi = upper_bound<uint64_t>(sorted_key, lo, n, key);
-        cnt = hi - lo;
-        lo32 = (int32_t)lo;
-        if (prefix_key[a] == key) {                 // a sits in its own bucket
-            int64_t p = lower_bound<uint32_t>(sorted_uid, lo, hi, (uint32_t)a);
-            sr = (int32_t)(p - lo);
-            cnt -= 1;
-        }
-    }
-    lo_out[i] = lo32;
-    self_rank[i] = sr;
-    cnt_out[i] = cnt;
-}
-
-// One thread per output pair; a CTA covers a contiguous tile of the output so both stores are
-// coalesced.  The owning source read is found by binary search over the scanned counts,
-// narrowed first to the tile's own [a_lo, a_hi] range (two searches per CTA).
-constexpr int kFillThreads = 256;
-constexpr int kFillItems = 8;
-constexpr int kFillTile = kFillThreads * kFillItems;
-
-__global__ void __launch_bounds__(kFillThreads) join_fill_kernel(const int64_t* __restrict__ pair_off,  // [nA+1]
-                                                                 int64_t nA, int64_t a_begin,
-                                                                 const int32_t* __restrict__ lo, const int32_t* __restrict__ self_rank,
-                                                                 const uint32_t* __restrict__ sorted_uid,
-                                                                 int64_t p_begin, int64_t p_count,
-                                                                 int32_t* __restrict__ pair_a, int32_t* __restrict__ pair_b) {
-    __shared__ int64_t range[2];
-    int64_t tile0 = (int64_t)blockIdx.x * kFillTile;
-    if (threadIdx.x == 0) {
-        int64_t first = p_begin + tile0;
-        int64_t last = p_begin + min(tile0 + kFillTile, p_count) - 1;
-        range[0] = upper_bound<int64_t>(pair_off, 0, nA + 1, first) - 1;
-        range[1] = upper_bound<int64_t>(pair_off, 0, nA + 1, last) - 1;
-    }
-    __syncthreads();
-    int64_t alo = range[0], ahi = range[1];
-#pragma unroll
-    for (int it = 0; it < kFillItems; ++it) {
-        int64_t q = tile0 + it * kFillThreads + threadIdx.x;
-        if (q >= p_count) break;
-        int64_t p = p_begin + q;
-        int64_t i = upper_bound<int64_t>(pair_off, alo, ahi + 1, p) - 1;
-        int32_t r = (int32_t)(p - pair_off[i]);
-        int32_t sr = self_rank[i];
-        if (sr >= 0 && r >= sr) r += 1;
-        pair_a[q] = (int32_t)(a_begin + i);
-        pair_b[q] = (int32_t)sorted_uid[lo[i] + r];
-    }
-}
-
-// Same output, one warp per source read: used when buckets are large (mean >= 32 candidates per
-// read), where every lane streams consecutive candidates -- no search, fully coalesced stores.
-__global__ void __launch_bounds__(256) join_fill_warp_kernel(const int64_t* __restrict__ pair_off, int64_t nA, int64_t a_begin,
-                                                             const int32_t* __restrict__ lo, const int32_t* __restrict__ self_rank,
-                                                             const uint32_t* __restrict__ sorted_uid,
-                                                             int64_t p_begin, int64_t p_count,
-                                                             int32_t* __restrict__ pair_a, int32_t* __restrict__ pair_b) {
-    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (i >= nA) return;
-    int64_t first = pair_off[i], last = pair_off[i + 1];
-    int64_t from = max(first, p_begin), to = min(last, p_begin + p_count);
-    if (from >= to) return;
-    int32_t sr = self_rank[i];
-    int64_t base = lo[i];
-    int32_t a = (int32_t)(a_begin + i);
-    for (int64_t p = from + lane_id(); p < to; p += 32) {
-        int32_t r = (int32_t)(p - first);
-        if (sr >= 0 && r >= sr) r += 1;
-        int64_t q = p - p_begin;
-        pair_a[q] = a;
-        pair_b[q] = (int32_t)sorted_uid[base + r];
-    }
-}
-
-// k == 0: every ordered pair a != b (overlapGraphs.py:49), a in [a_begin, a_end).
-__global__ void __launch_bounds__(256) all_pairs_fill_kernel(int64_t U, int64_t a_begin, int64_t p_begin, int64_t p_count,
-                                                             int32_t* __restrict__ pair_a, int32_t* __restrict__ pair_b) {
-    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= p_count) return;
-    int64_t p = p_begin + q;
-    int64_t per = U - 1;
-    int64_t ai = p / per;
-    int64_t r = p - ai * per;
-    int64_t a = a_begin + ai;
-    pair_a[q] = (int32_t)a;
-    pair_b[q] = (int32_t)(r >= a ? r + 1 : r);
 }
 
 // ------------------------------------------------------------------ K6 expand edges

@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "scan.cuh"
+#include "index.cuh"
 #include "kmer.cuh"
 #include "dp.cuh"
 #include "probe.cuh"
@@ -112,17 +113,39 @@ int32_t ovl_row_words(int32_t max_len) {
 }
 
 // ---------------------------------------------------------------- K0 / K1
+static int pack_launch(ovl_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int64_t U, int32_t row_words, int32_t k,
+                       const int32_t* segment, uint32_t* packed, int32_t* len, int32_t* bad_count, uint64_t* prefix_key,
+                       uint64_t* suffix_key, cudaStream_t st, const char* who) {
+    if (!ctx || !ascii || !offsets || !packed || !len || !bad_count) return fail(OVL_E_ARG, "%s: null argument", who);
+    if (U <= 0) return OVL_OK;
+    if (row_words < 4 || (row_words & 3)) return fail(OVL_E_ARG, "%s: row_words must be a positive multiple of 4", who);
+    if (((uintptr_t)ascii & 15) || ((uintptr_t)packed & 15)) return fail(OVL_E_ARG, "%s: ascii and packed must be 16-byte aligned", who);
+    unsigned grid = grid_for(U * (row_words / 4), 256);
+    if (prefix_key != nullptr) {
+        if (k < 1 || k > OVL_MAX_K) return fail(OVL_E_UNSUPPORTED, "%s: k=%d outside 1..%d", who, k, OVL_MAX_K);
+        if (segment && k > 31) return fail(OVL_E_UNSUPPORTED, "%s: segment tags need 2k < 64 (k=%d)", who, k);
+        if (!suffix_key) return fail(OVL_E_ARG, "%s: prefix_key given without suffix_key", who);
+        pack_reads_kernel<true><<<grid, 256, 0, st>>>(ascii, offsets, U, row_words, packed, len, bad_count, k, segment, prefix_key, suffix_key);
+    } else {
+        pack_reads_kernel<false><<<grid, 256, 0, st>>>(ascii, offsets, U, row_words, packed, len, bad_count, 0, nullptr, nullptr, nullptr);
+    }
+    LAUNCH_CHECK("pack_reads_kernel");
+    return OVL_OK;
+}
+
 int ovl_pack_reads(ovl_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int64_t U, int32_t row_words,
                    uint32_t* packed, int32_t* len, int32_t* bad_count, void* stream) {
     ON_CTX_DEVICE(ctx);
-    if (!ctx || !ascii || !offsets || !packed || !len || !bad_count) return fail(OVL_E_ARG, "ovl_pack_reads: null argument");
-    if (U <= 0) return OVL_OK;
-    if (row_words < 4 || (row_words & 3)) return fail(OVL_E_ARG, "ovl_pack_reads: row_words must be a positive multiple of 4");
-    if (((uintptr_t)ascii & 15) || ((uintptr_t)packed & 15)) return fail(OVL_E_ARG, "ovl_pack_reads: ascii and packed must be 16-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
-    pack_reads_kernel<<<grid_for(U * (row_words / 4), 256), 256, 0, st>>>(ascii, offsets, U, row_words, packed, len, bad_count);
-    LAUNCH_CHECK("pack_reads_kernel");
-    return OVL_OK;
+    return pack_launch(ctx, ascii, offsets, U, row_words, 0, nullptr, packed, len, bad_count, nullptr, nullptr, (cudaStream_t)stream, "ovl_pack_reads");
+}
+
+int ovl_pack_reads_keys(ovl_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int64_t U, int32_t row_words, int32_t k,
+                        const int32_t* segment, uint32_t* packed, int32_t* len, int32_t* bad_count, uint64_t* prefix_key,
+                        uint64_t* suffix_key, void* stream) {
+    ON_CTX_DEVICE(ctx);
+    if (!prefix_key || !suffix_key) return fail(OVL_E_ARG, "ovl_pack_reads_keys: null key output");
+    return pack_launch(ctx, ascii, offsets, U, row_words, k, segment, packed, len, bad_count, prefix_key, suffix_key, (cudaStream_t)stream,
+                       "ovl_pack_reads_keys");
 }
 
 int ovl_kmer_keys(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, int64_t U, int32_t k,
@@ -149,39 +172,58 @@ int ovl_kmer_hashes(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, con
 }
 
 // ---------------------------------------------------------------- K2
-// workspace: [hist int32 256*W][scan sums][tmp keys u64 U][tmp uids u32 U]
+// workspace: [hist int32 2^D*W + 1][scan sums][tmp keys u64 U][tmp uids u32 U]
 static inline int64_t sort_warps(int64_t U) { return (U + kSortChunk - 1) / kSortChunk; }
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t ovl_index_workspace_bytes(int64_t U) {
     if (U < 1) U = 1;
     int64_t W = sort_warps(U);
-    size_t hist = align256((size_t)(256 * W + 1) * sizeof(int32_t));
-    size_t sums = align256(scan_workspace_bytes(256 * W, sizeof(int32_t)));
+    int64_t hn = ((int64_t)1 << kSortMaxDigit) * W;
+    size_t hist = align256((size_t)(hn + 1) * sizeof(int32_t));
+    size_t sums = align256(scan_workspace_bytes(hn, sizeof(int32_t)));
     size_t keys = align256((size_t)U * sizeof(uint64_t));
     size_t uids = align256((size_t)U * sizeof(uint32_t));
     return hist + sums + keys + uids + 256;
 }
 
+int32_t ovl_index_table_bits(int64_t U, int32_t key_bits) {
+    if (key_bits < 1) return 0;
+    int lg = 0;
+    while (((int64_t)1 << lg) < U) ++lg;
+    int tb = std::min<int>(key_bits, kTableMaxBits);
+    return std::min(tb, std::max(8, lg + 2));
+}
+
 int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len, int64_t U, int32_t k, int32_t key_bits, uint64_t* sorted_key,
-                    uint32_t* sorted_uid, int64_t* n_indexed, void* workspace, size_t workspace_bytes, void* stream) {
+                    uint32_t* sorted_uid, int64_t* n_indexed, int32_t* table, int32_t table_bits, int32_t* pos_of, void* workspace,
+                    size_t workspace_bytes, void* stream) {
     ON_CTX_DEVICE(ctx);
     if (!ctx || !prefix_key || !len || !sorted_key || !sorted_uid || !n_indexed || !workspace) return fail(OVL_E_ARG, "ovl_index_build: null argument");
     if (k < 1) return fail(OVL_E_ARG, "ovl_index_build: k must be positive");
     if (k > OVL_MAX_K && key_bits != 64) return fail(OVL_E_ARG, "ovl_index_build: k=%d > %d needs hashed keys (key_bits = 64)", k, OVL_MAX_K);
     if (workspace_bytes < ovl_index_workspace_bytes(U)) return fail(OVL_E_ARG, "ovl_index_build: workspace too small");
+    if (U > 0x7fffffffll) return fail(OVL_E_UNSUPPORTED, "ovl_index_build: more than 2^31 - 1 reads");
     cudaStream_t st = (cudaStream_t)stream;
-    if (U <= 0) { CUDA_TRY(cudaMemsetAsync(n_indexed, 0, sizeof(int64_t), st)); return OVL_OK; }
+    if (key_bits <= 0) key_bits = 2 * k;                 // no segment tag above the k-mer
+    if ((key_bits < 2 * k && k <= OVL_MAX_K) || key_bits > 64) return fail(OVL_E_ARG, "ovl_index_build: key_bits=%d outside [2k, 64]", key_bits);
+    if (table && (table_bits < 1 || table_bits > key_bits || table_bits > kTableMaxBits))
+        return fail(OVL_E_ARG, "ovl_index_build: table_bits=%d outside [1, min(key_bits, %d)]", table_bits, kTableMaxBits);
+    if (U <= 0) {
+        CUDA_TRY(cudaMemsetAsync(n_indexed, 0, sizeof(int64_t), st));
+        if (table) CUDA_TRY(cudaMemsetAsync(table, 0, (((size_t)1 << table_bits) + 1) * sizeof(int32_t), st));
+        return OVL_OK;
+    }
     int64_t W = sort_warps(U);
+    int64_t hn_max = ((int64_t)1 << kSortMaxDigit) * W;
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    int32_t* hist = (int32_t*)ws;                 ws += align256((size_t)(256 * W + 1) * sizeof(int32_t));
-    void* sums = ws;                              ws += align256(scan_workspace_bytes(256 * W, sizeof(int32_t)));
+    int32_t* hist = (int32_t*)ws;                 ws += align256((size_t)(hn_max + 1) * sizeof(int32_t));
+    void* sums = ws;                              ws += align256(scan_workspace_bytes(hn_max, sizeof(int32_t)));
     uint64_t* tmp_key = (uint64_t*)ws;            ws += align256((size_t)U * sizeof(uint64_t));
     uint32_t* tmp_uid = (uint32_t*)ws;
 
-    if (key_bits <= 0) key_bits = 2 * k;                 // no segment tag above the k-mer
-    if ((key_bits < 2 * k && k <= OVL_MAX_K) || key_bits > 64) return fail(OVL_E_ARG, "ovl_index_build: key_bits=%d outside [2k, 64]", key_bits);
-    int passes = (key_bits + 7) / 8;
+    const int passes = sort_passes(key_bits);
+    const int D = sort_digit_bits(key_bits);
     int nl = 0;
     // ping-pong so that the last pass lands in (sorted_key, sorted_uid)
     uint64_t* kbuf[2] = {sorted_key, tmp_key};
@@ -191,59 +233,93 @@ int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len
     const uint64_t* src_key = prefix_key;
     const uint32_t* src_uid = nullptr;
     for (int p = 0; p < passes; ++p) {
-        int shift = 8 * p;
+        int shift = D * p;
+        int bits = std::min(D, key_bits - shift);
+        int64_t hn = ((int64_t)1 << bits) * W;
+        int32_t* pos_out = (p == passes - 1) ? pos_of : nullptr;
         if (p == 0) {
-            radix_hist_kernel<true><<<grid, kSortThreads, 0, st>>>(src_key, len, k, nullptr, U, shift, W, hist);
+            sort_hist_kernel<true><<<grid, kSortThreads, 0, st>>>(src_key, len, k, nullptr, U, shift, bits, W, hist);
         } else {
-            radix_hist_kernel<false><<<grid, kSortThreads, 0, st>>>(src_key, len, k, n_indexed, 0, shift, W, hist);
+            sort_hist_kernel<false><<<grid, kSortThreads, 0, st>>>(src_key, len, k, n_indexed, 0, shift, bits, W, hist);
         }
-        LAUNCH_CHECK("radix_hist_kernel");
-        CUDA_TRY((exclusive_scan<LoadArray<int32_t>, int32_t>(LoadArray<int32_t>{hist}, hist, 256 * W, sums, st, &nl)));
+        LAUNCH_CHECK("sort_hist_kernel");
+        CUDA_TRY((exclusive_scan<LoadArray<int32_t>, int32_t>(LoadArray<int32_t>{hist}, hist, hn, sums, st, &nl)));
         if (p == 0) {
-            radix_scatter_kernel<true><<<grid, kSortThreads, 0, st>>>(src_key, nullptr, len, k, nullptr, U, shift, W, hist,
-                                                                       kbuf[dst], ubuf[dst], n_indexed);
+            sort_scatter_kernel<true><<<grid, kSortThreads, 0, st>>>(src_key, nullptr, len, k, nullptr, U, shift, bits, W, hist,
+                                                                     kbuf[dst], ubuf[dst], pos_out, n_indexed);
         } else {
-            radix_scatter_kernel<false><<<grid, kSortThreads, 0, st>>>(src_key, src_uid, len, k, n_indexed, 0, shift, W, hist,
-                                                                        kbuf[dst], ubuf[dst], nullptr);
+            sort_scatter_kernel<false><<<grid, kSortThreads, 0, st>>>(src_key, src_uid, len, k, n_indexed, 0, shift, bits, W, hist,
+                                                                      kbuf[dst], ubuf[dst], pos_out, nullptr);
         }
-        LAUNCH_CHECK("radix_scatter_kernel");
+        LAUNCH_CHECK("sort_scatter_kernel");
         src_key = kbuf[dst];
         src_uid = ubuf[dst];
         dst ^= 1;
     }
     ctx->launches += nl;
+    if (table) {
+        bucket_table_kernel<<<grid_for(U + 1, 256), 256, 0, st>>>(sorted_key, n_indexed, key_bits - table_bits, table_bits, table);
+        LAUNCH_CHECK("bucket_table_kernel");
+    }
     return OVL_OK;
 }
 
 // ---------------------------------------------------------------- K3
-// workspace: [cnt int64 n][scan sums]
+// workspace: [cnt (int64 or 2 x int64) U][scan sums]
 size_t ovl_join_workspace_bytes(int64_t n_sources) {
     if (n_sources < 1) n_sources = 1;
-    return align256((size_t)n_sources * sizeof(int64_t)) + align256(scan_workspace_bytes(n_sources, sizeof(int64_t))) + 256;
+    return align256((size_t)n_sources * sizeof(I64x2)) + align256(scan_workspace_bytes(n_sources, sizeof(I64x2)) + scan_workspace_bytes(n_sources, sizeof(int64_t))) + 256;
 }
 
-int ovl_join_count(ovl_ctx* ctx, const uint64_t* suffix_key, const uint64_t* prefix_key, const int32_t* len, int32_t k,
-                   int64_t a_begin, int64_t a_end,
-                   const uint64_t* sorted_key, const uint32_t* sorted_uid, const int64_t* n_indexed, int32_t* bucket_lo,
-                   int32_t* self_rank, int64_t* pair_off, void* workspace, size_t workspace_bytes, void* stream) {
+int ovl_join_count(ovl_ctx* ctx, const uint64_t* suffix_key, const uint64_t* prefix_key, const int32_t* len, int32_t k, int64_t U,
+                   const uint64_t* sorted_key, const uint32_t* sorted_uid, const int64_t* n_indexed, const int32_t* table,
+                   int32_t table_bits, int32_t key_bits, const int32_t* pos_of, const int32_t* copies, int64_t* cum,
+                   int32_t* bucket_lo, int32_t* self_rank, int64_t* pair_off, int64_t* edge_base, void* workspace,
+                   size_t workspace_bytes, void* stream) {
     ON_CTX_DEVICE(ctx);
     if (!ctx || !suffix_key || !prefix_key || !len || !sorted_key || !sorted_uid || !n_indexed || !bucket_lo || !self_rank || !pair_off || !workspace)
         return fail(OVL_E_ARG, "ovl_join_count: null argument");
-    int64_t nA = a_end - a_begin;
-    if (nA < 0) return fail(OVL_E_ARG, "ovl_join_count: a_end < a_begin");
-    if (workspace_bytes < ovl_join_workspace_bytes(nA)) return fail(OVL_E_ARG, "ovl_join_count: workspace too small");
+    if (U < 0) return fail(OVL_E_ARG, "ovl_join_count: negative read count");
+    if (copies && (!cum || !edge_base)) return fail(OVL_E_ARG, "ovl_join_count: copies given without cum / edge_base");
+    if (workspace_bytes < ovl_join_workspace_bytes(U)) return fail(OVL_E_ARG, "ovl_join_count: workspace too small");
+    if (key_bits <= 0) key_bits = 2 * k;
+    if (table && (table_bits < 1 || table_bits > key_bits)) return fail(OVL_E_ARG, "ovl_join_count: table_bits=%d outside [1, key_bits]", table_bits);
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    int64_t* cnt = (int64_t*)ws;
-    void* sums = ws + align256((size_t)std::max<int64_t>(nA, 1) * sizeof(int64_t));
-    if (nA > 0) {
-        join_count_kernel<<<grid_for(nA, 256), 256, 0, st>>>(suffix_key, prefix_key, len, k, a_begin, a_end, sorted_key, sorted_uid,
-                                                              n_indexed, bucket_lo, self_rank, cnt);
+    void* cnt = ws;
+    void* sums = ws + align256((size_t)std::max<int64_t>(U, 1) * sizeof(I64x2));
+    int nl = 0;
+    if (copies) {
+        // copies along the sorted index, scanned: the copy mass of any bucket range is a difference of two entries
+        CUDA_TRY((exclusive_scan<SortedCopies, int64_t>(SortedCopies{sorted_uid, copies, n_indexed}, cum, U, sums, st, &nl)));
+    }
+    if (U > 0) {
+        join_count_kernel<<<grid_for(U, 256), 256, 0, st>>>(suffix_key, prefix_key, len, k, U, sorted_key, sorted_uid, n_indexed, table,
+                                                             table ? key_bits - table_bits : 0, pos_of, copies, cum, bucket_lo, self_rank,
+                                                             copies ? nullptr : (int64_t*)cnt, copies ? (I64x2*)cnt : nullptr);
         LAUNCH_CHECK("join_count_kernel");
     }
-    int nl = 0;
-    CUDA_TRY((exclusive_scan<LoadArray<int64_t>, int64_t>(LoadArray<int64_t>{cnt}, pair_off, nA, sums, st, &nl)));
+    if (copies) {
+        CUDA_TRY((exclusive_scan_to<LoadArray<I64x2>, StoreSplit, I64x2>(LoadArray<I64x2>{(const I64x2*)cnt}, StoreSplit{pair_off, edge_base}, U, sums, st, &nl)));
+    } else {
+        CUDA_TRY((exclusive_scan<LoadArray<int64_t>, int64_t>(LoadArray<int64_t>{(const int64_t*)cnt}, pair_off, U, sums, st, &nl)));
+    }
     ctx->launches += nl;
+    return OVL_OK;
+}
+
+int32_t ovl_totals_len(void) { return kTotalsLen; }
+
+int ovl_join_finalize(ovl_ctx* ctx, const int64_t* pair_off, const int64_t* edge_base, const int32_t* bucket_lo, const int32_t* self_rank,
+                      const int64_t* cum, const int32_t* copies, int64_t U, const int32_t* bad_count, const int64_t* n_indexed,
+                      int32_t rank, int32_t world, int64_t* totals, void* stream) {
+    ON_CTX_DEVICE(ctx);
+    if (!ctx || !pair_off || !totals) return fail(OVL_E_ARG, "ovl_join_finalize: null argument");
+    if (edge_base && (!bucket_lo || !self_rank || !cum || !copies)) return fail(OVL_E_ARG, "ovl_join_finalize: edge_base given without the join index");
+    if (world < 1 || rank < 0 || rank >= world) return fail(OVL_E_ARG, "ovl_join_finalize: rank %d outside world %d", rank, world);
+    JoinEdgeIndex jx{pair_off, edge_base, bucket_lo, self_rank, cum, 0, 0};
+    join_finalize_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(jx, copies, U, bad_count, n_indexed, rank, world, totals);
+    LAUNCH_CHECK("join_finalize_kernel");
     return OVL_OK;
 }
 
@@ -265,6 +341,84 @@ int ovl_join_fill(ovl_ctx* ctx, const int64_t* pair_off, int64_t a_begin, int64_
         LAUNCH_CHECK("join_fill_kernel");
     }
     return OVL_OK;
+}
+
+// ---------------------------------------------------------------- K0-K3 in one call
+// Everything between the ASCII reads and the sized pair list, launched back to back from C (the
+// per-call cost of going through Python for a dozen 5-50 us kernels was most of the stage's time).
+int ovl_candidates_layout(int64_t U, int32_t max_len, int32_t k, int32_t n_segments, int32_t has_copies, ovl_cand_layout* out) {
+    if (!out) return fail(OVL_E_ARG, "ovl_candidates_layout: out is null");
+    if (U < 0 || max_len < 0) return fail(OVL_E_ARG, "ovl_candidates_layout: negative size");
+    if (k < 1 || k > OVL_MAX_K) return fail(OVL_E_UNSUPPORTED, "ovl_candidates_layout: k=%d outside 1..%d", k, OVL_MAX_K);
+    if (max_len > OVL_MAX_LONG_READ_LEN) return fail(OVL_E_UNSUPPORTED, "read length %d exceeds the supported maximum %d", max_len, OVL_MAX_LONG_READ_LEN);
+    int seg_bits = 0;
+    if (n_segments > 1) while (((int64_t)1 << seg_bits) < n_segments) ++seg_bits;
+    int key_bits = 2 * k + seg_bits;
+    if (key_bits > 64) return fail(OVL_E_UNSUPPORTED, "k=%d with %d read sets needs %d key bits (> 64)", k, n_segments, key_bits);
+    memset(out, 0, sizeof(*out));
+    int64_t n = std::max<int64_t>(U, 1);
+    out->row_words = ovl_row_words(max_len);
+    out->key_bits = key_bits;
+    out->table_bits = ovl_index_table_bits(U, key_bits);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+    out->packed = take((size_t)n * out->row_words * 4 + 16);
+    out->len = take((size_t)n * 4);
+    out->bad = take(8);
+    out->n_indexed = take(8);
+    out->prefix_key = take((size_t)n * 8);
+    out->suffix_key = take((size_t)n * 8);
+    out->sorted_key = take((size_t)n * 8);
+    out->sorted_uid = take((size_t)n * 4);
+    out->table = take((((size_t)1 << out->table_bits) + 1) * 4);
+    out->pos_of = take((size_t)n * 4);
+    out->bucket_lo = take((size_t)n * 4);
+    out->self_rank = take((size_t)n * 4);
+    out->pair_off = take((size_t)(n + 1) * 8);
+    out->edge_base = has_copies ? take((size_t)(n + 1) * 8) : 0;
+    out->cum = has_copies ? take((size_t)(n + 1) * 8) : 0;
+    out->has_copies = has_copies ? 1 : 0;
+    out->scratch = off;
+    out->scratch_bytes = std::max(ovl_index_workspace_bytes(U), ovl_join_workspace_bytes(U));
+    off += align256(out->scratch_bytes);
+    out->total_bytes = off + 256;
+    return OVL_OK;
+}
+
+int ovl_candidates_build(ovl_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int64_t U, int32_t k, const int32_t* segments,
+                         const int32_t* copies, int32_t rank, int32_t world, void* arena, const ovl_cand_layout* lay, int64_t* totals,
+                         void* stream) {
+    ON_CTX_DEVICE(ctx);
+    if (!ctx || !arena || !lay || !totals || (U > 0 && (!ascii || !offsets))) return fail(OVL_E_ARG, "ovl_candidates_build: null argument");
+    if ((uintptr_t)arena & 255) return fail(OVL_E_ARG, "ovl_candidates_build: arena must be 256-byte aligned");
+    if ((copies != nullptr) != (lay->has_copies != 0)) return fail(OVL_E_ARG, "ovl_candidates_build: copies do not match the layout");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = (char*)arena;
+    uint32_t* packed = (uint32_t*)(base + lay->packed);
+    int32_t* len = (int32_t*)(base + lay->len);
+    int32_t* bad = (int32_t*)(base + lay->bad);
+    int64_t* n_indexed = (int64_t*)(base + lay->n_indexed);
+    uint64_t* pk = (uint64_t*)(base + lay->prefix_key);
+    uint64_t* sk = (uint64_t*)(base + lay->suffix_key);
+    uint64_t* skey = (uint64_t*)(base + lay->sorted_key);
+    uint32_t* suid = (uint32_t*)(base + lay->sorted_uid);
+    int32_t* table = (int32_t*)(base + lay->table);
+    int32_t* pos_of = (int32_t*)(base + lay->pos_of);
+    int32_t* lo = (int32_t*)(base + lay->bucket_lo);
+    int32_t* sr = (int32_t*)(base + lay->self_rank);
+    int64_t* pair_off = (int64_t*)(base + lay->pair_off);
+    int64_t* edge_base = copies ? (int64_t*)(base + lay->edge_base) : nullptr;
+    int64_t* cum = copies ? (int64_t*)(base + lay->cum) : nullptr;
+    void* scratch = base + lay->scratch;
+    CUDA_TRY(cudaMemsetAsync(bad, 0, 8, st));
+    int rc = pack_launch(ctx, ascii, offsets, U, lay->row_words, k, segments, packed, len, bad, pk, sk, st, "ovl_candidates_build");
+    if (rc != OVL_OK) return rc;
+    rc = ovl_index_build(ctx, pk, len, U, k, lay->key_bits, skey, suid, n_indexed, table, lay->table_bits, pos_of, scratch, lay->scratch_bytes, stream);
+    if (rc != OVL_OK) return rc;
+    rc = ovl_join_count(ctx, sk, pk, len, k, U, skey, suid, n_indexed, table, lay->table_bits, lay->key_bits, pos_of, copies, cum, lo, sr,
+                        pair_off, edge_base, scratch, lay->scratch_bytes, stream);
+    if (rc != OVL_OK) return rc;
+    return ovl_join_finalize(ctx, pair_off, edge_base, lo, sr, cum, copies, U, bad, n_indexed, rank, world, totals, stream);
 }
 
 int ovl_join_count_verify(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, int32_t k,
@@ -524,7 +678,7 @@ int ovl_overlap_dp(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, cons
                    int32_t* score, int32_t* end, int32_t mode, int32_t group_lanes, int32_t cols_per_lane, void* stream) {
     ON_CTX_DEVICE(ctx);
     if (P > 0 && (!score || !end)) return fail(OVL_E_ARG, "ovl_overlap_dp: null output");
-    DpEdgeOut eo{nullptr, nullptr, nullptr, nullptr};
+    DpEdgeOut eo{nullptr, nullptr, nullptr, nullptr, JoinEdgeIndex{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0}};
     return dp_dispatch(ctx, packed, row_words, len, pair_a, pair_b, P, max_len, match, mismatch, indel, score, end, eo,
                        mode, group_lanes, cols_per_lane, stream, "ovl_overlap_dp");
 }
@@ -537,7 +691,7 @@ int ovl_overlap_dp8(ovl_ctx* ctx, const uint8_t* rows, int32_t row_words, const 
     if (P > 0 && !edges && (!score || !end)) return fail(OVL_E_ARG, "ovl_overlap_dp8: null output");
     if ((uintptr_t)edges & 15) return fail(OVL_E_ARG, "ovl_overlap_dp8: edges must be 16-byte aligned");
     if (copies && (!node_off || !edge_off)) return fail(OVL_E_ARG, "ovl_overlap_dp8: copies given without node_off / edge_off");
-    DpEdgeOut eo{(int4*)edges, copies, node_off, edge_off};
+    DpEdgeOut eo{(int4*)edges, copies, node_off, edge_off, JoinEdgeIndex{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0}};
     return dp_dispatch(ctx, (const uint32_t*)rows, row_words, len, pair_a, pair_b, P, max_len, match, mismatch, indel, score, end, eo,
                        0, 0, 0, stream, "ovl_overlap_dp8", 8);
 }
@@ -550,9 +704,24 @@ int ovl_overlap_dp_edges(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words
     if (P > 0 && !edges) return fail(OVL_E_ARG, "ovl_overlap_dp_edges: null output");
     if ((uintptr_t)edges & 15) return fail(OVL_E_ARG, "ovl_overlap_dp_edges: edges must be 16-byte aligned");
     if (copies && (!node_off || !edge_off)) return fail(OVL_E_ARG, "ovl_overlap_dp_edges: copies given without node_off / edge_off");
-    DpEdgeOut eo{(int4*)edges, copies, node_off, edge_off};
+    DpEdgeOut eo{(int4*)edges, copies, node_off, edge_off, JoinEdgeIndex{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0}};
     return dp_dispatch(ctx, packed, row_words, len, pair_a, pair_b, P, max_len, match, mismatch, indel, nullptr, nullptr, eo,
                        0, 0, 0, stream, "ovl_overlap_dp_edges");
+}
+
+int ovl_overlap_dp_edges_join(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, const int32_t* pair_a,
+                              const int32_t* pair_b, int64_t P, int32_t max_len, int64_t match, int64_t mismatch, int64_t indel,
+                              const int32_t* copies, const int64_t* node_off, const int64_t* pair_off, const int64_t* edge_base,
+                              const int32_t* bucket_lo, const int32_t* self_rank, const int64_t* cum, int64_t p_begin,
+                              int64_t e_begin, int32_t* edges, void* stream) {
+    ON_CTX_DEVICE(ctx);
+    if (P > 0 && !edges) return fail(OVL_E_ARG, "ovl_overlap_dp_edges_join: null output");
+    if ((uintptr_t)edges & 15) return fail(OVL_E_ARG, "ovl_overlap_dp_edges_join: edges must be 16-byte aligned");
+    if (!copies || !node_off || !pair_off || !edge_base || !bucket_lo || !self_rank || !cum)
+        return fail(OVL_E_ARG, "ovl_overlap_dp_edges_join: null join index");
+    DpEdgeOut eo{(int4*)edges, copies, node_off, nullptr, JoinEdgeIndex{pair_off, edge_base, bucket_lo, self_rank, cum, p_begin, e_begin}};
+    return dp_dispatch(ctx, packed, row_words, len, pair_a, pair_b, P, max_len, match, mismatch, indel, nullptr, nullptr, eo,
+                       0, 0, 0, stream, "ovl_overlap_dp_edges_join");
 }
 
 // ---------------------------------------------------------------- byte-coded reads (any alphabet)

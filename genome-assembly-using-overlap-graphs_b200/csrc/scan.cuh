@@ -31,11 +31,11 @@ template <> struct ScanTraits<I64x2> {
         return I64x2{__shfl_up_sync(kFull, v.x, d), __shfl_up_sync(kFull, v.y, d)};
     }
 };
-template <typename T> constexpr int scan_tile() { return kScanThreads * ScanTraits<T>::items; }
+template <typename T> __host__ __device__ constexpr int scan_tile() { return kScanThreads * ScanTraits<T>::items; }
 // shared-memory slot of tile element j: one pad element per 16, so that the blocked accesses
 // (stride 16 elements across a warp) spread over the banks
 __device__ __forceinline__ int scan_slot(int j) { return j + (j >> 4); }
-template <typename T> constexpr int scan_smem_elems() { return scan_tile<T>() + scan_tile<T>() / 16 + 1; }
+template <typename T> __host__ __device__ constexpr int scan_smem_elems() { return scan_tile<T>() + scan_tile<T>() / 16 + 1; }
 
 template <typename TI>
 struct LoadArray {

@@ -41,6 +41,40 @@ class KmerIndex:
     sorted_key: torch.Tensor
     sorted_uid: torch.Tensor      # int32 view of uint32[U]
     n_indexed: torch.Tensor       # int64[1]
+    key_bits: int = 0             # significant key bits (2k + read-set tag bits); 64 for hashed keys
+    table: Optional[torch.Tensor] = None      # int32[2^table_bits + 1] direct-address bucket table, or None
+    table_bits: int = 0
+    pos_of: Optional[torch.Tensor] = None     # int32[U] sorted position of every indexed read, or None
+
+
+@dataclass
+class Candidates:
+    """Result of the K0-K3 job (build_candidates): packed reads, index, per-source join arrays and the
+    scalars the host read back in one sync."""
+    rs: ReadSet
+    index: KmerIndex
+    bucket_lo: torch.Tensor       # int32[U]
+    self_rank: torch.Tensor       # int32[U]
+    pair_off: torch.Tensor        # int64[U+1]
+    edge_base: Optional[torch.Tensor]     # int64[U+1] when reads have copies
+    cum: Optional[torch.Tensor]           # int64[U+1] copies scanned along the sorted index
+    copies: Optional[torch.Tensor]
+    node_off: Optional[torch.Tensor]
+    total_pairs: int
+    total_edges: int
+    p_begin: int                  # this rank's slice of the pair list
+    p_end: int
+    cut_pairs: list               # 65 pair indices cutting the slice into 64 equal parts ...
+    cut_edges: list               # ... and the first edge row of each
+    arena: torch.Tensor
+
+    @property
+    def e_begin(self) -> int:
+        return self.cut_edges[0]
+
+    @property
+    def e_end(self) -> int:
+        return self.cut_edges[-1]
 
 
 def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
@@ -64,6 +98,8 @@ class OverlapEngine:
         # one engine per device is shared by the whole process and hands out views of ONE pinned result
         # buffer: callers that consume such a view (the graph builders) hold this lock while they do
         self.lock = threading.RLock()
+        # the scalars of the K0-K3 job land here (page-locked, written by the device, read after one event wait)
+        self._totals = torch.zeros(int(nat.lib.ovl_totals_len()), dtype=torch.int64).pin_memory()
 
     @property
     def launches(self) -> int:
@@ -105,6 +141,11 @@ class OverlapEngine:
     # ------------------------------------------------------------------ K0
     def upload_reads(self, bases, offsets, max_len: Optional[int] = None, code_bits: int = 2) -> ReadSet:
         """bases: uint8[sum len] ASCII, offsets: int64[U+1] (NumPy or CPU/GPU torch tensors)."""
+        ascii_dev, off_dev, U, max_len = self._upload_ascii(bases, offsets, max_len)
+        return self.pack_reads(ascii_dev, off_dev, U, max_len, code_bits)
+
+    def _upload_ascii(self, bases, offsets, max_len: Optional[int] = None):
+        """Host (or device) reads -> (ascii_dev with slack, off_dev, U, max_len)."""
         off_host = None
         if isinstance(offsets, np.ndarray):
             off_host = offsets
@@ -123,7 +164,7 @@ class OverlapEngine:
             src = self._from_numpy(bases) if isinstance(bases, np.ndarray) else bases
             ascii_dev[:total].copy_(src[:total], non_blocking=True)
         off_dev = self._to_device(offsets, torch.int64)
-        return self.pack_reads(ascii_dev, off_dev, U, max_len, code_bits)
+        return ascii_dev, off_dev, U, max_len
 
     def pack_reads(self, ascii_dev: torch.Tensor, off_dev: torch.Tensor, U: int, max_len: int,
                    code_bits: int = 2) -> ReadSet:
@@ -196,9 +237,18 @@ class OverlapEngine:
         n_indexed = torch.zeros(1, dtype=torch.int64, device=self.device)
         ws_bytes = int(nat.lib.ovl_index_workspace_bytes(U))
         ws = self._empty(ws_bytes, torch.uint8)
+        kb = key_bits if key_bits else 2 * k
+        table = pos_of = None
+        table_bits = 0
+        if not hashed:
+            # direct-address bucket table + every read's own slot: the join then needs no search
+            table_bits = int(nat.lib.ovl_index_table_bits(U, kb))
+            table = self._empty((1 << table_bits) + 1, torch.int32)
+            pos_of = self._empty(U, torch.int32)
         nat.check(nat.lib.ovl_index_build(self._ctx, _ptr(pk), _ptr(rs.length), U, k, key_bits, _ptr(sorted_key), _ptr(sorted_uid),
-                                          _ptr(n_indexed), _ptr(ws), ws_bytes, self._stream()))
-        return KmerIndex(k, pk, sk, sorted_key, sorted_uid, n_indexed)
+                                          _ptr(n_indexed), _ptr(table), table_bits, _ptr(pos_of), _ptr(ws), ws_bytes,
+                                          self._stream()))
+        return KmerIndex(k, pk, sk, sorted_key, sorted_uid, n_indexed, kb, table, table_bits, pos_of)
 
     def _check_fits(self, pairs: int, what: str) -> None:
         """Refuse loudly (instead of running the GPU out of memory) when the pair list, its edge
@@ -241,9 +291,11 @@ class OverlapEngine:
         ws_bytes = int(nat.lib.ovl_join_workspace_bytes(U))
         ws = self._empty(ws_bytes, torch.uint8)
         nat.check(nat.lib.ovl_join_count(self._ctx, _ptr(index.suffix_key), _ptr(index.prefix_key),
-                                         _ptr(rs.length), k, 0, U,
+                                         _ptr(rs.length), k, U,
                                          _ptr(index.sorted_key), _ptr(index.sorted_uid), _ptr(index.n_indexed),
-                                         _ptr(lo), _ptr(self_rank), _ptr(pair_off), _ptr(ws), ws_bytes, st))
+                                         _ptr(index.table), index.table_bits, index.key_bits, _ptr(index.pos_of),
+                                         None, None, _ptr(lo), _ptr(self_rank), _ptr(pair_off), None,
+                                         _ptr(ws), ws_bytes, st))
         total = self._total_and_alphabet(rs, pair_off[U])    # host sync: the output size
         p_begin, p_end = total * rank // world, total * (rank + 1) // world
         P = p_end - p_begin
@@ -281,6 +333,166 @@ class OverlapEngine:
                                                    _ptr(index.sorted_uid), _ptr(index.n_indexed), _ptr(pair_off),
                                                    p_begin, P, _ptr(pair_a), _ptr(pair_b), st))
         return pair_a[:P], pair_b[:P], p_begin
+
+    # ------------------------------------------------------------------ K0-K3 as one job
+    def composite_ok(self, k: int, code_bits: int = 2) -> bool:
+        """The one-call K0-K3 job covers 2-bit packed reads with 1 <= k <= OVL_MAX_K."""
+        return code_bits == 2 and 1 <= k <= nat.OVL_MAX_K
+
+    def build_candidates(self, ascii_dev: torch.Tensor, off_dev: torch.Tensor, U: int, max_len: int, k: int,
+                         copies: Optional[torch.Tensor] = None, node_off: Optional[torch.Tensor] = None,
+                         shard: Tuple[int, int] = (0, 1), segments: Optional[torch.Tensor] = None,
+                         n_segments: int = 1) -> Candidates:
+        """ASCII reads in HBM -> everything up to the SIZED pair list, in ONE library call
+        (ovl_candidates_build: pack + keys, index + bucket table, join count, totals) and ONE host
+        sync: the totals land in page-locked memory and the host waits on an event.  Raises
+        OvlBadAlphabet before anything is sized on mis-coded rows."""
+        lay = nat.CandLayout()
+        nat.check(nat.lib.ovl_candidates_layout(U, max_len, k, int(n_segments) if segments is not None else 1,
+                                                1 if copies is not None else 0, ctypes.byref(lay)))
+        arena = torch.empty(int(lay.total_bytes), dtype=torch.uint8, device=self.device)
+        rank, world = shard
+        nat.check(nat.lib.ovl_candidates_build(self._ctx, _ptr(ascii_dev), _ptr(off_dev), U, k, _ptr(segments), _ptr(copies),
+                                               int(rank), int(world), _ptr(arena), ctypes.byref(lay),
+                                               ctypes.c_void_p(self._totals.data_ptr()), self._stream()))
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+        n = max(U, 1)
+
+        def view(off, count, dtype):
+            nbytes = count * torch.empty(0, dtype=dtype).element_size()
+            return arena[off:off + nbytes].view(dtype)
+
+        rs = ReadSet(arena[lay.packed:lay.packed + n * lay.row_words * 4 + 16], view(lay.len, n, torch.int32),
+                     view(lay.bad, 1, torch.int32), int(lay.row_words), U, max_len)
+        index = KmerIndex(k, view(lay.prefix_key, n, torch.int64), view(lay.suffix_key, n, torch.int64),
+                          view(lay.sorted_key, n, torch.int64), view(lay.sorted_uid, n, torch.int32),
+                          view(lay.n_indexed, 1, torch.int64), int(lay.key_bits),
+                          view(lay.table, (1 << lay.table_bits) + 1, torch.int32), int(lay.table_bits),
+                          view(lay.pos_of, n, torch.int32))
+        has = copies is not None
+        done.synchronize()                                            # the one host sync of the job
+        t = self._totals.tolist()
+        if t[2] != 0:
+            raise nat.OvlBadAlphabet("reads contain characters other than A, C, G, T; "
+                                     "the 2-bit CUDA path does not support them")
+        nc = 65
+        return Candidates(rs, index, view(lay.bucket_lo, n, torch.int32), view(lay.self_rank, n, torch.int32),
+                          view(lay.pair_off, n + 1, torch.int64),
+                          view(lay.edge_base, n + 1, torch.int64) if has else None,
+                          view(lay.cum, n + 1, torch.int64) if has else None,
+                          copies, node_off, int(t[0]), int(t[1]), int(t[3]), int(t[4]),
+                          [int(x) for x in t[8:8 + nc]], [int(x) for x in t[8 + nc:8 + 2 * nc]], arena)
+
+    def fill_pairs(self, cand: Candidates) -> Tuple[torch.Tensor, torch.Tensor]:
+        """This rank's slice of the ordered candidate list (overlapGraphs.py:43-52)."""
+        P = cand.p_end - cand.p_begin
+        self._check_fits(P, f"k = {cand.index.k}")
+        pair_a = self._empty(P, torch.int32)
+        pair_b = self._empty(P, torch.int32)
+        if P:
+            nat.check(nat.lib.ovl_join_fill(self._ctx, _ptr(cand.pair_off), 0, cand.rs.n_reads, _ptr(cand.bucket_lo),
+                                            _ptr(cand.self_rank), _ptr(cand.index.sorted_uid), cand.p_begin, P,
+                                            cand.total_pairs, _ptr(pair_a), _ptr(pair_b), self._stream()))
+        return pair_a[:P], pair_b[:P]
+
+    def _dp_edges_join_call(self, cand: Candidates, a_ptr, b_ptr, P: int, p_begin: int, e_begin: int, scoring, out_ptr, st):
+        """DP + fused edge expansion with the row offsets taken from the join index (no per-pair offset array)."""
+        match_score, mismatch, indel = scoring
+        rs = cand.rs
+        nat.check(nat.lib.ovl_overlap_dp_edges_join(self._ctx, _ptr(rs.packed), rs.row_words, _ptr(rs.length), a_ptr, b_ptr, P,
+                                                    rs.max_len, int(match_score), int(mismatch), int(indel),
+                                                    _ptr(cand.copies), _ptr(cand.node_off), _ptr(cand.pair_off),
+                                                    _ptr(cand.edge_base), _ptr(cand.bucket_lo), _ptr(cand.self_rank),
+                                                    _ptr(cand.cum), int(p_begin), int(e_begin), out_ptr, st))
+
+    def candidate_edges(self, cand: Candidates, pair_a: torch.Tensor, pair_b: torch.Tensor,
+                        match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT,
+                        events=None, sink=None) -> Optional[torch.Tensor]:
+        """DP + edge expansion (overlapGraphs.py:53-60) over this rank's slice of a build_candidates job:
+        device edge rows, or -- with `sink` -- rows stored wherever sink(E) points (peer memory)."""
+        P = int(pair_a.shape[0])
+        E = cand.e_end - cand.e_begin
+        st = self._stream()
+        if P == 0:
+            if sink is not None:
+                sink(0, cand.e_begin, cand.total_edges)
+            return torch.empty((0, 4), dtype=torch.int32, device=self.device)
+        if sink is not None:
+            # every rank knows its global row offset from the join index: no size exchange
+            edges = None
+            out_ptr = ctypes.c_void_p(int(sink(E, cand.e_begin, cand.total_edges)))
+        else:
+            edges = self._empty(E * 4, torch.int32)
+            out_ptr = _ptr(edges)
+        if events is not None:
+            events[0].record()
+        if cand.edge_base is not None:
+            self._dp_edges_join_call(cand, _ptr(pair_a), _ptr(pair_b), P, cand.p_begin, cand.e_begin,
+                                     (match_score, mismatch, indel), out_ptr, st)
+        else:
+            self._dp_edges_call(cand.rs, _ptr(pair_a), _ptr(pair_b), P, (match_score, mismatch, indel), None, None,
+                                ctypes.c_void_p(0), out_ptr, st)
+        if events is not None:
+            events[1].record()
+        return None if edges is None else edges[:E * 4].view(E, 4)
+
+    def candidate_edges_to_host(self, cand: Candidates, pair_a: torch.Tensor, pair_b: torch.Tensor,
+                                match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT,
+                                chunk_pairs: int = 48_000_000, host_sink=None) -> np.ndarray:
+        """The same with the device->host copy of the edge rows overlapped with the DP: the slice is cut at
+        the boundaries the job already computed (cand.cut_pairs / cut_edges), each chunk's rows are copied
+        to the pinned host buffer on a second stream while the next chunk computes."""
+        P = int(pair_a.shape[0])
+        if P == 0:
+            if host_sink is not None:
+                host_sink(0, cand.e_begin, cand.total_edges)
+            return np.zeros((0, 4), np.int32)
+        main = torch.cuda.current_stream(self.device)
+        st = self._stream()
+        n_chunks = max(1, min(64, (P + chunk_pairs - 1) // chunk_pairs))
+        if P >= 1_000_000:
+            n_chunks = max(n_chunks, 8)        # even a few-ms job hides most of its copy behind the DP
+        n_chunks = 1 << (n_chunks - 1).bit_length()          # 1, 2, 4, ... 64: a subset of the 64 computed cuts
+        step = 64 // n_chunks
+        bounds = [cand.cut_pairs[i * step] - cand.p_begin for i in range(n_chunks + 1)]
+        e_bounds = [cand.cut_edges[i * step] - cand.e_begin for i in range(n_chunks + 1)]
+        E = e_bounds[-1]
+        edges = self._empty(E * 4, torch.int32).view(-1, 4)
+        host = host_sink(E, cand.e_begin, cand.total_edges) if host_sink is not None else self._host_rows(E)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(self.device)
+        scoring = (match_score, mismatch, indel)
+        for c in range(n_chunks):
+            p0, p1 = bounds[c], bounds[c + 1]
+            if p1 == p0:
+                continue
+            e0, e1 = e_bounds[c], e_bounds[c + 1]
+            a_ptr = ctypes.c_void_p(pair_a.data_ptr() + 4 * p0)
+            b_ptr = ctypes.c_void_p(pair_b.data_ptr() + 4 * p0)
+            out_ptr = ctypes.c_void_p(edges.data_ptr() + 16 * e0)
+            if cand.edge_base is not None:
+                self._dp_edges_join_call(cand, a_ptr, b_ptr, p1 - p0, cand.p_begin + p0, cand.e_begin + e0, scoring, out_ptr, st)
+            else:
+                self._dp_edges_call(cand.rs, a_ptr, b_ptr, p1 - p0, scoring, None, None, ctypes.c_void_p(0), out_ptr, st)
+            done = torch.cuda.Event()
+            done.record(main)
+            if e1 > e0:
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(done)
+                    host[e0:e1].copy_(edges[e0:e1], non_blocking=True)
+        self._copy_stream.synchronize()
+        main.wait_stream(self._copy_stream)
+        edges.record_stream(self._copy_stream)
+        return host.numpy()
+
+    def _host_rows(self, E: int, host_sink=None) -> torch.Tensor:
+        """Page-locked destination for E edge rows: the caller's sink or the engine's reusable buffer."""
+        if host_sink is not None:
+            return host_sink(E)
+        if self._pinned_out is None or self._pinned_out.shape[0] < max(E, 1):
+            self._pinned_out = torch.empty((max(E, 1) * 5 // 4 + 16, 4), dtype=torch.int32).pin_memory()
+        return self._pinned_out[:E]
 
     # ------------------------------------------------------------------ K4 / K5
     def overlap_scores(self, rs: ReadSet, pair_a: torch.Tensor, pair_b: torch.Tensor,
@@ -585,7 +797,6 @@ class OverlapEngine:
         insertion order.  This is the call the drop-in graph builder makes."""
         if k < 0:
             raise AssertionError("k-mer length must be non-negative")      # overlapGraphs.py:17
-        rs = self.upload_reads(bases, offsets, code_bits=code_bits)
         copies = node_off = None
         if counts is not None:
             counts_np = counts if isinstance(counts, np.ndarray) else counts.numpy()
@@ -594,6 +805,26 @@ class OverlapEngine:
                 np.cumsum(counts_np, out=no[1:])
                 copies = self._to_device(counts_np, torch.int32)
                 node_off = self._to_device(no, torch.int64)
+        if pairs is None and self.composite_ok(k, code_bits):
+            # the common call: K0-K3 as one job, one host sync, then fill + DP (+ D2H overlapped with the DP)
+            ascii_dev, off_dev, U, max_len = self._upload_ascii(bases, offsets)
+            seg_dev = self._to_device(segments, torch.int32) if segments is not None else None
+            cand = self.build_candidates(ascii_dev, off_dev, U, max_len, k, copies, node_off, shard, seg_dev, n_segments)
+            pa, pb = self.fill_pairs(cand)
+            if stats is not None:
+                stats["pairs"], stats["edges"] = int(pa.shape[0]), cand.e_end - cand.e_begin
+                stats["pair_a"], stats["pair_b"] = pa, pb
+            if to_host and min_weight is None:
+                host = self.candidate_edges_to_host(cand, pa, pb, match_score, mismatch, indel, host_sink=host_sink)
+                return host if (reuse_host_buffer or host_sink is not None) else host.copy()
+            edges = self.candidate_edges(cand, pa, pb, match_score, mismatch, indel)
+            if min_weight is not None:
+                edges = self.filter_edges(edges, min_weight)
+            if not to_host:
+                return edges
+            host = self.to_pinned_host(edges)
+            return host if reuse_host_buffer else host.copy()
+        rs = self.upload_reads(bases, offsets, code_bits=code_bits)
         if pairs is not None:        # caller-supplied unique-read index pairs instead of the k-mer join
             self.check_alphabet(rs)
             pa = self._to_device(pairs[0], torch.int32)

@@ -121,13 +121,27 @@ class SharedEdgeSink:
         self.capacity = rows
         dist.barrier(group=self.group)
 
-    def __call__(self, n_local: int) -> torch.Tensor:
-        sizes = [None] * self.world
-        dist.all_gather_object(sizes, int(n_local), group=self.group)
-        self.total = int(sum(sizes))
+    def __call__(self, n_local: int, e_begin: Optional[int] = None, total: Optional[int] = None) -> torch.Tensor:
+        """The slice this rank must fill.  With (e_begin, total) -- the global row offset of the rank's slice
+        and the global row count, both known to every rank from the join index -- no communication is
+        needed (a re-size is collective, but every rank sees the same `total` and takes it together);
+        otherwise the row counts are exchanged (one all_gather of an int64 per rank)."""
+        if e_begin is None or total is None:
+            sizes = torch.zeros(self.world, dtype=torch.int64)
+            mine = torch.tensor([int(n_local)], dtype=torch.int64)
+            if self.cuda and dist.get_backend(self.group) == "nccl":
+                dev = torch.device("cuda", torch.cuda.current_device())
+                sizes_d = sizes.to(dev)
+                dist.all_gather_into_tensor(sizes_d, mine.to(dev), group=self.group)
+                sizes = sizes_d.cpu()
+            else:
+                dist.all_gather_into_tensor(sizes, mine, group=self.group)
+            sizes = sizes.tolist()
+            total = int(sum(sizes))
+            e_begin = int(sum(sizes[:self.rank]))
+        self.total = int(total)
         self._ensure(self.total)
-        off = int(sum(sizes[:self.rank]))
-        return self.tensor[off:off + int(n_local)]
+        return self.tensor[int(e_begin):int(e_begin) + int(n_local)]
 
     def rows(self):
         """NumPy view of the complete list (meaningful on every rank after a barrier)."""
@@ -162,14 +176,20 @@ class PeerEdgeBuffer:
         self.total = 0
         self._sizes = torch.zeros(self.world, dtype=torch.int64, device=device)
 
-    def slot(self, n_local: int) -> int:
-        n = torch.tensor([int(n_local)], dtype=torch.int64, device=self.local.device)
-        dist.all_gather_into_tensor(self._sizes, n, group=self.group)
-        sizes = self._sizes.cpu().tolist()
-        self.total = int(sum(sizes))
+    def slot(self, n_local: int, e_begin: Optional[int] = None, total: Optional[int] = None) -> int:
+        """Device address (inside the destination rank's buffer) of this rank's first row.  With
+        (e_begin, total) from the join index no communication is needed; otherwise the row counts are
+        exchanged first."""
+        if e_begin is None or total is None:
+            n = torch.tensor([int(n_local)], dtype=torch.int64, device=self.local.device)
+            dist.all_gather_into_tensor(self._sizes, n, group=self.group)
+            sizes = self._sizes.cpu().tolist()
+            total = int(sum(sizes))
+            e_begin = int(sum(sizes[:self.rank]))
+        self.total = int(total)
         if self.total > self.capacity:
             raise RuntimeError(f"peer edge buffer too small: {self.total} rows > capacity {self.capacity}")
-        return self.dst_ptr + 16 * int(sum(sizes[:self.rank]))
+        return self.dst_ptr + 16 * int(e_begin)
 
     def barrier(self) -> None:
         """All ranks' kernels have finished storing (stream-ordered) and the stores are visible."""

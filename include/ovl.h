@@ -79,28 +79,64 @@ int ovl_kmer_keys(ovl_ctx *ctx, const uint32_t *packed, int32_t row_words, const
 int ovl_kmer_hashes(ovl_ctx *ctx, const uint32_t *packed, int32_t row_words, const int32_t *len,
                     int64_t U, int32_t k, uint64_t *prefix_hash, uint64_t *suffix_hash, void *stream);
 
+/* K0 + K1 in one pass: the thread that packs a read's first / last bases also emits its prefix /
+ * suffix k-mer key (1 <= k <= OVL_MAX_K; segment as in ovl_kmer_keys). */
+int ovl_pack_reads_keys(ovl_ctx *ctx, const uint8_t *ascii, const int64_t *offsets, int64_t U,
+                        int32_t row_words, int32_t k, const int32_t *segment, uint32_t *packed,
+                        int32_t *len, int32_t *bad_count, uint64_t *prefix_key, uint64_t *suffix_key,
+                        void *stream);
+
 /* K2: the prefix index, overlapGraphs.py:30-40, as a stable sort of (prefix_key, uid):
  * sorted_key / sorted_uid hold the *n_indexed reads with len >= k, keys ascending and uids
- * ascending inside equal keys (the reference's bucket-append order). */
+ * ascending inside equal keys (the reference's bucket-append order).  LSD radix sort with digits of
+ * up to 10 bits: one pass for k <= 5, two for k <= 10.
+ * Optional outputs (NULL to skip):
+ *   table   int32[2^table_bits + 1], a direct-address bucket table over the top table_bits bits of the
+ *           key: table[t] = first sorted position whose key >> (key_bits - table_bits) is >= t.  With
+ *           table_bits == key_bits (4^k <= 2^22) a bucket is table[key] .. table[key + 1] -- the
+ *           dict lookup of overlapGraphs.py:49 without any search.  ovl_index_table_bits gives the
+ *           size this library picks for (U, key_bits).
+ *   pos_of  int32[U]: sorted position of every indexed read (its own slot in its bucket). */
 size_t ovl_index_workspace_bytes(int64_t U);
+int32_t ovl_index_table_bits(int64_t U, int32_t key_bits);
 /* key_bits: number of significant key bits to sort on (2k + segment-tag bits); 0 means 2k. */
 int ovl_index_build(ovl_ctx *ctx, const uint64_t *prefix_key, const int32_t *len, int64_t U, int32_t k,
                     int32_t key_bits, uint64_t *sorted_key, uint32_t *sorted_uid, int64_t *n_indexed,
+                    int32_t *table, int32_t table_bits, int32_t *pos_of,
                     void *workspace, size_t workspace_bytes, void *stream);
 
-/* K3: candidate generation, overlapGraphs.py:43-52, for source reads a in [a_begin, a_end).
+/* K3: candidate generation, overlapGraphs.py:43-52, for all source reads a in [0, U).
  * ovl_join_count writes, per a, the bucket start, a's own rank inside the bucket (-1 if it
- * is not in it) and the exclusive scan pair_off[(a_end-a_begin)+1] of the candidate counts;
- * pair_off[last] is the number of pairs.  ovl_join_fill then writes pairs
- * [p_begin, p_begin+p_count) of that range, ordered by (a, b) ascending.  total_hint = the
- * total number of pairs of the range (pair_off[last], which the host has read anyway): it
+ * is not in it) and the exclusive scan pair_off[U+1] of the candidate counts; pair_off[U] is the
+ * number of pairs.  table / pos_of (from ovl_index_build) are optional: without them the bucket
+ * and the own slot are found by binary search.
+ * With duplicate reads (copies != NULL; overlapGraphs.py:55-60 expands pair (a, b) to
+ * copies[a] * copies[b] edges) it also writes cum[U+1], the exclusive scan of copies along the sorted
+ * index, and edge_base[U+1], the exclusive scan of the per-source edge counts: together with
+ * bucket_lo / self_rank they give the first edge row of ANY pair in O(1), so no per-pair offset array
+ * is ever built (ovl_overlap_dp_edges_join).
+ * ovl_join_fill then writes pairs [p_begin, p_begin+p_count), ordered by (a, b) ascending.
+ * total_hint = the total number of pairs (pair_off[U], which the host has read anyway): it
  * only selects between the thread-per-pair and the warp-per-source fill kernels. */
 size_t ovl_join_workspace_bytes(int64_t n_sources);
 int ovl_join_count(ovl_ctx *ctx, const uint64_t *suffix_key, const uint64_t *prefix_key,
-                   const int32_t *len, int32_t k, int64_t a_begin, int64_t a_end, const uint64_t *sorted_key,
-                   const uint32_t *sorted_uid, const int64_t *n_indexed, int32_t *bucket_lo,
-                   int32_t *self_rank, int64_t *pair_off, void *workspace, size_t workspace_bytes,
-                   void *stream);
+                   const int32_t *len, int32_t k, int64_t U, const uint64_t *sorted_key,
+                   const uint32_t *sorted_uid, const int64_t *n_indexed, const int32_t *table,
+                   int32_t table_bits, int32_t key_bits, const int32_t *pos_of, const int32_t *copies,
+                   int64_t *cum, int32_t *bucket_lo, int32_t *self_rank, int64_t *pair_off,
+                   int64_t *edge_base, void *workspace, size_t workspace_bytes, void *stream);
+/* The scalars the host needs before it can size anything, in ONE block of ovl_totals_len() int64
+ * words written by one small kernel (totals may be page-locked host memory: the host then needs a
+ * stream/event wait and no copy): [0] pairs, [1] edge rows, [2] *bad_count, [3],[4] this rank's
+ * slice [p_begin, p_end) of the pair list (rank of world equal slices), [5] *n_indexed,
+ * [8 .. 8+64] pair indices cutting the slice into 64 equal parts, [73 .. 73+64] the first edge row
+ * of each of those pairs (D2H chunk boundaries, shard boundaries). */
+int32_t ovl_totals_len(void);
+int ovl_join_finalize(ovl_ctx *ctx, const int64_t *pair_off, const int64_t *edge_base,
+                      const int32_t *bucket_lo, const int32_t *self_rank, const int64_t *cum,
+                      const int32_t *copies, int64_t U, const int32_t *bad_count,
+                      const int64_t *n_indexed, int32_t rank, int32_t world, int64_t *totals,
+                      void *stream);
 int ovl_join_fill(ovl_ctx *ctx, const int64_t *pair_off, int64_t a_begin, int64_t a_end,
                   const int32_t *bucket_lo, const int32_t *self_rank, const uint32_t *sorted_uid,
                   int64_t p_begin, int64_t p_count, int64_t total_hint, int32_t *pair_a,
@@ -120,6 +156,23 @@ int ovl_join_fill_verify(ovl_ctx *ctx, const uint32_t *packed, int32_t row_words
  * counts from a_begin: a = a_begin + p / (U-1). */
 int ovl_all_pairs_fill(ovl_ctx *ctx, int64_t U, int64_t a_begin, int64_t p_begin, int64_t p_count,
                        int32_t *pair_a, int32_t *pair_b, void *stream);
+
+/* K0-K3 in one call (2-bit reads, 1 <= k <= OVL_MAX_K): pack + keys, index + table, join count,
+ * totals -- a dozen kernels launched back to back on `stream`, all arrays carved out of one
+ * caller-owned arena.  ovl_candidates_layout fills the byte offsets (and the sizes it chose);
+ * arena must be 256-byte aligned and lay->total_bytes long.  After the call (and a wait on the
+ * stream) `totals` holds the block described at ovl_join_finalize; the caller then sizes the pair
+ * list and calls ovl_join_fill / ovl_overlap_dp_edges[_join] on the arrays inside the arena. */
+typedef struct ovl_cand_layout {
+    size_t packed, len, bad, n_indexed, prefix_key, suffix_key, sorted_key, sorted_uid, table, pos_of,
+           bucket_lo, self_rank, pair_off, edge_base, cum, scratch, scratch_bytes, total_bytes;
+    int32_t row_words, key_bits, table_bits, has_copies;
+} ovl_cand_layout;
+int ovl_candidates_layout(int64_t U, int32_t max_len, int32_t k, int32_t n_segments, int32_t has_copies,
+                          ovl_cand_layout *out);
+int ovl_candidates_build(ovl_ctx *ctx, const uint8_t *ascii, const int64_t *offsets, int64_t U, int32_t k,
+                         const int32_t *segments, const int32_t *copies, int32_t rank, int32_t world,
+                         void *arena, const ovl_cand_layout *lay, int64_t *totals, void *stream);
 
 /* K4/K5: the DP call site overlapGraphs.py:53, i.e. aligners.py:27-57 for every pair:
  *   score[p], end[p] = overlap_alignment(read[pair_a[p]], read[pair_b[p]], match, mismatch, indel)[3:5]
@@ -141,6 +194,14 @@ int ovl_overlap_dp_edges(ovl_ctx *ctx, const uint32_t *packed, int32_t row_words
                          int64_t match, int64_t mismatch, int64_t indel, const int32_t *copies,
                          const int64_t *node_off, const int64_t *edge_off, int32_t *edges,
                          void *stream);
+/* The same with the edge-row offsets taken from the join index (ovl_join_count with copies) instead of
+ * a per-pair edge_off array: pair_a[0] is global pair p_begin, edges[0] is global edge row e_begin. */
+int ovl_overlap_dp_edges_join(ovl_ctx *ctx, const uint32_t *packed, int32_t row_words, const int32_t *len,
+                              const int32_t *pair_a, const int32_t *pair_b, int64_t P, int32_t max_len,
+                              int64_t match, int64_t mismatch, int64_t indel, const int32_t *copies,
+                              const int64_t *node_off, const int64_t *pair_off, const int64_t *edge_base,
+                              const int32_t *bucket_lo, const int32_t *self_rank, const int64_t *cum,
+                              int64_t p_begin, int64_t e_begin, int32_t *edges, void *stream);
 /* which kernel ovl_overlap_dp would pick: out[0]=mode (1 packed, 2 int32, 3 long-read kernel), out[1]=lanes,
  * out[2]=columns per lane.  Returns OVL_E_UNSUPPORTED when nothing fits. */
 int ovl_overlap_dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_t indel,

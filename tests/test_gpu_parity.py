@@ -525,3 +525,151 @@ def test_edge_list_hash_matches_host_mirror_and_sees_order(eng):
     comp[6, 2] -= 1                                     # compensating errors
     assert int(eng.edge_hash(torch.from_numpy(comp).to(eng.device)).item()) & 0xFFFFFFFFFFFFFFFF != h
     assert int(eng.edge_hash(d[:0]).item()) == 0
+
+
+# --------------------------------------------------------------------------- K0-K3 as one job
+def _job(eng, reads, k, counts=None, shard=(0, 1), segments=None, n_segments=1):
+    import torch
+    bases, offsets = orc.concat_reads(reads)
+    ascii_dev, off_dev, U, max_len = eng._upload_ascii(bases[:int(offsets[-1])] if len(reads) else bases[:0], offsets)
+    copies = node_off = None
+    if counts is not None and max(counts) > 1:
+        c = np.asarray(counts, dtype=np.int32)
+        no = np.zeros(len(c) + 1, np.int64)
+        np.cumsum(c, out=no[1:])
+        copies, node_off = torch.from_numpy(c).to(eng.device), torch.from_numpy(no).to(eng.device)
+    seg = torch.from_numpy(np.asarray(segments, dtype=np.int32)).to(eng.device) if segments is not None else None
+    return eng.build_candidates(ascii_dev, off_dev, U, max_len, k, copies, node_off, shard, seg, n_segments)
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 8, 10, 11, 12, 15, 16, 31, 32])
+def test_one_call_job_keys_index_table_and_pairs(eng, k):
+    """ovl_candidates_build (fused pack + keys, wide-digit sort, bucket table, table join) against NumPy / the oracle."""
+    import torch
+    rng = random.Random(100 + k)
+    reads = list(dict.fromkeys(overlapping_reads(rng, 2500, 700, 70, 0.01) + rand_reads(rng, 200, 0, 140) +
+                               ["G" * 40, "G" * 33 + "A", "A" + "G" * 35, "C" * 64, "C" * 65, "T" * 63 + "A", "A" * 96 + "C" * 32]))
+    U = len(reads)
+    cand = _job(eng, reads, k)
+    idx = cand.index
+    pk = idx.prefix_key[:U].cpu().numpy().view(np.uint64)
+    sk = idx.suffix_key[:U].cpu().numpy().view(np.uint64)
+    valid = np.array([len(r) >= k for r in reads])
+    want_pk = np.array([np_key(r, k, False) if len(r) >= k else 0 for r in reads], dtype=np.uint64)
+    want_sk = np.array([np_key(r, k, True) if len(r) >= k else 0 for r in reads], dtype=np.uint64)
+    assert np.array_equal(pk[valid], want_pk[valid]) and np.array_equal(sk[valid], want_sk[valid])
+    got_rows = cand.rs.packed[:U * cand.rs.row_words * 4].view(torch.int32).cpu().numpy().view(np.uint32).reshape(U, -1)
+    assert np.array_equal(got_rows, np_pack(reads, cand.rs.row_words))
+    n_idx = int(idx.n_indexed.item())
+    assert n_idx == int(valid.sum())
+    order = np.argsort(want_pk[valid], kind="stable")
+    uids = np.nonzero(valid)[0][order]
+    skeys = want_pk[valid][order]
+    assert np.array_equal(idx.sorted_uid[:n_idx].cpu().numpy().view(np.uint32), uids.astype(np.uint32))
+    assert np.array_equal(idx.sorted_key[:n_idx].cpu().numpy().view(np.uint64), skeys)
+    # every indexed read knows its own sorted position
+    pos_of = idx.pos_of[:U].cpu().numpy()
+    assert np.array_equal(pos_of[uids], np.arange(n_idx))
+    # the bucket table: first sorted position whose key prefix is >= t
+    shift = idx.key_bits - idx.table_bits
+    table = idx.table.cpu().numpy()
+    want_table = np.searchsorted(skeys >> np.uint64(shift), np.arange((1 << idx.table_bits) + 1, dtype=np.uint64), side="left")
+    assert np.array_equal(table, want_table.astype(np.int32))
+    wa, wb = orc.candidate_pairs(reads, k)
+    assert cand.total_pairs == len(wa) == cand.total_edges and (cand.p_begin, cand.p_end) == (0, len(wa))
+    pa, pb = eng.fill_pairs(cand)
+    assert np.array_equal(pa.cpu().numpy(), wa) and np.array_equal(pb.cpu().numpy(), wb)
+    # the 65 cuts: monotone, from p_begin to p_end, equal parts
+    assert cand.cut_pairs[0] == 0 and cand.cut_pairs[-1] == len(wa) and cand.cut_pairs == sorted(cand.cut_pairs)
+    assert cand.cut_pairs[32] == len(wa) // 64 * 32 + len(wa) % 64 * 32 // 64 and cand.cut_edges == cand.cut_pairs
+    # sharded jobs tile the list
+    parts = [_job(eng, reads, k, shard=(r, 3)) for r in range(3)]
+    assert [(c.p_begin, c.p_end) for c in parts] == [(len(wa) * r // 3, len(wa) * (r + 1) // 3) for r in range(3)]
+    filled = [eng.fill_pairs(c) for c in parts]
+    assert np.array_equal(torch.cat([f[0] for f in filled]).cpu().numpy(), wa)
+    assert np.array_equal(torch.cat([f[1] for f in filled]).cpu().numpy(), wb)
+    # the granular entry points (separate pack, keys, index, join calls) give the same list
+    rs, _, _ = upload(eng, reads)
+    gi = eng.kmer_index(rs, k)
+    ga, gb, _ = eng.candidate_pairs(rs, gi, k)
+    assert torch.equal(ga, pa) and torch.equal(gb, pb)
+
+
+def test_one_call_job_suffix_key_straddles_groups_and_warps(eng):
+    """The fused suffix key: k-mers that straddle two 64-base groups, incl. groups packed by different warps."""
+    rng = random.Random(77)
+    reads = []
+    for L in list(range(1, 200)) + [255, 256, 257, 319, 320, 321, 1000, 2047, 2048, 2049]:
+        reads.append("".join(rng.choice("ACGT") for _ in range(L)))
+    reads = list(dict.fromkeys(reads))
+    U = len(reads)
+    for k in (1, 7, 17, 31, 32):
+        cand = _job(eng, reads, k)
+        sk = cand.index.suffix_key[:U].cpu().numpy().view(np.uint64)
+        pk = cand.index.prefix_key[:U].cpu().numpy().view(np.uint64)
+        for u, r in enumerate(reads):
+            if len(r) >= k:
+                assert int(sk[u]) == np_key(r, k, True) and int(pk[u]) == np_key(r, k, False), (k, len(r))
+    # 600 reads of 65..96 bases: row = 2 groups, so every 16th read's second group starts a warp
+    reads = list(dict.fromkeys("".join(rng.choice("ACGT") for _ in range(rng.randint(65, 96))) for _ in range(600)))
+    for k in (20, 32):
+        cand = _job(eng, reads, k)
+        sk = cand.index.suffix_key[:len(reads)].cpu().numpy().view(np.uint64)
+        assert [int(x) for x in sk] == [np_key(r, k, True) for r in reads]
+
+
+def test_one_call_job_edge_offsets_with_copies(eng):
+    """Reads with copies: the implicit edge offsets of the join index (no per-pair offset array) reproduce the
+    explicit scan of copies[a] * copies[b], for the whole list, for shards and for D2H chunks."""
+    import torch
+    rng = random.Random(5)
+    base = overlapping_reads(rng, 1500, 500, 50, 0.01) + ["ACGTACGTAC", "CGTACGTACG", "GTACG"]
+    base = list(dict.fromkeys(base))
+    counts = [rng.choice([1, 1, 1, 2, 3, 7]) for _ in base]
+    reads = [r for r, c in zip(base, counts) for _ in range(c)]
+    rng.shuffle(reads)
+    rc = orc.dedup_reads(reads)
+    uniq, cnts = list(rc.keys()), list(rc.values())
+    for k in (3, 6, 12):
+        nodes, edges, _ = orc.construct_overlap_graph(reads, k)
+        nid = {n: i for i, n in enumerate(nodes)}
+        want = np.array([[nid[u], nid[v], w, e] for u, v, w, e in edges], dtype=np.int32).reshape(-1, 4)
+        cand = _job(eng, uniq, k, cnts)
+        assert cand.total_edges == len(want) and cand.edge_base is not None
+        pa, pb = eng.fill_pairs(cand)
+        got = eng.candidate_edges(cand, pa, pb)
+        assert np.array_equal(got.cpu().numpy(), want)
+        # cut_edges are the true edge offsets of cut_pairs
+        c = np.asarray(cnts, dtype=np.int64)
+        per_pair = c[pa.cpu().numpy()] * c[pb.cpu().numpy()]
+        off = np.concatenate([[0], np.cumsum(per_pair)])
+        assert cand.cut_edges == [int(off[p]) for p in cand.cut_pairs]
+        # shards: rows land at their global offsets
+        parts = []
+        for r in range(4):
+            cs = _job(eng, uniq, k, cnts, shard=(r, 4))
+            sa, sb = eng.fill_pairs(cs)
+            rows = eng.candidate_edges(cs, sa, sb)
+            assert cs.e_begin == int(off[cs.p_begin]) and cs.e_end == int(off[cs.p_end])
+            parts.append(rows)
+        assert np.array_equal(torch.cat(parts).cpu().numpy(), want)
+        # host path (chunked D2H) and the public host call
+        host = eng.candidate_edges_to_host(cand, pa, pb, chunk_pairs=max(1, len(pa) // 5))
+        assert np.array_equal(host, want)
+        b, o = orc.concat_reads(uniq)
+        assert np.array_equal(eng.overlap_edges(b, o, np.asarray(cnts, np.int32), k), want)
+
+
+def test_one_call_job_finite_indel_and_all_a_genome(eng):
+    """Degenerate buckets: a homopolymer genome puts every read in ONE bucket (every read is its own candidate's
+    neighbour); results must still equal the oracle."""
+    reads = ["A" * n for n in range(3, 60)] + ["A" * 20 + "C", "C" + "A" * 20]
+    counts = [1 + (i % 3) for i in range(len(reads))]
+    many = [r for r, c in zip(reads, counts) for _ in range(c)]
+    for k in (3, 5):
+        nodes, edges, _ = orc.construct_overlap_graph(many, k)
+        nid = {n: i for i, n in enumerate(nodes)}
+        want = np.array([[nid[u], nid[v], w, e] for u, v, w, e in edges], dtype=np.int32).reshape(-1, 4)
+        b, o = orc.concat_reads(reads)
+        got = eng.overlap_edges(b, o, np.asarray(counts, np.int32), k)
+        assert np.array_equal(got, want)
