@@ -439,9 +439,9 @@ class OverlapEngine:
 
     def candidate_edges_to_host(self, cand: Candidates, pair_a: torch.Tensor, pair_b: torch.Tensor,
                                 match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT,
-                                chunk_pairs: int = 48_000_000, host_sink=None) -> np.ndarray:
+                                chunk_pairs: int = 1 << 62, host_sink=None, min_chunked_pairs: int = 1_000_000) -> np.ndarray:
         """The same with the device->host copy of the edge rows overlapped with the DP: the slice is cut at
-        the boundaries the job already computed (cand.cut_pairs / cut_edges), each chunk's rows are copied
+        boundaries the job already computed (cand.cut_pairs / cut_edges), each chunk's rows are copied
         to the pinned host buffer on a second stream while the next chunk computes."""
         P = int(pair_a.shape[0])
         if P == 0:
@@ -450,13 +450,19 @@ class OverlapEngine:
             return np.zeros((0, 4), np.int32)
         main = torch.cuda.current_stream(self.device)
         st = self._stream()
-        n_chunks = max(1, min(64, (P + chunk_pairs - 1) // chunk_pairs))
-        if P >= 1_000_000:
-            n_chunks = max(n_chunks, 8)        # even a few-ms job hides most of its copy behind the DP
-        n_chunks = 1 << (n_chunks - 1).bit_length()          # 1, 2, 4, ... 64: a subset of the 64 computed cuts
-        step = 64 // n_chunks
-        bounds = [cand.cut_pairs[i * step] - cand.p_begin for i in range(n_chunks + 1)]
-        e_bounds = [cand.cut_edges[i * step] - cand.e_begin for i in range(n_chunks + 1)]
+        # Chunk sizes shrink geometrically (1/2, 1/4, ... 1/64 of the slice, cut at the 64ths the job computed):
+        # every copy hides behind the next, larger-than-needed DP chunk and only the last 1/64 is exposed.
+        # chunk_pairs caps the chunk size (more, equal chunks first) for very long lists.
+        if P < min_chunked_pairs:
+            cuts = [0, 64]
+        else:
+            cuts = [0, 32, 48, 56, 60, 62, 63, 64]
+            while (cuts[1] - cuts[0]) * P // 64 > chunk_pairs and cuts[1] - cuts[0] > 1:
+                half = (cuts[1] - cuts[0]) // 2
+                cuts = [c for c in range(0, cuts[1], half)] + cuts[1:]
+        n_chunks = len(cuts) - 1
+        bounds = [cand.cut_pairs[c] - cand.p_begin for c in cuts]
+        e_bounds = [cand.cut_edges[c] - cand.e_begin for c in cuts]
         E = e_bounds[-1]
         edges = self._empty(E * 4, torch.int32).view(-1, 4)
         host = host_sink(E, cand.e_begin, cand.total_edges) if host_sink is not None else self._host_rows(E)

@@ -654,7 +654,9 @@ def test_one_call_job_edge_offsets_with_copies(eng):
             parts.append(rows)
         assert np.array_equal(torch.cat(parts).cpu().numpy(), want)
         # host path (chunked D2H) and the public host call
-        host = eng.candidate_edges_to_host(cand, pa, pb, chunk_pairs=max(1, len(pa) // 5))
+        host = eng.candidate_edges_to_host(cand, pa, pb, min_chunked_pairs=0)                 # 7 shrinking chunks
+        assert np.array_equal(host, want)
+        host = eng.candidate_edges_to_host(cand, pa, pb, chunk_pairs=max(1, len(pa) // 5), min_chunked_pairs=0)
         assert np.array_equal(host, want)
         b, o = orc.concat_reads(uniq)
         assert np.array_equal(eng.overlap_edges(b, o, np.asarray(cnts, np.int32), k), want)
