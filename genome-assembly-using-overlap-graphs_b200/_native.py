@@ -18,6 +18,7 @@ OVL_E_UNSUPPORTED = -3
 OVL_MAX_K = 32
 OVL_MAX_READ_LEN = 2432
 OVL_MAX_LONG_READ_LEN = 16384
+OVL_LOCAL_BATCH_MAX_QUERY = 1024
 
 
 class OvlError(RuntimeError):
@@ -49,7 +50,7 @@ class CandLayout(ctypes.Structure):
     """ovl_cand_layout (include/ovl.h): byte offsets of every array of the K0-K3 job inside its arena."""
     _fields_ = [(n, ctypes.c_size_t) for n in (
         "packed", "len", "bad", "n_indexed", "prefix_key", "suffix_key", "sorted_key", "sorted_uid", "table", "pos_of",
-        "bucket_lo", "self_rank", "pair_off", "edge_base", "cum", "scratch", "scratch_bytes", "total_bytes")] + \
+        "bucket_lo", "self_rank", "pair_off", "edge_base", "cum", "sorted_copies", "scratch", "scratch_bytes", "total_bytes")] + \
         [(n, ctypes.c_int32) for n in ("row_words", "key_bits", "table_bits", "has_copies")]
 
 
@@ -72,9 +73,9 @@ _SIGS = {
     "ovl_index_workspace_bytes": (_sz, [_i64]),
     "ovl_pack_reads_keys": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ovl_index_table_bits": (_i32, [_i64, _i32]),
-    "ovl_index_build": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "ovl_index_build": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ovl_join_workspace_bytes": (_sz, [_i64]),
-    "ovl_join_count": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
+    "ovl_join_count": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                       _vp, _vp, _vp, _sz, _vp]),
     "ovl_totals_len": (_i32, []),
     "ovl_join_finalize": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp]),
@@ -107,6 +108,8 @@ _SIGS = {
     "ovl_align_pair": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp, _vp, _vp]),
     "ovl_local_align_workspace_bytes": (_sz, [_i32, _i32]),
     "ovl_local_align": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp, _vp, _vp]),
+    "ovl_local_align_batch": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp,
+                                             _vp, _vp]),
     "ovl_edge_list_hash": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "ovl_int_peak_probe": (ctypes.c_int, [_vp, _i32, _i32, ctypes.POINTER(ctypes.c_double),
                                           ctypes.POINTER(ctypes.c_double)]),

@@ -60,19 +60,8 @@ def overlap_alignment(s, t, match_score=10, mismatch=-1, indel=-2 ** 31):
     return alignment_to_print, align_s, align_t, int(score), int(end)
 
 
-def local_alignment(query, reference, match_score=10, mismatch=-1, indel=-1):
-    """Best local alignment of `query` in `reference` -- drop-in for aligners.py:85-167.
-
-    Returns (alignment_to_print, aligned_reference, aligned_query, best_score, start_pos, end_pos).
-    """
-    if not isinstance(query, str) or not isinstance(reference, str):
-        raise TypeError("local_alignment expects str arguments (the reference raises a Numba TypingError)")
-    for name, v in (("match_score", match_score), ("mismatch", mismatch), ("indel", indel)):
-        if isinstance(v, bool) or not isinstance(v, (int, np.integer)):
-            raise TypeError(f"{name} must be an integer")
-    eng = _engine.get_engine()
-    score, start, end, best_i, ops = eng.local_align(_codes(query), _codes(reference), int(match_score),
-                                                     int(mismatch), int(indel))
+def _local_tuple(query, reference, score, start, end, best_i, ops):
+    """Device result (scores + op list from the best cell backwards) -> the reference's 6-tuple."""
     i, j = best_i, end
     a_q, a_r = [], []
     for op in ops.tolist():                                           # aligners.py:143-160
@@ -89,10 +78,34 @@ def local_alignment(query, reference, match_score=10, mismatch=-1, indel=-1):
     return alignment_to_print, aligned_reference, aligned_query, int(score), int(start), int(end)
 
 
+def _check_local_args(query, reference, match_score, mismatch, indel):
+    if not isinstance(query, str) or not isinstance(reference, str):
+        raise TypeError("local_alignment expects str arguments (the reference raises a Numba TypingError)")
+    for name, v in (("match_score", match_score), ("mismatch", mismatch), ("indel", indel)):
+        if isinstance(v, bool) or not isinstance(v, (int, np.integer)):
+            raise TypeError(f"{name} must be an integer")
+
+
+def local_alignment(query, reference, match_score=10, mismatch=-1, indel=-1):
+    """Best local alignment of `query` in `reference` -- drop-in for aligners.py:85-167.
+
+    Returns (alignment_to_print, aligned_reference, aligned_query, best_score, start_pos, end_pos).
+    """
+    _check_local_args(query, reference, match_score, mismatch, indel)
+    eng = _engine.get_engine()
+    score, start, end, best_i, ops = eng.local_align(_codes(query), _codes(reference), int(match_score),
+                                                     int(mismatch), int(indel))
+    return _local_tuple(query, reference, score, start, end, best_i, ops)
+
+
 def align_read_or_contig_to_reference(read_or_contig, reference_genome, read_length, match_score=10, mismatch=-1,
                                       indel=-1):
     """Drop-in for aligners.py:170-202: local alignment against the genome, or -- for a sequence
-    shorter than a read -- against the genome's last len(sequence) bases."""
+    shorter than a read -- against the genome's last len(sequence) bases.  A result computed ahead by
+    prefetch_alignments() for exactly these arguments is returned without touching the GPU again."""
+    hit = _PREFETCHED.get((read_or_contig, id(reference_genome), len(reference_genome), read_length, match_score, mismatch, indel))
+    if hit is not None:
+        return hit
     n = len(read_or_contig)
     if n < read_length:
         to_print, aligned_ref, aligned, score, start, end = local_alignment(
@@ -103,6 +116,56 @@ def align_read_or_contig_to_reference(read_or_contig, reference_genome, read_len
         to_print, aligned_ref, aligned, score, start, end = local_alignment(
             read_or_contig, reference_genome, match_score, mismatch, indel)
     return to_print, aligned_ref, aligned, score, start, end
+
+
+def align_reads_or_contigs_to_reference(sequences, reference_genome, read_length, match_score=10, mismatch=-1, indel=-1):
+    """[align_read_or_contig_to_reference(s, reference_genome, read_length, ...) for s in sequences] from ONE
+    kernel launch: one CTA per sequence, the genome uploaded once (not in the reference, which aligns the
+    contigs of an assembly one call at a time, performanceMeasures.py:219-221).  Sequences longer than
+    1,024 symbols take the per-call path."""
+    sequences = list(sequences)
+    for q in sequences:
+        _check_local_args(q, reference_genome, match_score, mismatch, indel)
+    eng = _engine.get_engine()
+    G = len(reference_genome)
+    out = [None] * len(sequences)
+    batch = [x for x, q in enumerate(sequences) if len(q) <= _engine.nat.OVL_LOCAL_BATCH_MAX_QUERY]
+    windows = []
+    for x in batch:
+        n = len(sequences[x])
+        windows.append((G - n, n) if n < read_length else (0, G))      # aligners.py:191-199
+    if batch:
+        res = eng.local_align_batch([_codes(sequences[x]) for x in batch], _codes(reference_genome), windows,
+                                    int(match_score), int(mismatch), int(indel))
+        for x, (w0, wl), (score, start, end, best_i, ops) in zip(batch, windows, res):
+            q = sequences[x]
+            ref = reference_genome if w0 == 0 and wl == G else reference_genome[w0:w0 + wl]
+            to_print, aligned_ref, aligned, score, start, end = _local_tuple(q, ref, score, start, end, best_i, ops)
+            out[x] = (to_print, aligned_ref, aligned, score, w0 + start, w0 + end)
+    for x, q in enumerate(sequences):
+        if out[x] is None:
+            out[x] = align_read_or_contig_to_reference(q, reference_genome, read_length, match_score, mismatch, indel)
+    return out
+
+
+def local_alignment_batch(queries, reference, match_score=10, mismatch=-1, indel=-1):
+    """[local_alignment(q, reference, ...) for q in queries] from one kernel launch."""
+    return align_reads_or_contigs_to_reference(queries, reference, 0, match_score, mismatch, indel)
+
+
+_PREFETCHED = {}
+
+
+def prefetch_alignments(sequences, reference_genome, read_length, match_score=10, mismatch=-1, indel=-1):
+    """Compute align_read_or_contig_to_reference for all `sequences` in one launch and keep the results, so that
+    the reference's own per-contig loop (performanceMeasures.py:219-221) is served from them: call this once
+    before the loop with the same genome object.  The cache holds the results of the latest call only."""
+    _PREFETCHED.clear()
+    seqs = list(dict.fromkeys(sequences))
+    res = align_reads_or_contigs_to_reference(seqs, reference_genome, read_length, match_score, mismatch, indel)
+    for q, r in zip(seqs, res):
+        _PREFETCHED[(q, id(reference_genome), len(reference_genome), read_length, match_score, mismatch, indel)] = r
+    return len(seqs)
 
 
 def __getattr__(name):

@@ -153,11 +153,11 @@ __global__ void __launch_bounds__(kAlignThreads) local_align_kernel(const int32_
 // __shfl_up_sync) and its "diag" H[i-1][j-1] the one before that.  Only warp boundaries go through
 // shared memory, double buffered, so a diagonal costs one block barrier (none for a single warp).
 // tb is diagonal-major here: byte (d, i) at tb[d*(n+1) + i] -- consecutive threads, consecutive bytes.
-__global__ void __launch_bounds__(kAlignThreads) local_align_rows_kernel(const int32_t* __restrict__ q, int n,
-                                                                         const int32_t* __restrict__ ref, int m,
-                                                                         int64_t match, int64_t mismatch, int64_t indel,
-                                                                         int8_t* __restrict__ tb,
-                                                                         int32_t* __restrict__ result, uint8_t* __restrict__ ops) {
+__device__ __forceinline__ void local_align_rows_body(const int32_t* __restrict__ q, int n,
+                                                      const int32_t* __restrict__ ref, int m,
+                                                      int64_t match, int64_t mismatch, int64_t indel,
+                                                      int8_t* __restrict__ tb,
+                                                      int32_t* __restrict__ result, uint8_t* __restrict__ ops) {
     __shared__ int32_t edge[2][kAlignThreads / 32];
     __shared__ int32_t s_best[kAlignThreads / 32], s_bi[kAlignThreads / 32], s_bj[kAlignThreads / 32];
     const int t = threadIdx.x, i = t + 1, wid = t >> 5;
@@ -222,6 +222,41 @@ __global__ void __launch_bounds__(kAlignThreads) local_align_rows_kernel(const i
         result[3] = L;
         result[4] = bi;
     }
+}
+
+__global__ void __launch_bounds__(kAlignThreads) local_align_rows_kernel(const int32_t* __restrict__ q, int n,
+                                                                         const int32_t* __restrict__ ref, int m,
+                                                                         int64_t match, int64_t mismatch, int64_t indel,
+                                                                         int8_t* __restrict__ tb,
+                                                                         int32_t* __restrict__ result, uint8_t* __restrict__ ops) {
+    local_align_rows_body(q, n, ref, m, match, mismatch, indel, tb, result, ops);
+}
+
+// K8 batch: one CTA per query, all queries against windows of ONE reference that is read from L2 by every
+// CTA (performanceMeasures.py:219-221 aligns every contig of an assembly to the same genome, one call
+// each: 148+ of them now run side by side).  Query x: symbols queries[q_off[x] .. q_off[x+1]), reference
+// window [ref_start[x], ref_start[x] + ref_len[x]), traceback bytes at tb + tb_off[x], op list at
+// ops + ops_off[x], result row results + 8 x.  Every query has at most blockDim.x symbols.
+__global__ void __launch_bounds__(kAlignThreads) local_align_batch_kernel(const int32_t* __restrict__ queries,
+                                                                          const int64_t* __restrict__ q_off,
+                                                                          const int32_t* __restrict__ reference,
+                                                                          const int32_t* __restrict__ ref_start,
+                                                                          const int32_t* __restrict__ ref_len,
+                                                                          int64_t match, int64_t mismatch, int64_t indel,
+                                                                          int8_t* __restrict__ tb, const int64_t* __restrict__ tb_off,
+                                                                          int32_t* __restrict__ results,
+                                                                          uint8_t* __restrict__ ops, const int64_t* __restrict__ ops_off) {
+    const int x = blockIdx.x;
+    const int64_t q0 = q_off[x];
+    const int n = (int)(q_off[x + 1] - q0);
+    const int m = ref_len[x];
+    int32_t* result = results + 8 * (size_t)x;
+    if (n == 0 || m == 0) {                                  // empty query or window: score 0 at (0, 0), aligners.py:113-114
+        if (threadIdx.x < 8) result[threadIdx.x] = 0;
+        return;
+    }
+    local_align_rows_body(queries + q0, n, reference + ref_start[x], m, match, mismatch, indel, tb + tb_off[x], result,
+                          ops + ops_off[x]);
 }
 
 }  // namespace ovl

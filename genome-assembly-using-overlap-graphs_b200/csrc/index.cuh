@@ -18,11 +18,12 @@
 
 namespace ovl {
 
-constexpr int kSortWarps = 4;            // warps per CTA
+constexpr int kSortWarps = 8;            // warps per CTA
 constexpr int kSortThreads = kSortWarps * 32;
-constexpr int kSortChunk = 2048;         // consecutive elements owned by one warp
-constexpr int kSortBatch = 16;           // loads in flight per lane
-constexpr int kSortMaxDigit = 10;        // bits per pass: 4 warps x 1024 counters = 16 KB of shared memory
+constexpr int kSortRounds = 8;           // elements per lane
+constexpr int kSortWarpChunk = 32 * kSortRounds;             // 256 consecutive elements owned by one warp
+constexpr int kSortChunk = kSortWarps * kSortWarpChunk;      // 2,048 consecutive elements owned by one CTA
+constexpr int kSortMaxDigit = 10;        // bits per pass: 8 warps x 1024 counters = 32 KB of shared memory
 constexpr int kTableMaxBits = 22;        // direct-address table: at most 4 Mi + 1 entries (16 MB)
 
 __host__ __device__ inline int sort_passes(int key_bits) { return (key_bits + kSortMaxDigit - 1) / kSortMaxDigit; }
@@ -31,99 +32,160 @@ __host__ __device__ inline int sort_digit_bits(int key_bits) {
     return (key_bits + p - 1) / p;
 }
 
-// per-warp digit histogram of the warp's chunk -> hist[digit * W + warp]
+// per-CTA digit histogram of the CTA's chunk -> hist[digit * C + cta]   (C = number of CTAs)
 template <bool FIRST>
 __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint64_t* __restrict__ keys,
                                                                  const int32_t* __restrict__ len, int k,
                                                                  const int64_t* __restrict__ n_ptr, int64_t n_static,
-                                                                 int shift, int digit_bits, int64_t W,
+                                                                 int shift, int digit_bits, int64_t C,
                                                                  int32_t* __restrict__ hist) {
-    __shared__ int32_t cnt[kSortWarps][1 << kSortMaxDigit];
-    const int wib = threadIdx.x >> 5;
-    const int64_t warp = (int64_t)blockIdx.x * kSortWarps + wib;
+    __shared__ int32_t cnt[1 << kSortMaxDigit];
     const int nd = 1 << digit_bits;
     const unsigned mask = (unsigned)nd - 1u;
-    for (int i = lane_id(); i < nd; i += 32) cnt[wib][i] = 0;
-    __syncwarp();
-    if (warp >= W) return;
+    for (int i = threadIdx.x; i < nd; i += kSortThreads) cnt[i] = 0;
+    __syncthreads();
     const int64_t n = FIRST ? n_static : *n_ptr;
-    const int64_t base = warp * kSortChunk;
-    for (int b = 0; b < kSortChunk / 32; b += kSortBatch) {
-        if (base + (int64_t)b * 32 >= n) break;
-        uint64_t key[kSortBatch];
-        bool live[kSortBatch];
+    const int64_t base = (int64_t)blockIdx.x * kSortChunk;
+    uint64_t key[kSortRounds];
+    bool live[kSortRounds];
 #pragma unroll
-        for (int it = 0; it < kSortBatch; ++it) {                 // all loads of the batch before the first atomic
-            int64_t idx = base + (int64_t)(b + it) * 32 + lane_id();
-            live[it] = idx < n;
-            key[it] = live[it] ? keys[idx] : 0;
-            if (FIRST && live[it]) live[it] = len[idx] >= k;
-        }
-#pragma unroll
-        for (int it = 0; it < kSortBatch; ++it)
-            if (live[it]) atomicAdd(&cnt[wib][(unsigned)(key[it] >> shift) & mask], 1);
+    for (int r = 0; r < kSortRounds; ++r) {                       // all loads before the first atomic
+        int64_t idx = base + r * kSortThreads + threadIdx.x;
+        live[r] = idx < n;
+        key[r] = live[r] ? keys[idx] : 0;
+        if (FIRST && live[r]) live[r] = len[idx] >= k;
     }
-    __syncwarp();
-    for (int d = lane_id(); d < nd; d += 32) hist[(int64_t)d * W + warp] = cnt[wib][d];
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r)
+        if (live[r]) atomicAdd(&cnt[(unsigned)(key[r] >> shift) & mask], 1);
+    __syncthreads();
+    for (int d = threadIdx.x; d < nd; d += kSortThreads) hist[(int64_t)d * C + blockIdx.x] = cnt[d];
 }
 
-// stable scatter of the warp's chunk to the scanned offsets.  FIRST: input is (prefix_key, uid = index)
-// straight from K1 and reads shorter than k are dropped; n_out receives the number of survivors.
-// pos_of (last pass only): sorted position of every uid.
+// Stable scatter of the CTA's chunk to the scanned offsets.  Warp w owns elements [256 w, 256 w + 256) of the
+// chunk and ranks them among themselves (8 rounds of __match_any_sync); the CTA scans the per-warp digit
+// counts into CTA-local sorted positions, the elements are staged in shared memory in that order, and
+// consecutive threads then write consecutive elements: every run of equal digits goes out as one
+// contiguous, coalesced piece.
+// FIRST: input is (prefix_key, uid = index) straight from K1 and reads shorter than k are dropped; n_out
+// receives the number of survivors.  Last pass only: pos_of[uid] = sorted position, and -- when reads have
+// copies -- sorted_copies[position] = copies[uid] (what the join scans into `cum`).
 template <bool FIRST>
 __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint64_t* __restrict__ keys_in,
                                                                     const uint32_t* __restrict__ uid_in,
                                                                     const int32_t* __restrict__ len, int k,
                                                                     const int64_t* __restrict__ n_ptr, int64_t n_static,
-                                                                    int shift, int digit_bits, int64_t W,
+                                                                    int shift, int digit_bits, int64_t C,
                                                                     const int32_t* __restrict__ hist_scanned,
                                                                     uint64_t* __restrict__ keys_out,
                                                                     uint32_t* __restrict__ uid_out,
                                                                     int32_t* __restrict__ pos_of,
+                                                                    const int32_t* __restrict__ copies,
+                                                                    int32_t* __restrict__ sorted_copies,
                                                                     int64_t* __restrict__ n_out) {
-    __shared__ int32_t off[kSortWarps][1 << kSortMaxDigit];
-    const int wib = threadIdx.x >> 5;
-    const int64_t warp = (int64_t)blockIdx.x * kSortWarps + wib;
-    if (warp >= W) return;
+    constexpr int ND_MAX = 1 << kSortMaxDigit;
+    constexpr int DPT = ND_MAX / kSortThreads;                    // digits per thread in the CTA scan (4)
+    __shared__ uint16_t wcnt[kSortWarps][ND_MAX];                 // per-warp digit counts, then per-warp local bases
+    __shared__ int32_t delta[ND_MAX];                             // global position - local position, per digit
+    __shared__ uint64_t keys_s[kSortChunk];
+    __shared__ uint32_t uid_s[kSortChunk];
+    __shared__ int32_t warp_sums[kSortWarps + 1];
     const int nd = 1 << digit_bits;
     const unsigned mask = (unsigned)nd - 1u;
-    for (int d = lane_id(); d < nd; d += 32) off[wib][d] = hist_scanned[(int64_t)d * W + warp];
-    __syncwarp();
     const int64_t n = FIRST ? n_static : *n_ptr;
-    const int64_t base = warp * kSortChunk;
-    for (int b = 0; b < kSortChunk / 32; b += kSortBatch) {
-        if (base + (int64_t)b * 32 >= n) break;
-        uint64_t key[kSortBatch];
-        uint32_t uid[kSortBatch];
-        bool live[kSortBatch];
+    const int64_t base = (int64_t)blockIdx.x * kSortChunk;
+    if (FIRST && n_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+        *n_out = (int64_t)hist_scanned[(int64_t)nd * C];           // grand total of the scan = reads with len >= k
+    if (base >= n) return;
+    const int wib = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kSortWarps * ND_MAX / 2; i += kSortThreads) reinterpret_cast<uint32_t*>(&wcnt[0][0])[i] = 0u;
+    uint64_t key[kSortRounds];
+    uint32_t uid[kSortRounds];
+    int rank[kSortRounds];             // rank among the warp's earlier elements with the same digit, or -1 (dead)
 #pragma unroll
-        for (int it = 0; it < kSortBatch; ++it) {                 // issue every load of the batch up front
-            int64_t idx = base + (int64_t)(b + it) * 32 + lane_id();
-            live[it] = idx < n;
-            key[it] = live[it] ? keys_in[idx] : 0;
-            uid[it] = FIRST ? (uint32_t)idx : (live[it] ? uid_in[idx] : 0u);
-            if (FIRST && live[it]) live[it] = len[idx] >= k;
+    for (int r = 0; r < kSortRounds; ++r) {                       // issue every load of the chunk up front
+        int64_t idx = base + wib * kSortWarpChunk + r * 32 + lane_id();
+        bool live = idx < n;
+        key[r] = live ? keys_in[idx] : 0;
+        uid[r] = FIRST ? (uint32_t)idx : (live ? uid_in[idx] : 0u);
+        if (FIRST && live) live = len[idx] >= k;
+        rank[r] = live ? 0 : -1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        const bool live = rank[r] >= 0;
+        const unsigned d = live ? ((unsigned)(key[r] >> shift) & mask) : (unsigned)nd + lane_id();   // dead lanes match nobody
+        const unsigned peers = __match_any_sync(kFull, d);
+        const int within = __popc(peers & lanemask_lt());
+        if (live) rank[r] = (int)wcnt[wib][d] + within;
+        __syncwarp();
+        if (live && within == 0) wcnt[wib][d] = (uint16_t)(wcnt[wib][d] + __popc(peers));
+        __syncwarp();
+    }
+    __syncthreads();
+    // CTA scan over (digit, warp): local sorted position of every warp's first element of every digit
+    {
+        int32_t cnt[DPT];
+        int32_t mine = 0;
+#pragma unroll
+        for (int x = 0; x < DPT; ++x) {
+            const int d = threadIdx.x * DPT + x;
+            int32_t c = 0;
+            if (d < nd)
+                for (int w = 0; w < kSortWarps; ++w) c += wcnt[w][d];
+            cnt[x] = c;
+            mine += c;
         }
+        int32_t inc = mine;
 #pragma unroll
-        for (int it = 0; it < kSortBatch; ++it) {
-            unsigned d = live[it] ? ((unsigned)(key[it] >> shift) & mask) : (unsigned)nd + lane_id();   // dead lanes match nobody
-            unsigned peers = __match_any_sync(kFull, d);
-            int rank = __popc(peers & lanemask_lt());
-            int pos = 0;
-            if (live[it]) pos = off[wib][d] + rank;
-            __syncwarp();
-            if (live[it] && rank == 0) off[wib][d] += __popc(peers);
-            __syncwarp();
-            if (live[it]) {
-                keys_out[pos] = key[it];
-                uid_out[pos] = uid[it];
-                if (pos_of != nullptr) pos_of[uid[it]] = pos;
+        for (int o = 1; o < 32; o <<= 1) {
+            int32_t v = __shfl_up_sync(kFull, inc, o);
+            if ((int)lane_id() >= o) inc += v;
+        }
+        if (lane_id() == 31) warp_sums[wib] = inc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int32_t run = 0;
+            for (int w = 0; w < kSortWarps; ++w) { int32_t t = warp_sums[w]; warp_sums[w] = run; run += t; }
+            warp_sums[kSortWarps] = run;                           // live elements of the CTA
+        }
+        __syncthreads();
+        int32_t lstart = inc - mine + warp_sums[wib];
+#pragma unroll
+        for (int x = 0; x < DPT; ++x) {
+            const int d = threadIdx.x * DPT + x;
+            if (d < nd) {
+                delta[d] = hist_scanned[(int64_t)d * C + blockIdx.x] - lstart;
+                int32_t run = lstart;
+                for (int w = 0; w < kSortWarps; ++w) {
+                    int32_t c = wcnt[w][d];
+                    wcnt[w][d] = (uint16_t)run;
+                    run += c;
+                }
+                lstart += cnt[x];
             }
         }
     }
-    if (FIRST && n_out != nullptr && warp == W - 1 && lane_id() == 0) {
-        // after the last warp's chunk, the running offset of the last digit is the number of survivors
-        *n_out = (int64_t)off[wib][nd - 1];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        if (rank[r] < 0) continue;
+        const unsigned d = (unsigned)(key[r] >> shift) & mask;
+        const int lp = (int)wcnt[wib][d] + rank[r];
+        keys_s[lp] = key[r];
+        uid_s[lp] = uid[r];
+    }
+    __syncthreads();
+    const int live_cta = warp_sums[kSortWarps];
+    for (int j = threadIdx.x; j < live_cta; j += kSortThreads) {
+        const uint64_t kk = keys_s[j];
+        const uint32_t uu = uid_s[j];
+        const int pos = delta[(unsigned)(kk >> shift) & mask] + j;
+        keys_out[pos] = kk;
+        uid_out[pos] = uu;
+        if (pos_of != nullptr) pos_of[uu] = pos;
+        if (sorted_copies != nullptr) sorted_copies[pos] = copies[uu];
     }
 }
 
@@ -140,12 +202,17 @@ __global__ void __launch_bounds__(256) bucket_table_kernel(const uint64_t* __res
     for (int64_t t = prev + 1; t <= cur; ++t) table[t] = (int32_t)i;
 }
 
-// copies of the read at sorted position i (0 past the end of the index): scanned into `cum`
+// copies of the read at sorted position i (0 past the end of the index): scanned into `cum`.
+// sorted_copies (written by the last sort pass) when available, else gathered through sorted_uid.
 struct SortedCopies {
     const uint32_t* sorted_uid;
     const int32_t* copies;
+    const int32_t* sorted_copies;
     const int64_t* n_ptr;
-    __device__ __forceinline__ int64_t operator()(int64_t i) const { return i < *n_ptr ? (int64_t)copies[sorted_uid[i]] : 0; }
+    __device__ __forceinline__ int64_t operator()(int64_t i) const {
+        if (i >= *n_ptr) return 0;
+        return sorted_copies != nullptr ? (int64_t)sorted_copies[i] : (int64_t)copies[sorted_uid[i]];
+    }
 };
 
 // One thread per source read a (overlapGraphs.py:43-52): bucket of suffix_key[a] in the sorted prefix
@@ -213,35 +280,56 @@ constexpr int kTotalsCuts = 64;
 constexpr int kTotalsEdgeBounds = kTotalsBounds + kTotalsCuts + 1;     // ... and the edge offset of each
 constexpr int kTotalsLen = kTotalsEdgeBounds + kTotalsCuts + 1;
 
-__device__ __forceinline__ int64_t join_edge_offset_at(const JoinEdgeIndex& jx, const int32_t* __restrict__ copies, int64_t U,
-                                                       int64_t p, int64_t total_pairs, int64_t total_edges) {
-    if (jx.edge_base == nullptr) return p;              // every read occurs once: one row per pair
-    if (p >= total_pairs) return total_edges;
-    int64_t a = upper_bound<int64_t>(jx.pair_off, 0, U + 1, p) - 1;      // the (non-empty) source that owns pair p
-    return join_edge_offset(jx, copies, p, (int32_t)a);
+// pair index of cut i of the slice [p_begin, p_begin + P): p_begin + floor(P * i / kTotalsCuts), overflow-free
+__device__ __forceinline__ int64_t join_cut(int64_t p_begin, int64_t P, int i) {
+    return p_begin + P / kTotalsCuts * i + P % kTotalsCuts * i / kTotalsCuts;
 }
 
-__global__ void __launch_bounds__(128) join_finalize_kernel(JoinEdgeIndex jx, const int32_t* __restrict__ copies, int64_t U,
+// One thread per source read: the thread whose pair range [pair_off[a], pair_off[a+1]) contains a cut
+// writes that cut's pair index and edge offset -- no search.  Thread 0 writes the scalars and the cuts
+// that sit at the very end of the list.  (The 64-bit divisions are done once per CTA.)
+__global__ void __launch_bounds__(256) join_finalize_kernel(JoinEdgeIndex jx, const int32_t* __restrict__ copies, int64_t U,
                                                             const int32_t* __restrict__ bad, const int64_t* __restrict__ n_indexed,
                                                             int rank, int world, int64_t* __restrict__ totals) {
-    const int64_t total = jx.pair_off[U];
-    const int64_t etotal = jx.edge_base != nullptr ? jx.edge_base[U] : total;
-    const int64_t p_begin = total / world * rank + total % world * rank / world;       // == total * rank / world, no overflow
-    const int64_t p_end = total / world * (rank + 1) + total % world * (rank + 1) / world;
-    const int i = threadIdx.x;
-    if (i == 0) {
+    __shared__ int64_t s_slice[2];
+    __shared__ float s_inv_step;
+    if (threadIdx.x == 0) {
+        const int64_t total = jx.pair_off[U];
+        s_slice[0] = total / world * rank + total % world * rank / world;              // == total * rank / world, no overflow
+        s_slice[1] = total / world * (rank + 1) + total % world * (rank + 1) / world;
+        const int64_t step = (s_slice[1] - s_slice[0]) / kTotalsCuts;
+        s_inv_step = step > 0 ? 1.0f / (float)step : 0.0f;
+    }
+    __syncthreads();
+    const int64_t p_begin = s_slice[0], p_end = s_slice[1];
+    const int64_t P = p_end - p_begin;
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a == 0) {
+        const int64_t total = jx.pair_off[U];
+        const int64_t etotal = jx.edge_base != nullptr ? jx.edge_base[U] : total;
         totals[kTotalsPairs] = total;
         totals[kTotalsEdges] = etotal;
         totals[kTotalsBad] = bad != nullptr ? (int64_t)*bad : 0;
         totals[kTotalsPBegin] = p_begin;
         totals[kTotalsPEnd] = p_end;
         totals[kTotalsIndexed] = n_indexed != nullptr ? *n_indexed : 0;
+        for (int i = kTotalsCuts; i >= 0 && join_cut(p_begin, P, i) >= total; --i) {   // cuts at the end of the whole list
+            totals[kTotalsBounds + i] = total;
+            totals[kTotalsEdgeBounds + i] = etotal;
+        }
     }
-    if (i <= kTotalsCuts) {
-        const int64_t P = p_end - p_begin;
-        const int64_t p = p_begin + P / kTotalsCuts * i + P % kTotalsCuts * i / kTotalsCuts;
+    if (a >= U) return;
+    const int64_t lo_p = jx.pair_off[a], hi_p = jx.pair_off[a + 1];
+    if (hi_p <= lo_p || hi_p <= p_begin || lo_p > p_end) return;
+    // first cut that is >= lo_p: start from the proportional guess and correct
+    int i = (int)fminf((float)kTotalsCuts, fmaxf(0.0f, (float)(lo_p - p_begin) * s_inv_step));
+    while (i > 0 && join_cut(p_begin, P, i - 1) >= lo_p) --i;
+    while (i <= kTotalsCuts && join_cut(p_begin, P, i) < lo_p) ++i;
+    for (; i <= kTotalsCuts; ++i) {
+        const int64_t p = join_cut(p_begin, P, i);
+        if (p >= hi_p) break;
         totals[kTotalsBounds + i] = p;
-        totals[kTotalsEdgeBounds + i] = join_edge_offset_at(jx, copies, U, p, total, etotal);
+        totals[kTotalsEdgeBounds + i] = jx.edge_base != nullptr ? join_edge_offset(jx, copies, p, (int32_t)a) : p;
     }
 }
 
@@ -283,39 +371,42 @@ __global__ void __launch_bounds__(kFillThreads) join_fill_kernel(const int64_t* 
     }
 }
 
-// Same output, one warp per source read: used when buckets are large (mean >= 32 candidates per
-// read), where every lane streams consecutive candidates -- no search, fully coalesced stores; four
+// Same output, LANES lanes per source read (32: a warp streams a large bucket; 8 / 4 / 1 for smaller
+// buckets, so that lanes are not idle): no search, the lanes of a group write consecutive pairs; four
 // independent loads in flight per lane.
-__global__ void __launch_bounds__(256) join_fill_warp_kernel(const int64_t* __restrict__ pair_off, int64_t nA, int64_t a_begin,
-                                                             const int32_t* __restrict__ lo, const int32_t* __restrict__ self_rank,
-                                                             const uint32_t* __restrict__ sorted_uid,
-                                                             int64_t p_begin, int64_t p_count,
-                                                             int32_t* __restrict__ pair_a, int32_t* __restrict__ pair_b) {
-    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+template <int LANES>
+__global__ void __launch_bounds__(256) join_fill_group_kernel(const int64_t* __restrict__ pair_off, int64_t nA, int64_t a_begin,
+                                                              const int32_t* __restrict__ lo, const int32_t* __restrict__ self_rank,
+                                                              const uint32_t* __restrict__ sorted_uid,
+                                                              int64_t p_begin, int64_t p_count,
+                                                              int32_t* __restrict__ pair_a, int32_t* __restrict__ pair_b) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = t / LANES;
     if (i >= nA) return;
-    int64_t first = pair_off[i], last = pair_off[i + 1];
-    int64_t from = max(first, p_begin), to = min(last, p_begin + p_count);
+    const int sub = (int)(t % LANES);
+    const int64_t first = pair_off[i], last = pair_off[i + 1];
+    const int64_t from = max(first, p_begin), to = min(last, p_begin + p_count);
     if (from >= to) return;
     const int32_t sr = self_rank[i];
     const uint32_t* __restrict__ bucket = sorted_uid + lo[i];
     const int32_t a = (int32_t)(a_begin + i);
-    int64_t p = from + lane_id();
-    for (; p + 96 < to; p += 128) {
+    int64_t p = from + sub;
+    for (; p + 3 * LANES < to; p += 4 * LANES) {
         int32_t b[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            int32_t r = (int32_t)(p + 32 * j - first);
+            int32_t r = (int32_t)(p + LANES * j - first);
             if (sr >= 0 && r >= sr) r += 1;
             b[j] = (int32_t)bucket[r];
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            int64_t q = p + 32 * j - p_begin;
+            int64_t q = p + LANES * j - p_begin;
             pair_a[q] = a;
             pair_b[q] = b[j];
         }
     }
-    for (; p < to; p += 32) {
+    for (; p < to; p += LANES) {
         int32_t r = (int32_t)(p - first);
         if (sr >= 0 && r >= sr) r += 1;
         int64_t q = p - p_begin;

@@ -13,119 +13,113 @@ namespace ovl {
 // compared for equality and the DP only tests s[i] == t[j].
 constexpr uint64_t kInvalidKey = ~0ull;
 
-// ------------------------------------------------------------------ K0 pack_reads
-// One thread per 4 output words (64 bases, one 16-byte store).  The read's ASCII bytes start at
-// an arbitrary byte offset, so the thread loads the five aligned 16-byte segments that cover
-// its 64 bytes (all issued up front) and funnel-shifts them into place; the segment shared with
-// the neighbouring thread comes from L1, DRAM sees each byte once.  Requires: ascii base 16-byte
-// aligned and >= 32 bytes of slack after the last read.
-__device__ __forceinline__ uint32_t pack16(const uint32_t r[4], int nvalid, uint32_t& bad) {
-    uint32_t out = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int nv = nvalid - 4 * i;                     // valid bytes in this word
-        uint32_t keep = nv >= 4 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u));
-        uint32_t c = (r[i] & keep) | (0x41414141u & ~keep);          // filler 'A' -> code 0
-        uint32_t t = (c >> 1) & 0x03030303u;
-        // exact check: rebuild the byte each code stands for and compare
-        uint32_t is_t = (t >> 1) & ~t & 0x01010101u;                 // code 2 == 'T'
-        uint32_t expect = 0x41414141u + 2u * t + 0x0fu * is_t;       // A 41, C 43, G 47, T 54
-        bad |= c ^ expect;
-        // gather the four 2-bit fields (at bits 0,8,16,24) into one byte with a multiply
-        uint32_t pk = (t * 0x01041040u) >> 24;
-        out |= pk << (8 * i);
-    }
-    return out;
+// ------------------------------------------------------------------ K0 pack_reads (+ K1 fused)
+// One thread per 4 output words (64 bases, one 16-byte store), 256 such slots per CTA.  The slots of a CTA
+// cover one contiguous span of the ASCII input (<= 16 KB), so the CTA
+//   1. converts the span in ALIGNED 16-byte pieces -- perfectly coalesced 128-bit loads, each piece
+//      becomes one 32-bit word of 2-bit codes in shared memory (with an exact A/C/G/T check), and
+//   2. lets every thread cut its 4 output words out of that bit stream at its read's own (arbitrary) byte
+//      offset: two shared-memory words and one funnel shift per output word.
+// The byte re-alignment therefore happens on the 4x smaller packed stream, not on the ASCII bytes.
+// KEYS (K1 fused): the prefix k-mer is the first words of the row; the suffix k-mer is cut out of the same
+// bit stream (the span starts 32 bases early so that a k-mer reaching back into the previous slot is there).
+// Requires: ascii base 16-byte aligned and >= 32 bytes of slack after the last read.
+constexpr int kPackThreads = 256;
+constexpr int kPackPieces = (kPackThreads * 64 + 32 + 16) / 16 + 2;      // 16-byte pieces a CTA's span can touch
+
+// 4 ASCII bytes -> their 2-bit codes gathered in byte 3 of the result; `bad` collects c ^ (the letter each code stands for)
+__device__ __forceinline__ uint32_t codes4(uint32_t c, uint32_t& bad) {
+    uint32_t t = (c >> 1) & 0x03030303u;
+    uint32_t is_t = (t >> 1) & ~t & 0x01010101u;                 // code 2 == 'T'
+    uint32_t expect = 0x41414141u + 2u * t + 0x0fu * is_t;       // A 41, C 43, G 47, T 54
+    bad |= c ^ expect;
+    return t * 0x01041040u;                                      // the four 2-bit fields land in bits 24..31
 }
 
-// bits [o, o + 64) of the word array w[0..7] (o < 192), without dynamic register indexing
-__device__ __forceinline__ uint64_t window64(const uint32_t (&w)[8], int o) {
-    const int wi = o >> 5, sh = o & 31;
-    uint32_t a = 0, b = 0, c = 0;
-#pragma unroll
-    for (int j = 0; j < 6; ++j)
-        if (wi == j) { a = w[j]; b = w[j + 1]; c = w[j + 2]; }
-    return ((uint64_t)__funnelshift_r(b, c, sh) << 32) | __funnelshift_r(a, b, sh);
-}
-
-// KEYS: K1 fused into K0 -- the thread that packs a read's first 64 bases holds its prefix k-mer, the
-// thread that packs its last bases holds (with one shuffle from its left neighbour when the k-mer
-// straddles two 64-base groups) its suffix k-mer, so the keys cost no further pass over the rows.
 template <bool KEYS>
-__global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t* __restrict__ ascii,
-                                                         const int64_t* __restrict__ offsets,
-                                                         int64_t U, int row_words,
-                                                         uint32_t* __restrict__ packed,
-                                                         int32_t* __restrict__ len_out,
-                                                         int32_t* __restrict__ bad_count,
-                                                         int k, const int32_t* __restrict__ segment,
-                                                         uint64_t* __restrict__ prefix_key,
-                                                         uint64_t* __restrict__ suffix_key) {
+__global__ void __launch_bounds__(kPackThreads) pack_reads_kernel(const uint8_t* __restrict__ ascii,
+                                                                  const int64_t* __restrict__ offsets,
+                                                                  int64_t U, int row_words,
+                                                                  uint32_t* __restrict__ packed,
+                                                                  int32_t* __restrict__ len_out,
+                                                                  int32_t* __restrict__ bad_count,
+                                                                  int k, const int32_t* __restrict__ segment,
+                                                                  uint64_t* __restrict__ prefix_key,
+                                                                  uint64_t* __restrict__ suffix_key) {
+    __shared__ uint32_t bits[kPackPieces + 3];
+    __shared__ int64_t s_span[2];
     const int quads = row_words >> 2;                // 16-byte groups per row
-    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = slot < U * quads;
-    if (!KEYS && !active) return;
-    const int64_t u = active ? slot / quads : 0;
-    const int q = active ? (int)(slot - u * quads) : 0;
-    int64_t o0 = 0;
-    int len = 0;
+    const int64_t n_slots = U * quads;
+    const int64_t slot = (int64_t)blockIdx.x * kPackThreads + threadIdx.x;
+    const bool active = slot < n_slots;
+    int64_t u = 0, o0 = 0;
+    int q = 0, len = 0;
     if (active) {
+        u = slot / quads;
+        q = (int)(slot - u * quads);
         o0 = offsets[u];
         len = (int)(offsets[u + 1] - o0);
         if (q == 0) len_out[u] = len;
     }
-    const int nvalid = len - 64 * q;                 // bases this thread holds
-    uint4 outv = make_uint4(0u, 0u, 0u, 0u);
-    if (nvalid > 0) {
-        int64_t addr = o0 + 64 * (int64_t)q;         // byte index of the first base
-        const uint4* seg = reinterpret_cast<const uint4*>(ascii + (addr & ~(int64_t)15));
-        int nseg = min(5, (int)(((addr & 15) + min(nvalid, 64) + 15) >> 4));
-        uint4 sv[5];
+    const int nvalid = len - 64 * q;                 // bases this thread holds (<= 0: none)
+    const int64_t my_begin = o0 + min(64 * q, len);
+    if (threadIdx.x == 0) s_span[0] = max((int64_t)0, my_begin - 32) & ~(int64_t)15;
+    if (active && (threadIdx.x == kPackThreads - 1 || slot == n_slots - 1)) s_span[1] = o0 + min(64 * (q + 1), len);
+    __syncthreads();
+    const int64_t span_base = s_span[0];
+    const int n_pieces = (int)((s_span[1] - span_base + 15) >> 4);
+    const int64_t total_bytes = offsets[U];
+    uint32_t bad = 0;
+    for (int p = threadIdx.x; p < n_pieces + 3; p += kPackThreads) {
+        uint32_t w = 0;
+        if (p < n_pieces) {
+            const int64_t g = span_base + 16 * (int64_t)p;
+            uint4 v = __ldg(reinterpret_cast<const uint4*>(ascii + g));
+            if (g + 16 > total_bytes) {              // the slack after the last read is not input: treat it as 'A'
+                uint32_t x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int i = 0; i < 5; ++i) sv[i] = i < nseg ? __ldg(seg + i) : make_uint4(0u, 0u, 0u, 0u);
-        uint32_t x[20];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) { x[4 * i] = sv[i].x; x[4 * i + 1] = sv[i].y; x[4 * i + 2] = sv[i].z; x[4 * i + 3] = sv[i].w; }
-        unsigned sh = (unsigned)(addr & 15);
-        // shift right by sh bytes: 8, 4, then 0..3 bytes
-        uint32_t y[18], z[17], r[16];
-#pragma unroll
-        for (int i = 0; i < 18; ++i) y[i] = (sh & 8) ? x[i + 2] : x[i];
-#pragma unroll
-        for (int i = 0; i < 17; ++i) z[i] = (sh & 4) ? y[i + 1] : y[i];
-        unsigned bs = (sh & 3) * 8;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = __funnelshift_r(z[i], z[i + 1], bs);
-        uint32_t bad = 0;
-        outv.x = pack16(r, nvalid, bad);
-        outv.y = pack16(r + 4, nvalid - 16, bad);
-        outv.z = pack16(r + 8, nvalid - 32, bad);
-        outv.w = pack16(r + 12, nvalid - 48, bad);
-        if (bad) atomicAdd(bad_count, 1);
+                for (int i = 0; i < 4; ++i) {
+                    int64_t nv = total_bytes - (g + 4 * i);
+                    uint32_t keep = nv >= 4 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << (8 * (int)nv)) - 1u));
+                    x[i] = (x[i] & keep) | (0x41414141u & ~keep);
+                }
+                v = make_uint4(x[0], x[1], x[2], x[3]);
+            }
+            const uint32_t m0 = codes4(v.x, bad), m1 = codes4(v.y, bad), m2 = codes4(v.z, bad), m3 = codes4(v.w, bad);
+            w = __byte_perm(__byte_perm(m0, m1, 0x0073), __byte_perm(m2, m3, 0x0073), 0x5410);
+        }
+        bits[p] = w;                                 // three zero words of padding after the stream
     }
-    if (active) reinterpret_cast<uint4*>(packed)[slot] = outv;
+    if (bad) atomicAdd(bad_count, 1);
+    __syncthreads();
+    if (!active) return;
+    uint32_t o[4] = {0u, 0u, 0u, 0u};
+    if (nvalid > 0) {
+        const int bit0 = 2 * (int)(my_begin - span_base);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int nv = nvalid - 16 * w;
+            if (nv > 0) {
+                const int bit = bit0 + 32 * w;
+                uint32_t x = __funnelshift_r(bits[bit >> 5], bits[(bit >> 5) + 1], bit & 31);
+                if (nv < 16) x &= (1u << (2 * nv)) - 1u;
+                o[w] = x;
+            }
+        }
+    }
+    reinterpret_cast<uint4*>(packed)[slot] = make_uint4(o[0], o[1], o[2], o[3]);
     if (KEYS) {
-        // bases 32..63 of the left neighbour's group (the same read's previous group when q > 0)
-        const uint32_t pz = __shfl_up_sync(kFull, outv.z, 1), pw = __shfl_up_sync(kFull, outv.w, 1);
-        if (!active) return;
         const uint64_t mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
         const uint64_t tag = segment != nullptr ? (uint64_t)(uint32_t)segment[u] << (2 * k) : 0ull;
         if (q == 0)                                                       // overlapGraphs.py:33-37: prefix = read[:k]
-            prefix_key[u] = len >= k ? (((((uint64_t)outv.y << 32) | outv.x) & mask) | tag) : kInvalidKey;
+            prefix_key[u] = len >= k ? (((((uint64_t)o[1] << 32) | o[0]) & mask) | tag) : kInvalidKey;
         if (q == (len > 0 ? (len - 1) >> 6 : 0)) {                        // :44-47: suffix = read[-k:]
             uint64_t sk = kInvalidKey;
             if (len >= k) {
-                const int s_local = len - k - 64 * q;                     // first base of the k-mer, relative to my group (>= -31)
-                if (s_local >= 0 || lane_id() != 0) {
-                    const uint32_t w[8] = {pz, pw, outv.x, outv.y, outv.z, outv.w, 0u, 0u};
-                    sk = window64(w, 64 + 2 * s_local);
-                } else {
-                    // the k-mer starts in a group packed by another warp: take it from the ASCII bytes (L1/L2 hits)
-                    sk = 0;
-                    const uint8_t* p = ascii + o0 + (len - k);
-                    for (int i = 0; i < k; ++i) sk |= (uint64_t)((p[i] >> 1) & 3u) << (2 * i);
-                }
-                sk = (sk & mask) | tag;
+                const int bit = 2 * (int)(o0 + len - k - span_base);      // >= 0: the span starts 32 bases before my slot
+                const int i = bit >> 5, sh = bit & 31;
+                const uint32_t a = bits[i], b = bits[i + 1], c = bits[i + 2];
+                sk = ((((uint64_t)__funnelshift_r(b, c, sh) << 32) | __funnelshift_r(a, b, sh)) & mask) | tag;
             }
             suffix_key[u] = sk;
         }

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 #include "common.cuh"
@@ -172,7 +173,7 @@ int ovl_kmer_hashes(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, con
 }
 
 // ---------------------------------------------------------------- K2
-// workspace: [hist int32 2^D*W + 1][scan sums][tmp keys u64 U][tmp uids u32 U]
+// workspace: [hist int32 2^D*C + 1][scan sums][tmp keys u64 U][tmp uids u32 U]     (C = CTAs of 2,048 elements)
 static inline int64_t sort_warps(int64_t U) { return (U + kSortChunk - 1) / kSortChunk; }
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -196,14 +197,15 @@ int32_t ovl_index_table_bits(int64_t U, int32_t key_bits) {
 }
 
 int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len, int64_t U, int32_t k, int32_t key_bits, uint64_t* sorted_key,
-                    uint32_t* sorted_uid, int64_t* n_indexed, int32_t* table, int32_t table_bits, int32_t* pos_of, void* workspace,
-                    size_t workspace_bytes, void* stream) {
+                    uint32_t* sorted_uid, int64_t* n_indexed, int32_t* table, int32_t table_bits, int32_t* pos_of,
+                    const int32_t* copies, int32_t* sorted_copies, void* workspace, size_t workspace_bytes, void* stream) {
     ON_CTX_DEVICE(ctx);
     if (!ctx || !prefix_key || !len || !sorted_key || !sorted_uid || !n_indexed || !workspace) return fail(OVL_E_ARG, "ovl_index_build: null argument");
     if (k < 1) return fail(OVL_E_ARG, "ovl_index_build: k must be positive");
     if (k > OVL_MAX_K && key_bits != 64) return fail(OVL_E_ARG, "ovl_index_build: k=%d > %d needs hashed keys (key_bits = 64)", k, OVL_MAX_K);
     if (workspace_bytes < ovl_index_workspace_bytes(U)) return fail(OVL_E_ARG, "ovl_index_build: workspace too small");
     if (U > 0x7fffffffll) return fail(OVL_E_UNSUPPORTED, "ovl_index_build: more than 2^31 - 1 reads");
+    if ((copies != nullptr) != (sorted_copies != nullptr)) return fail(OVL_E_ARG, "ovl_index_build: copies and sorted_copies go together");
     cudaStream_t st = (cudaStream_t)stream;
     if (key_bits <= 0) key_bits = 2 * k;                 // no segment tag above the k-mer
     if ((key_bits < 2 * k && k <= OVL_MAX_K) || key_bits > 64) return fail(OVL_E_ARG, "ovl_index_build: key_bits=%d outside [2k, 64]", key_bits);
@@ -229,14 +231,16 @@ int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len
     uint64_t* kbuf[2] = {sorted_key, tmp_key};
     uint32_t* ubuf[2] = {sorted_uid, tmp_uid};
     int dst = (passes & 1) ? 0 : 1;
-    unsigned grid = grid_for(W, kSortWarps);
+    unsigned grid = (unsigned)W;                        // one CTA per 2,048-element chunk
     const uint64_t* src_key = prefix_key;
     const uint32_t* src_uid = nullptr;
     for (int p = 0; p < passes; ++p) {
         int shift = D * p;
         int bits = std::min(D, key_bits - shift);
         int64_t hn = ((int64_t)1 << bits) * W;
-        int32_t* pos_out = (p == passes - 1) ? pos_of : nullptr;
+        const bool last_pass = p == passes - 1;
+        int32_t* pos_out = last_pass ? pos_of : nullptr;
+        int32_t* sc_out = last_pass ? sorted_copies : nullptr;
         if (p == 0) {
             sort_hist_kernel<true><<<grid, kSortThreads, 0, st>>>(src_key, len, k, nullptr, U, shift, bits, W, hist);
         } else {
@@ -246,10 +250,10 @@ int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len
         CUDA_TRY((exclusive_scan<LoadArray<int32_t>, int32_t>(LoadArray<int32_t>{hist}, hist, hn, sums, st, &nl)));
         if (p == 0) {
             sort_scatter_kernel<true><<<grid, kSortThreads, 0, st>>>(src_key, nullptr, len, k, nullptr, U, shift, bits, W, hist,
-                                                                     kbuf[dst], ubuf[dst], pos_out, n_indexed);
+                                                                     kbuf[dst], ubuf[dst], pos_out, copies, sc_out, n_indexed);
         } else {
             sort_scatter_kernel<false><<<grid, kSortThreads, 0, st>>>(src_key, src_uid, len, k, n_indexed, 0, shift, bits, W, hist,
-                                                                      kbuf[dst], ubuf[dst], pos_out, nullptr);
+                                                                      kbuf[dst], ubuf[dst], pos_out, copies, sc_out, nullptr);
         }
         LAUNCH_CHECK("sort_scatter_kernel");
         src_key = kbuf[dst];
@@ -273,9 +277,9 @@ size_t ovl_join_workspace_bytes(int64_t n_sources) {
 
 int ovl_join_count(ovl_ctx* ctx, const uint64_t* suffix_key, const uint64_t* prefix_key, const int32_t* len, int32_t k, int64_t U,
                    const uint64_t* sorted_key, const uint32_t* sorted_uid, const int64_t* n_indexed, const int32_t* table,
-                   int32_t table_bits, int32_t key_bits, const int32_t* pos_of, const int32_t* copies, int64_t* cum,
-                   int32_t* bucket_lo, int32_t* self_rank, int64_t* pair_off, int64_t* edge_base, void* workspace,
-                   size_t workspace_bytes, void* stream) {
+                   int32_t table_bits, int32_t key_bits, const int32_t* pos_of, const int32_t* copies,
+                   const int32_t* sorted_copies, int64_t* cum, int32_t* bucket_lo, int32_t* self_rank, int64_t* pair_off,
+                   int64_t* edge_base, void* workspace, size_t workspace_bytes, void* stream) {
     ON_CTX_DEVICE(ctx);
     if (!ctx || !suffix_key || !prefix_key || !len || !sorted_key || !sorted_uid || !n_indexed || !bucket_lo || !self_rank || !pair_off || !workspace)
         return fail(OVL_E_ARG, "ovl_join_count: null argument");
@@ -291,7 +295,7 @@ int ovl_join_count(ovl_ctx* ctx, const uint64_t* suffix_key, const uint64_t* pre
     int nl = 0;
     if (copies) {
         // copies along the sorted index, scanned: the copy mass of any bucket range is a difference of two entries
-        CUDA_TRY((exclusive_scan<SortedCopies, int64_t>(SortedCopies{sorted_uid, copies, n_indexed}, cum, U, sums, st, &nl)));
+        CUDA_TRY((exclusive_scan<SortedCopies, int64_t>(SortedCopies{sorted_uid, copies, sorted_copies, n_indexed}, cum, U, sums, st, &nl)));
     }
     if (U > 0) {
         join_count_kernel<<<grid_for(U, 256), 256, 0, st>>>(suffix_key, prefix_key, len, k, U, sorted_key, sorted_uid, n_indexed, table,
@@ -318,7 +322,7 @@ int ovl_join_finalize(ovl_ctx* ctx, const int64_t* pair_off, const int64_t* edge
     if (edge_base && (!bucket_lo || !self_rank || !cum || !copies)) return fail(OVL_E_ARG, "ovl_join_finalize: edge_base given without the join index");
     if (world < 1 || rank < 0 || rank >= world) return fail(OVL_E_ARG, "ovl_join_finalize: rank %d outside world %d", rank, world);
     JoinEdgeIndex jx{pair_off, edge_base, bucket_lo, self_rank, cum, 0, 0};
-    join_finalize_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(jx, copies, U, bad_count, n_indexed, rank, world, totals);
+    join_finalize_kernel<<<grid_for(std::max<int64_t>(U, 1), 256), 256, 0, (cudaStream_t)stream>>>(jx, copies, U, bad_count, n_indexed, rank, world, totals);
     LAUNCH_CHECK("join_finalize_kernel");
     return OVL_OK;
 }
@@ -330,16 +334,23 @@ int ovl_join_fill(ovl_ctx* ctx, const int64_t* pair_off, int64_t a_begin, int64_
     if (!ctx || !pair_off || !bucket_lo || !self_rank || !sorted_uid || !pair_a || !pair_b) return fail(OVL_E_ARG, "ovl_join_fill: null argument");
     if (p_count <= 0) return OVL_OK;
     int64_t nA = a_end - a_begin;
-    if (total_hint >= 32 * nA) {
-        // large buckets: one warp per source read streams its candidates
-        join_fill_warp_kernel<<<grid_for(nA * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+    // lanes per source read, by the mean bucket size (total_hint / nA); OVL_FILL_LANES overrides (tuning knob)
+    cudaStream_t st = (cudaStream_t)stream;
+    static const int force_lanes = getenv("OVL_FILL_LANES") ? atoi(getenv("OVL_FILL_LANES")) : -1;
+#define FILL_GROUP(L) join_fill_group_kernel<L><<<grid_for(nA * L, 256), 256, 0, st>>>(pair_off, nA, a_begin, bucket_lo, self_rank, sorted_uid, p_begin, p_count, pair_a, pair_b)
+    const int lanes = force_lanes >= 0 ? force_lanes
+                    : total_hint >= 48 * nA ? 32 : total_hint >= 12 * nA ? 8 : total_hint >= 3 * nA ? 4 : total_hint * 8 >= nA ? 1 : 0;
+    if (lanes == 32) FILL_GROUP(32);
+    else if (lanes == 8) FILL_GROUP(8);
+    else if (lanes == 4) FILL_GROUP(4);
+    else if (lanes == 1) FILL_GROUP(1);
+    else {
+        // sparse: most source reads have no candidate at all -- one thread per output pair
+        join_fill_kernel<<<grid_for(p_count, kFillTile), kFillThreads, 0, st>>>(
             pair_off, nA, a_begin, bucket_lo, self_rank, sorted_uid, p_begin, p_count, pair_a, pair_b);
-        LAUNCH_CHECK("join_fill_warp_kernel");
-    } else {
-        join_fill_kernel<<<grid_for(p_count, kFillTile), kFillThreads, 0, (cudaStream_t)stream>>>(
-            pair_off, nA, a_begin, bucket_lo, self_rank, sorted_uid, p_begin, p_count, pair_a, pair_b);
-        LAUNCH_CHECK("join_fill_kernel");
     }
+#undef FILL_GROUP
+    LAUNCH_CHECK("join_fill kernel");
     return OVL_OK;
 }
 
@@ -377,6 +388,7 @@ int ovl_candidates_layout(int64_t U, int32_t max_len, int32_t k, int32_t n_segme
     out->pair_off = take((size_t)(n + 1) * 8);
     out->edge_base = has_copies ? take((size_t)(n + 1) * 8) : 0;
     out->cum = has_copies ? take((size_t)(n + 1) * 8) : 0;
+    out->sorted_copies = has_copies ? take((size_t)n * 4) : 0;
     out->has_copies = has_copies ? 1 : 0;
     out->scratch = off;
     out->scratch_bytes = std::max(ovl_index_workspace_bytes(U), ovl_join_workspace_bytes(U));
@@ -409,14 +421,16 @@ int ovl_candidates_build(ovl_ctx* ctx, const uint8_t* ascii, const int64_t* offs
     int64_t* pair_off = (int64_t*)(base + lay->pair_off);
     int64_t* edge_base = copies ? (int64_t*)(base + lay->edge_base) : nullptr;
     int64_t* cum = copies ? (int64_t*)(base + lay->cum) : nullptr;
+    int32_t* sorted_copies = copies ? (int32_t*)(base + lay->sorted_copies) : nullptr;
     void* scratch = base + lay->scratch;
     CUDA_TRY(cudaMemsetAsync(bad, 0, 8, st));
     int rc = pack_launch(ctx, ascii, offsets, U, lay->row_words, k, segments, packed, len, bad, pk, sk, st, "ovl_candidates_build");
     if (rc != OVL_OK) return rc;
-    rc = ovl_index_build(ctx, pk, len, U, k, lay->key_bits, skey, suid, n_indexed, table, lay->table_bits, pos_of, scratch, lay->scratch_bytes, stream);
+    rc = ovl_index_build(ctx, pk, len, U, k, lay->key_bits, skey, suid, n_indexed, table, lay->table_bits, pos_of, copies, sorted_copies,
+                         scratch, lay->scratch_bytes, stream);
     if (rc != OVL_OK) return rc;
-    rc = ovl_join_count(ctx, sk, pk, len, k, U, skey, suid, n_indexed, table, lay->table_bits, lay->key_bits, pos_of, copies, cum, lo, sr,
-                        pair_off, edge_base, scratch, lay->scratch_bytes, stream);
+    rc = ovl_join_count(ctx, sk, pk, len, k, U, skey, suid, n_indexed, table, lay->table_bits, lay->key_bits, pos_of, copies, sorted_copies,
+                        cum, lo, sr, pair_off, edge_base, scratch, lay->scratch_bytes, stream);
     if (rc != OVL_OK) return rc;
     return ovl_join_finalize(ctx, pair_off, edge_base, lo, sr, cum, copies, U, bad, n_indexed, rank, world, totals, stream);
 }
@@ -927,6 +941,23 @@ int ovl_local_align(ovl_ctx* ctx, const int32_t* query, int32_t n, const int32_t
         local_align_kernel<false><<<1, threads, 0, (cudaStream_t)stream>>>(query, n, reference, m, match, mismatch, indel, diag, tb, result, ops);
     }
     LAUNCH_CHECK("local_align_kernel");
+    return OVL_OK;
+}
+
+int ovl_local_align_batch(ovl_ctx* ctx, const int32_t* queries, const int64_t* q_off, int32_t n_queries, int32_t max_query_len,
+                          const int32_t* reference, const int32_t* ref_start, const int32_t* ref_len, int64_t match,
+                          int64_t mismatch, int64_t indel, uint8_t* tb, const int64_t* tb_off, int32_t* results, uint8_t* ops,
+                          const int64_t* ops_off, void* stream) {
+    ON_CTX_DEVICE(ctx);
+    if (n_queries <= 0) return OVL_OK;
+    if (!ctx || !queries || !q_off || !reference || !ref_start || !ref_len || !tb || !tb_off || !results || !ops || !ops_off)
+        return fail(OVL_E_ARG, "ovl_local_align_batch: null argument");
+    if (max_query_len < 0 || max_query_len > kAlignThreads)
+        return fail(OVL_E_UNSUPPORTED, "ovl_local_align_batch: queries longer than %d symbols go through ovl_local_align", kAlignThreads);
+    int threads = std::max(32, ((max_query_len + 31) / 32) * 32);
+    local_align_batch_kernel<<<(unsigned)n_queries, threads, 0, (cudaStream_t)stream>>>(
+        queries, q_off, reference, ref_start, ref_len, match, mismatch, indel, (int8_t*)tb, tb_off, results, ops, ops_off);
+    LAUNCH_CHECK("local_align_batch_kernel");
     return OVL_OK;
 }
 

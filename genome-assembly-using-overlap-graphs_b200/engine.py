@@ -246,7 +246,7 @@ class OverlapEngine:
             table = self._empty((1 << table_bits) + 1, torch.int32)
             pos_of = self._empty(U, torch.int32)
         nat.check(nat.lib.ovl_index_build(self._ctx, _ptr(pk), _ptr(rs.length), U, k, key_bits, _ptr(sorted_key), _ptr(sorted_uid),
-                                          _ptr(n_indexed), _ptr(table), table_bits, _ptr(pos_of), _ptr(ws), ws_bytes,
+                                          _ptr(n_indexed), _ptr(table), table_bits, _ptr(pos_of), None, None, _ptr(ws), ws_bytes,
                                           self._stream()))
         return KmerIndex(k, pk, sk, sorted_key, sorted_uid, n_indexed, kb, table, table_bits, pos_of)
 
@@ -294,7 +294,7 @@ class OverlapEngine:
                                          _ptr(rs.length), k, U,
                                          _ptr(index.sorted_key), _ptr(index.sorted_uid), _ptr(index.n_indexed),
                                          _ptr(index.table), index.table_bits, index.key_bits, _ptr(index.pos_of),
-                                         None, None, _ptr(lo), _ptr(self_rank), _ptr(pair_off), None,
+                                         None, None, None, _ptr(lo), _ptr(self_rank), _ptr(pair_off), None,
                                          _ptr(ws), ws_bytes, st))
         total = self._total_and_alphabet(rs, pair_off[U])    # host sync: the output size
         p_begin, p_end = total * rank // world, total * (rank + 1) // world
@@ -685,6 +685,50 @@ class OverlapEngine:
                                           _ptr(ws), ws_bytes, _ptr(result), _ptr(ops), self._stream()))
         res = result.cpu().numpy()
         return int(res[0]), int(res[1]), int(res[2]), int(res[4]), ops[:int(res[3])].cpu().numpy()
+
+    def local_align_batch(self, queries, r_codes: np.ndarray, windows, match_score: int = 10, mismatch: int = -1,
+                          indel: int = -1):
+        """Many queries (int32 code arrays, each <= OVL_LOCAL_BATCH_MAX_QUERY symbols) against windows
+        (start, length) of one reference, ONE launch with one CTA per query (aligners.py:85-167 each).
+        Returns [(best_score, start_pos, end_pos, best_i, ops)] with positions relative to the window."""
+        nq = len(queries)
+        if nq == 0:
+            return []
+        lens = np.fromiter((len(q) for q in queries), dtype=np.int64, count=nq)
+        if int(lens.max()) > nat.OVL_LOCAL_BATCH_MAX_QUERY:
+            raise nat.OvlUnsupported(f"batched local alignment takes queries of at most {nat.OVL_LOCAL_BATCH_MAX_QUERY} symbols")
+        q_off = np.zeros(nq + 1, np.int64)
+        np.cumsum(lens, out=q_off[1:])
+        w = np.asarray(windows, dtype=np.int64).reshape(nq, 2)
+        m = w[:, 1]
+        tb_sz = ((lens + 1) * (lens + m + 2) + 15) // 16 * 16
+        ops_sz = (lens + m + 1 + 15) // 16 * 16
+        tb_off = np.zeros(nq + 1, np.int64)
+        np.cumsum(tb_sz, out=tb_off[1:])
+        ops_off = np.zeros(nq + 1, np.int64)
+        np.cumsum(ops_sz, out=ops_off[1:])
+        q_all = np.concatenate([np.asarray(q, dtype=np.int32) for q in queries] + [np.zeros(1, np.int32)])
+        d_q = self._to_device(q_all, torch.int32)
+        d_ref = self._to_device(np.concatenate([r_codes.astype(np.int32), np.zeros(1, np.int32)]), torch.int32)
+        meta = np.concatenate([q_off, tb_off[:-1], ops_off[:-1]])
+        d_meta = self._to_device(meta, torch.int64)
+        d_win = self._to_device(np.concatenate([w[:, 0], w[:, 1]]).astype(np.int32), torch.int32)
+        tb = self._empty(int(tb_off[-1]), torch.uint8)
+        ops = self._empty(int(ops_off[-1]), torch.uint8)
+        results = torch.zeros(nq * 8, dtype=torch.int32, device=self.device)
+        base = d_meta.data_ptr()
+        nat.check(nat.lib.ovl_local_align_batch(
+            self._ctx, _ptr(d_q), ctypes.c_void_p(base), nq, int(lens.max()), _ptr(d_ref),
+            ctypes.c_void_p(d_win.data_ptr()), ctypes.c_void_p(d_win.data_ptr() + 4 * nq),
+            int(match_score), int(mismatch), int(indel), _ptr(tb), ctypes.c_void_p(base + 8 * (nq + 1)),
+            _ptr(results), _ptr(ops), ctypes.c_void_p(base + 8 * (2 * nq + 1)), self._stream()))
+        res = results.cpu().numpy().reshape(nq, 8)
+        ops_h = ops.cpu().numpy()
+        out = []
+        for x in range(nq):
+            o0 = int(ops_off[x])
+            out.append((int(res[x, 0]), int(res[x, 1]), int(res[x, 2]), int(res[x, 4]), ops_h[o0:o0 + int(res[x, 3])]))
+        return out
 
     # ------------------------------------------------------------------ K6
     def expand_edges(self, pair_a, pair_b, score, end, copies: Optional[torch.Tensor] = None,

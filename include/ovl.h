@@ -96,13 +96,17 @@ int ovl_pack_reads_keys(ovl_ctx *ctx, const uint8_t *ascii, const int64_t *offse
  *           table_bits == key_bits (4^k <= 2^22) a bucket is table[key] .. table[key + 1] -- the
  *           dict lookup of overlapGraphs.py:49 without any search.  ovl_index_table_bits gives the
  *           size this library picks for (U, key_bits).
- *   pos_of  int32[U]: sorted position of every indexed read (its own slot in its bucket). */
+ *   pos_of  int32[U]: sorted position of every indexed read (its own slot in its bucket).
+ *   copies / sorted_copies (both or neither): int32[U] multiplicity of every read in, the same along
+ *           the sorted index out (sorted_copies[i] = copies[sorted_uid[i]]) -- what ovl_join_count
+ *           scans when reads have copies. */
 size_t ovl_index_workspace_bytes(int64_t U);
 int32_t ovl_index_table_bits(int64_t U, int32_t key_bits);
 /* key_bits: number of significant key bits to sort on (2k + segment-tag bits); 0 means 2k. */
 int ovl_index_build(ovl_ctx *ctx, const uint64_t *prefix_key, const int32_t *len, int64_t U, int32_t k,
                     int32_t key_bits, uint64_t *sorted_key, uint32_t *sorted_uid, int64_t *n_indexed,
                     int32_t *table, int32_t table_bits, int32_t *pos_of,
+                    const int32_t *copies, int32_t *sorted_copies,
                     void *workspace, size_t workspace_bytes, void *stream);
 
 /* K3: candidate generation, overlapGraphs.py:43-52, for all source reads a in [0, U).
@@ -112,7 +116,7 @@ int ovl_index_build(ovl_ctx *ctx, const uint64_t *prefix_key, const int32_t *len
  * and the own slot are found by binary search.
  * With duplicate reads (copies != NULL; overlapGraphs.py:55-60 expands pair (a, b) to
  * copies[a] * copies[b] edges) it also writes cum[U+1], the exclusive scan of copies along the sorted
- * index, and edge_base[U+1], the exclusive scan of the per-source edge counts: together with
+ * index (read from sorted_copies when ovl_index_build produced it, else gathered), and edge_base[U+1], the exclusive scan of the per-source edge counts: together with
  * bucket_lo / self_rank they give the first edge row of ANY pair in O(1), so no per-pair offset array
  * is ever built (ovl_overlap_dp_edges_join).
  * ovl_join_fill then writes pairs [p_begin, p_begin+p_count), ordered by (a, b) ascending.
@@ -123,8 +127,9 @@ int ovl_join_count(ovl_ctx *ctx, const uint64_t *suffix_key, const uint64_t *pre
                    const int32_t *len, int32_t k, int64_t U, const uint64_t *sorted_key,
                    const uint32_t *sorted_uid, const int64_t *n_indexed, const int32_t *table,
                    int32_t table_bits, int32_t key_bits, const int32_t *pos_of, const int32_t *copies,
-                   int64_t *cum, int32_t *bucket_lo, int32_t *self_rank, int64_t *pair_off,
-                   int64_t *edge_base, void *workspace, size_t workspace_bytes, void *stream);
+                   const int32_t *sorted_copies, int64_t *cum, int32_t *bucket_lo, int32_t *self_rank,
+                   int64_t *pair_off, int64_t *edge_base, void *workspace, size_t workspace_bytes,
+                   void *stream);
 /* The scalars the host needs before it can size anything, in ONE block of ovl_totals_len() int64
  * words written by one small kernel (totals may be page-locked host memory: the host then needs a
  * stream/event wait and no copy): [0] pairs, [1] edge rows, [2] *bad_count, [3],[4] this rank's
@@ -165,7 +170,7 @@ int ovl_all_pairs_fill(ovl_ctx *ctx, int64_t U, int64_t a_begin, int64_t p_begin
  * list and calls ovl_join_fill / ovl_overlap_dp_edges[_join] on the arrays inside the arena. */
 typedef struct ovl_cand_layout {
     size_t packed, len, bad, n_indexed, prefix_key, suffix_key, sorted_key, sorted_uid, table, pos_of,
-           bucket_lo, self_rank, pair_off, edge_base, cum, scratch, scratch_bytes, total_bytes;
+           bucket_lo, self_rank, pair_off, edge_base, cum, sorted_copies, scratch, scratch_bytes, total_bytes;
     int32_t row_words, key_bits, table_bits, has_copies;
 } ovl_cand_layout;
 int ovl_candidates_layout(int64_t U, int32_t max_len, int32_t k, int32_t n_segments, int32_t has_copies,
@@ -275,6 +280,21 @@ size_t ovl_local_align_workspace_bytes(int32_t n, int32_t m);
 int ovl_local_align(ovl_ctx *ctx, const int32_t *query, int32_t n, const int32_t *reference, int32_t m,
                     int64_t match, int64_t mismatch, int64_t indel, void *workspace,
                     size_t workspace_bytes, int32_t *result, uint8_t *ops, void *stream);
+
+/* K8 batch: many queries against windows of ONE reference in a single launch, one CTA per query
+ * (performanceMeasures.py:219-221 calls align_read_or_contig_to_reference once per contig, always with
+ * the same genome).  Per query x (all arrays on the device): symbols queries[q_off[x] .. q_off[x+1]),
+ * at most OVL_LOCAL_BATCH_MAX_QUERY of them (max_query_len = the longest); reference window
+ * [ref_start[x], ref_start[x] + ref_len[x]); tb_off[x] = byte offset of its traceback area inside tb,
+ * (n + 1) * (n + m + 2) bytes; ops_off[x] = byte offset of its op list inside ops, n + m + 1 bytes;
+ * results + 8 * x receives the same five words as ovl_local_align.  Results equal one
+ * ovl_local_align call per query. */
+#define OVL_LOCAL_BATCH_MAX_QUERY 1024
+int ovl_local_align_batch(ovl_ctx *ctx, const int32_t *queries, const int64_t *q_off, int32_t n_queries,
+                          int32_t max_query_len, const int32_t *reference, const int32_t *ref_start,
+                          const int32_t *ref_len, int64_t match, int64_t mismatch, int64_t indel,
+                          uint8_t *tb, const int64_t *tb_off, int32_t *results, uint8_t *ops,
+                          const int64_t *ops_off, void *stream);
 
 /* Order-sensitive fingerprint of an edge list: adds, into *accum (device u64, zeroed by the caller),
  * the sum over rows of mix(first_row + i, row i) mod 2^64.  Shards hashed with their global row

@@ -675,3 +675,59 @@ def test_one_call_job_finite_indel_and_all_a_genome(eng):
         b, o = orc.concat_reads(reads)
         got = eng.overlap_edges(b, o, np.asarray(counts, np.int32), k)
         assert np.array_equal(got, want)
+
+
+def test_local_alignment_batch_golden_and_oracle(golden_local):
+    """K8 batch (one CTA per query, one launch): every golden case through the batch entry points, and a contig set
+    against the 5,386-base genome the way performanceMeasures.py:219-221 uses it -- identical to per-call results."""
+    al = load_pkg("aligners")
+    groups = {}
+    for c in golden_local["local"]:
+        groups.setdefault((c["reference"], c["match"], c["mismatch"], c["indel"]), []).append(c)
+    n_batched = 0
+    for (ref, ma, mi, ind), cases in groups.items():
+        got = al.local_alignment_batch([c["query"] for c in cases], ref, ma, mi, ind)
+        for c, g in zip(cases, got):
+            assert list(g) == c["out"], (c["query"], ref, ma, mi, ind)
+            assert all(type(x) is int for x in g[3:])
+        n_batched += len(cases)
+    assert n_batched == len(golden_local["local"])
+    wgroups = {}
+    for c in golden_local["wrapped"]:
+        wgroups.setdefault((c["genome"], c["read_length"]), []).append(c)
+    for (genome, rl), cases in wgroups.items():
+        got = al.align_reads_or_contigs_to_reference([c["seq"] for c in cases], genome, rl)
+        for c, g in zip(cases, got):
+            assert list(g) == c["out"]
+    # contigs vs genome: lengths 1..1024 in the batch kernel, one longer contig through the per-call path, an empty one
+    synth = load_pkg("synth")
+    genome = synth.phix_like_genome().tobytes().decode()
+    rng = random.Random(9)
+    contigs = [""]
+    for L in [1, 5, 31, 32, 33, 60, 99, 100, 101, 150, 257, 511, 700, 1023, 1024, 1500] + [rng.randint(20, 400) for _ in range(40)]:
+        st = rng.randrange(len(genome) - L)
+        c = "".join(ch if rng.random() > 0.03 else rng.choice("ACGT") for ch in genome[st:st + L])
+        if L > 40:
+            c = c[:L // 2] + c[L // 2 + 2:]                                  # a deletion
+        contigs.append(c)
+    contigs.append(genome[-80:])                                             # at the genome's end
+    contigs.append(contigs[5])                                               # a repeated contig
+    read_length = 100
+    got = al.align_reads_or_contigs_to_reference(contigs, genome, read_length)
+    for c, g in zip(contigs, got):
+        n = len(c)
+        if n < read_length:                                                  # aligners.py:191-199
+            w = orc.local_alignment(c, genome[-n:]) if n else orc.local_alignment(c, genome[len(genome):])
+            want = (w[0], w[1], w[2], w[3], len(genome) - n + w[4], len(genome) - n + w[5])
+        else:
+            want = orc.local_alignment(c, genome)
+        assert tuple(g) == tuple(want), n
+        assert tuple(al.align_read_or_contig_to_reference(c, genome, read_length)) == tuple(want)
+    # the prefetch cache serves the reference's own per-contig loop
+    assert al.prefetch_alignments(contigs, genome, read_length) == len(set(contigs))
+    eng = load_pkg("engine").get_engine()
+    before = eng.launches
+    for c, g in zip(contigs, got):
+        assert tuple(al.align_read_or_contig_to_reference(c, genome, read_length)) == tuple(g)
+    assert eng.launches == before                                            # no kernel ran
+    al._PREFETCHED.clear()
