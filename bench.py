@@ -604,17 +604,24 @@ def dropin_wall(env, wl, reps=3):
             "nodes": G.number_of_nodes(), "edges": G.number_of_edges()}
 
 
-def sweep_sets(iterations, seed0=1000):
-    """The experiments.py:49-53 grid (N x l x p), `iterations` read sets per point, on the PhiX-like genome."""
+def sweep_sets(iterations, seed0=1000, eng=None):
+    """The experiments.py:49-53 grid (N x l x p), `iterations` read sets per point, on the PhiX-like genome.
+    With an engine the reads come from the DEVICE simulator (ovl_simulate_reads; same bytes as its NumPy mirror)."""
     synth = importlib.import_module(PKG + ".synth")
     g = synth.phix_like_genome()
+    g_dev = eng._to_device(g, eng.torch_uint8()) if eng is not None else None
     sets, meta = [], []
     i = 0
     for it in range(iterations):
         for n in (100, 316, 1000, 3162, 10000):
             for l in (50, 100, 150):
                 for p in (0.001, 0.01, 0.1):
-                    b, o = synth.simulate_reads(g, n, l, p, seed=seed0 + i)
+                    if eng is not None:
+                        a_dev, o_dev = eng.simulate_reads(g_dev, n, l, p, seed0 + i)
+                        o = o_dev.cpu().numpy()
+                        b = a_dev[:int(o[-1])].cpu().numpy()
+                    else:
+                        b, o = synth.simulate_reads_counter(g, n, l, p, seed0 + i)
                     i += 1
                     sets.append(synth.to_strings(b, o))
                     meta.append((n, l, p, it))
@@ -638,11 +645,15 @@ def sweep_extra(env, iterations=10, cpu_seconds=20.0):
     import multiprocessing as mp
     og = importlib.import_module(PKG + ".overlapGraphs")
     torch = env.torch
-    sets, meta = sweep_sets(iterations)
+    t0 = time.perf_counter()
+    sets, meta = sweep_sets(iterations, eng=env.eng)
+    t_sim = time.perf_counter() - t0
     n_reads = sum(len(s) for s in sets)
     out = {"grid": "N in {100,316,1000,3162,10000} x l in {50,100,150} x p in {0.001,0.01,0.1} x k in {5,10,15} "
                    f"x {iterations} iterations (experiments.py:49-53), PhiX-like genome",
-           "read_sets_per_k": len(sets), "reads_per_k": n_reads, "per_k": {}}
+           "read_sets_per_k": len(sets), "reads_per_k": n_reads,
+           "read_simulation_s": t_sim, "read_simulation": "device (ovl_simulate_reads) + D2H + Python strings, untimed part of the job",
+           "per_k": {}}
     one_iter = [s for s, m in zip(sets, meta) if m[3] == 0]
     cores = os.cpu_count() or 1
     total_gpu_s = total_graph_s = 0.0

@@ -128,6 +128,8 @@ __device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xffffu
 __device__ __forceinline__ constexpr bool dp_form2(int c) {
     return OVL_DP_F2_NUM > 0 && (c * OVL_DP_F2_NUM) % OVL_DP_F2_DEN < OVL_DP_F2_NUM;
 }
+// (There is no cheaper 2-input packed min to build a third form from: __vminu2 compiles to
+// VIMNMX3.U16x2 with a repeated operand on sm_100a -- probe kind 17.)
 
 // ---- TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

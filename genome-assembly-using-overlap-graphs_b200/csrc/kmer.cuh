@@ -37,7 +37,7 @@ __device__ __forceinline__ uint32_t codes4(uint32_t c, uint32_t& bad) {
 }
 
 template <bool KEYS>
-__global__ void __launch_bounds__(kPackThreads) pack_reads_kernel(const uint8_t* __restrict__ ascii,
+__global__ void __launch_bounds__(kPackThreads, 8) pack_reads_kernel(const uint8_t* __restrict__ ascii,
                                                                   const int64_t* __restrict__ offsets,
                                                                   int64_t U, int row_words,
                                                                   uint32_t* __restrict__ packed,
@@ -52,11 +52,17 @@ __global__ void __launch_bounds__(kPackThreads) pack_reads_kernel(const uint8_t*
     const int64_t n_slots = U * quads;
     const int64_t slot = (int64_t)blockIdx.x * kPackThreads + threadIdx.x;
     const bool active = slot < n_slots;
+    const int64_t total_bytes = offsets[U];          // issued first: only the tail check needs it
     int64_t u = 0, o0 = 0;
     int q = 0, len = 0;
     if (active) {
-        u = slot / quads;
-        q = (int)(slot - u * quads);
+        // (u, q) = divmod(slot, quads): one 64-bit division per CTA (uniform), a 32-bit one per thread
+        const int64_t slot0 = (int64_t)blockIdx.x * kPackThreads;
+        const int64_t u0 = slot0 / quads;
+        const unsigned local = (unsigned)(slot0 - u0 * quads) + threadIdx.x;
+        const unsigned du = local / (unsigned)quads;
+        u = u0 + du;
+        q = (int)(local - du * (unsigned)quads);
         o0 = offsets[u];
         len = (int)(offsets[u + 1] - o0);
         if (q == 0) len_out[u] = len;
@@ -68,7 +74,6 @@ __global__ void __launch_bounds__(kPackThreads) pack_reads_kernel(const uint8_t*
     __syncthreads();
     const int64_t span_base = s_span[0];
     const int n_pieces = (int)((s_span[1] - span_base + 15) >> 4);
-    const int64_t total_bytes = offsets[U];
     uint32_t bad = 0;
     for (int p = threadIdx.x; p < n_pieces + 3; p += kPackThreads) {
         uint32_t w = 0;

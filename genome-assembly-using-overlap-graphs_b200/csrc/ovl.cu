@@ -16,6 +16,7 @@
 #include "probe.cuh"
 #include "align.cuh"
 #include "check.cuh"
+#include "simulate.cuh"
 
 using namespace ovl;
 
@@ -961,6 +962,39 @@ int ovl_local_align_batch(ovl_ctx* ctx, const int32_t* queries, const int64_t* q
     return OVL_OK;
 }
 
+// ---------------------------------------------------------------- read simulator
+size_t ovl_simulate_workspace_bytes(int64_t n_reads) {
+    if (n_reads < 1) n_reads = 1;
+    return align256((size_t)n_reads * 8) * 2 + align256(scan_workspace_bytes(n_reads, sizeof(int64_t))) + 256;
+}
+
+int ovl_simulate_reads(ovl_ctx* ctx, const uint8_t* genome, int64_t genome_len, int64_t n_reads, int32_t read_len, uint32_t error_thr,
+                       uint64_t seed, int64_t* offsets, uint8_t* ascii, void* workspace, size_t workspace_bytes, void* stream) {
+    ON_CTX_DEVICE(ctx);
+    if (!ctx || !genome || !offsets || !ascii || !workspace) return fail(OVL_E_ARG, "ovl_simulate_reads: null argument");
+    if (genome_len < 1 || genome_len >= (1ll << 32) || read_len < 1 || n_reads < 0)
+        return fail(OVL_E_ARG, "ovl_simulate_reads: need 1 <= genome_len < 2^32, read_len >= 1, n_reads >= 0");
+    if (workspace_bytes < ovl_simulate_workspace_bytes(n_reads)) return fail(OVL_E_ARG, "ovl_simulate_reads: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    int64_t* start = (int64_t*)ws;                 ws += align256((size_t)std::max<int64_t>(n_reads, 1) * 8);
+    int64_t* len = (int64_t*)ws;                   ws += align256((size_t)std::max<int64_t>(n_reads, 1) * 8);
+    void* sums = ws;
+    int nl = 0;
+    if (n_reads > 0) {
+        sim_starts_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(n_reads, genome_len, read_len, seed, start, len);
+        LAUNCH_CHECK("sim_starts_kernel");
+    }
+    CUDA_TRY((exclusive_scan<LoadArray<int64_t>, int64_t>(LoadArray<int64_t>{len}, offsets, n_reads, sums, st, &nl)));
+    ctx->launches += nl;
+    if (n_reads > 0) {
+        int64_t chunks = (read_len + 15) / 16;
+        sim_bases_kernel<<<grid_for(n_reads * chunks, 256), 256, 0, st>>>(genome, n_reads, read_len, error_thr, seed, start, offsets, ascii);
+        LAUNCH_CHECK("sim_bases_kernel");
+    }
+    return OVL_OK;
+}
+
 // ---------------------------------------------------------------- edge-list fingerprint
 int ovl_edge_list_hash(ovl_ctx* ctx, const int32_t* edges, int64_t E, int64_t first_row, uint64_t* accum, void* stream) {
     ON_CTX_DEVICE(ctx);
@@ -1023,6 +1057,9 @@ int ovl_int_peak_probe(ovl_ctx* ctx, int32_t kind, int32_t iters, double* h_gops
         case 14: return run_probe<14>(ctx, iters, h_gops, h_ms);
         case 15: return run_probe<15>(ctx, iters, h_gops, h_ms);
         case 16: return run_probe<16>(ctx, iters, h_gops, h_ms);
+        case 17: return run_probe<17>(ctx, iters, h_gops, h_ms);
+        case 18: return run_probe<18>(ctx, iters, h_gops, h_ms);
+        case 20: return run_probe<20>(ctx, iters, h_gops, h_ms);
         default: return fail(OVL_E_ARG, "ovl_int_peak_probe: unknown kind %d", kind);
     }
 }

@@ -87,6 +87,13 @@ __global__ void __launch_bounds__(kProbeThreads) int_probe_kernel(uint32_t* out,
                     uint32_t a1 = dc + z[c];
                     uint32_t t1 = __viaddmin_u16x2(w[c], b0, a1);
                     v[c] = __viaddmin_u16x2(v[c], a0, t1);
+                } else if (KIND == 17) {    // 2-input packed min (__vminu2): SASS is VIMNMX3.U16x2 with a repeated operand
+                    v[c] = __vminu2(v[c], w[c]);
+                    w[c] += 0;
+                } else if (KIND == 18) {    // VIMNMX3.U16x2 alone (3-input packed min)
+                    v[c] = __vimin3_u16x2(v[c], w[c], x[c]);
+                } else if (KIND == 20) {    // VIADDMNMX.U16x2 alone (the kernel's fused add+min)
+                    v[c] = __viaddmin_u16x2(v[c], b0, w[c]);
                 } else if (KIND == 5) {     // PRMT
                     asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(v[c]) : "r"(w[c]), "r"(b0));
                 } else {                    // LOP3

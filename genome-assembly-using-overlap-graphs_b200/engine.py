@@ -106,6 +106,10 @@ class OverlapEngine:
         """Kernels launched through this engine's context so far (counted inside libovl_b200.so)."""
         return int(nat.lib.ovl_ctx_launch_count(self._ctx)) if getattr(self, "_ctx", None) else 0
 
+    @staticmethod
+    def torch_uint8():
+        return torch.uint8
+
     def close(self) -> None:
         if getattr(self, "_ctx", None):
             nat.lib.ovl_ctx_destroy(self._ctx)
@@ -772,6 +776,23 @@ class OverlapEngine:
         out = self._empty(kept * 4, torch.int32)
         nat.check(nat.lib.ovl_filter_fill(self._ctx, _ptr(edges), _ptr(keep_off), E, int(min_weight), _ptr(out), st))
         return out[:kept * 4].view(kept, 4)
+
+    # ------------------------------------------------------------------ read simulator
+    def simulate_reads(self, genome, n_reads: int, read_len: int, error_prob: float, seed: int):
+        """Seeded read simulation ON THE DEVICE (generateErrorFreeReads.py:22-52 + generateErrorProneReads.py:4-45
+        as a counter-based stream): returns (ascii_dev with 64 bytes of slack, offsets_dev int64[n_reads+1]) --
+        directly what build_candidates() takes -- bit-identical to synth.simulate_reads_counter()."""
+        from .synth import error_threshold
+        g = self._to_device(genome, torch.uint8) if not (isinstance(genome, torch.Tensor) and genome.is_cuda) else genome
+        G = int(g.shape[0])
+        ascii_dev = torch.empty(n_reads * read_len + 64, dtype=torch.uint8, device=self.device)
+        offsets = torch.empty(n_reads + 1, dtype=torch.int64, device=self.device)
+        ws_bytes = int(nat.lib.ovl_simulate_workspace_bytes(n_reads))
+        ws = self._empty(ws_bytes, torch.uint8)
+        nat.check(nat.lib.ovl_simulate_reads(self._ctx, _ptr(g), G, n_reads, read_len, error_threshold(error_prob),
+                                             int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(offsets), _ptr(ascii_dev), _ptr(ws),
+                                             ws_bytes, self._stream()))
+        return ascii_dev, offsets
 
     # ------------------------------------------------------------------ edge-list fingerprint
     def edge_hash(self, edges: torch.Tensor, first_row: int = 0, accum: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -72,6 +72,50 @@ def simulate_reads(genome: np.ndarray, n_reads: int, read_len: int, error_prob: 
     return bases, offsets
 
 
+_M64 = (1 << 64) - 1
+
+
+def _sim_hash(seed: int, stream: int, index: np.ndarray) -> np.ndarray:
+    """splitmix64 finaliser over (seed, stream, index) -- the mirror of csrc/simulate.cuh:sim_hash."""
+    with np.errstate(over="ignore"):
+        z = (np.uint64((seed + 0x9E3779B97F4A7C15 * (stream + 1)) & _M64)
+             + np.uint64(0xD1B54A32D192ED03) * index.astype(np.uint64))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def error_threshold(error_prob: float) -> int:
+    """P(error) as the 32-bit integer threshold both the device kernel and the NumPy mirror compare with."""
+    return max(0, min(0xFFFFFFFF, int(error_prob * 4294967296.0)))
+
+
+def simulate_reads_counter(genome: np.ndarray, n_reads: int, read_len: int, error_prob: float,
+                           seed: int) -> Tuple[np.ndarray, np.ndarray]:
+    """The same read model as simulate_reads() on a counter-based stream: every start and every base is an
+    independent function of (seed, read, position), so the device kernel ovl_simulate_reads produces these
+    exact bytes (OverlapEngine.simulate_reads).  Returns (bases uint8[sum len], offsets int64[n_reads+1])."""
+    G = int(genome.shape[0])
+    idx = np.arange(n_reads, dtype=np.uint64)
+    h = _sim_hash(seed, 0, idx)
+    starts = (((h >> np.uint64(32)) * np.uint64(G)) >> np.uint64(32)).astype(np.int64)
+    lens = np.minimum(read_len, G - starts).astype(np.int64)
+    offsets = np.zeros(n_reads + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    total = int(offsets[-1])
+    read_id = np.repeat(np.arange(n_reads, dtype=np.int64), lens)
+    within = np.arange(total, dtype=np.int64) - offsets[read_id]
+    bases = genome[starts[read_id] + within].copy()
+    hb = _sim_hash(seed, 1, (read_id * read_len + within).astype(np.uint64))
+    hit = (hb >> np.uint64(32)) < np.uint64(error_threshold(error_prob))
+    if hit.any():
+        code = np.zeros(256, dtype=np.uint32)
+        code[_ALPHABET] = np.arange(4, dtype=np.uint32)
+        shift = 1 + (((hb[hit] & np.uint64(0xFFFFFFFF)) * np.uint64(3)) >> np.uint64(32)).astype(np.uint32)
+        bases[hit] = _ALPHABET[(code[bases[hit]] + shift) & 3]
+    return bases, offsets
+
+
 def to_strings(bases: np.ndarray, offsets: np.ndarray) -> List[str]:
     buf = bases.tobytes().decode("ascii")
     off = offsets.tolist()

@@ -296,6 +296,18 @@ int ovl_local_align_batch(ovl_ctx *ctx, const int32_t *queries, const int64_t *q
                           uint8_t *tb, const int64_t *tb_off, int32_t *results, uint8_t *ops,
                           const int64_t *ops_off, void *stream);
 
+/* Seeded read simulator (the input generators generateErrorFreeReads.py:22-52 and
+ * generateErrorProneReads.py:4-45 as one counter-based stream): n_reads reads of read_len bases with
+ * uniform starts on the LINEAR genome (A/C/G/T ASCII, genome_len < 2^32; reads are truncated at its
+ * end), every base replaced with probability error_thr / 2^32 by one of the three other letters.
+ * Writes offsets[n_reads + 1] and the reads back to back into ascii (capacity n_reads * read_len + 64,
+ * 16-byte aligned: directly the input of ovl_pack_reads / ovl_candidates_build).  Same bytes as
+ * synth.simulate_reads_counter() for the same seed. */
+size_t ovl_simulate_workspace_bytes(int64_t n_reads);
+int ovl_simulate_reads(ovl_ctx *ctx, const uint8_t *genome, int64_t genome_len, int64_t n_reads,
+                       int32_t read_len, uint32_t error_thr, uint64_t seed, int64_t *offsets,
+                       uint8_t *ascii, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Order-sensitive fingerprint of an edge list: adds, into *accum (device u64, zeroed by the caller),
  * the sum over rows of mix(first_row + i, row i) mod 2^64.  Shards hashed with their global row
  * offset add up to the fingerprint of the whole list; any misplaced or reordered row changes it.
@@ -308,7 +320,9 @@ int ovl_edge_list_hash(ovl_ctx *ctx, const int32_t *edges, int64_t E, int64_t fi
  * 3 VIADDMNMX.S16x2, 4 the DP inner-loop mix (PRMT, IMAD, 2x VIADDMNMX.S16x2), 5 PRMT, 6 LOP3,
  * 7 LOP3 + IMAD on independent chains (do the ALU and FMA pipes issue side by side?),
  * 8 VIMNMX3 + IMAD with all-distinct register operands, 9 one form-1 DP column per chain,
- * 10 one form-2 DP column per chain, 11 a 2 ALU + 2 IMAD column.
+ * 10 one form-2 DP column per chain, 11 a 2 ALU + 2 IMAD column, 12-16 pipe-pairing experiments,
+ * 17 __vminu2 (2-input packed min: compiles to VIMNMX3.U16x2 with a repeated operand), 18 VIMNMX3.U16x2,
+ * 20 VIADDMNMX.U16x2.
  * Synchronises the device.  h_gops receives giga lane-instructions per second. */
 int ovl_int_peak_probe(ovl_ctx *ctx, int32_t kind, int32_t iters, double *h_gops, double *h_ms);
 

@@ -731,3 +731,33 @@ def test_local_alignment_batch_golden_and_oracle(golden_local):
         assert tuple(al.align_read_or_contig_to_reference(c, genome, read_length)) == tuple(g)
     assert eng.launches == before                                            # no kernel ran
     al._PREFETCHED.clear()
+
+
+@pytest.mark.parametrize("n,l,p,G", [(1, 1, 0.0, 1), (500, 50, 0.001, 5386), (3162, 150, 0.1, 5386), (20000, 100, 0.01, 123457),
+                                     (40, 1000, 0.02, 900)])
+def test_device_read_simulator_equals_numpy_mirror(eng, n, l, p, G):
+    """ovl_simulate_reads (generateErrorFreeReads.py:22-52 + generateErrorProneReads.py:4-45 on a counter-based stream)
+    produces the bytes of synth.simulate_reads_counter, and they are what the builder consumes."""
+    synth = load_pkg("synth")
+    genome = synth.random_genome(G, 5)
+    for seed in (0, 12345, 2 ** 63 + 11):
+        want_b, want_o = synth.simulate_reads_counter(genome, n, l, p, seed)
+        ascii_dev, off_dev = eng.simulate_reads(genome, n, l, p, seed)
+        got_o = off_dev.cpu().numpy()
+        assert np.array_equal(got_o, want_o)
+        assert np.array_equal(ascii_dev[:int(got_o[-1])].cpu().numpy(), want_b)
+    lens = want_o[1:] - want_o[:-1]
+    assert lens.min() >= 1 and lens.max() <= l                       # end-truncated, never empty (:42)
+    if n >= 500:
+        clean_b, _ = synth.simulate_reads_counter(genome, n, l, 0.0, 2 ** 63 + 11)
+        rate = float((clean_b != want_b).mean())
+        assert abs(rate - p) < 0.25 * p + 0.002                      # substitution rate ~ p, always to another base
+    # device reads straight into the one-call job == the host path on the same reads
+    if n >= 500 and l <= 150:
+        reads = synth.to_strings(want_b, want_o)
+        ub, uo, counts, _ = synth.dedup(want_b, want_o)
+        if counts.max() == 1:                                        # the device job has no de-duplication of its own
+            cand = eng.build_candidates(ascii_dev, off_dev, n, l, 5)
+            pa, pb = eng.fill_pairs(cand)
+            wa, wb = orc.candidate_pairs(reads, 5)
+            assert np.array_equal(pa.cpu().numpy(), wa) and np.array_equal(pb.cpu().numpy(), wb)
