@@ -112,6 +112,8 @@ _SIGS = {
                                              _vp, _vp]),
     "ovl_simulate_workspace_bytes": (_sz, [_i64]),
     "ovl_simulate_reads": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, ctypes.c_uint32, ctypes.c_uint64, _vp, _vp, _vp, _sz, _vp]),
+    "ovl_trim_workspace_bytes": (_sz, [_i64]),
+    "ovl_trim_sinks": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _sz, ctypes.POINTER(_i32), _vp]),
     "ovl_edge_list_hash": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "ovl_int_peak_probe": (ctypes.c_int, [_vp, _i32, _i32, ctypes.POINTER(ctypes.c_double),
                                           ctypes.POINTER(ctypes.c_double)]),

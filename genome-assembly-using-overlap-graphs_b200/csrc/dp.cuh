@@ -56,7 +56,18 @@ struct DpParams {
     // the same constants pre-packed on the host (both 16-bit halves in packed mode); only read with
     // OVL_DP_PREPACK=1, which was measured slower than packing them in the kernel prologue
     uint32_t gu2, gl2, maxs2, beta2;
+    int32_t cmax;       // upper bound of every cell value (cost space)
+    int32_t gaps_never_win;   // both gap costs exceed cmax: no gap candidate can ever be the minimum
 };
+
+// When no gap can ever win (the reference's default indel = -2^31, overlapGraphs.py:53) the two gap costs
+// are interchangeable with ANY constant above cmax.  The IMMG instantiation uses this fixed one, so that
+// the gap adds carry an IMMEDIATE instead of a third register source: VIADDMNMX.U16x2 R, R, imm, R issues
+// at twice the rate of the three-register form on this GPU (probe kinds 20 / 21).  Same recurrence,
+// same instruction count, same results.  Requires cmax < kGapNever (so that it still never wins) and
+// cmax + kGapNever <= 65535 (no carry between the halves): cmax <= 0x6fff.
+constexpr uint32_t kGapNever = 0x7000u;
+constexpr uint32_t kGapNever2 = kGapNever * 0x10001u;
 
 // optional fused edge expansion in the DP epilogue (all null: plain score/end output)
 struct DpEdgeOut {
@@ -161,7 +172,7 @@ __host__ __device__ inline int dp_lut_rows(int max_len) {
 // BITS = 8 (byte-coded reads, any alphabet; packed mode only): the diagonal cost comes from
 // XOR + min(.,1) + multiply-add (LOP3, VIMNMX.U16x2, IMAD) instead of the 4-entry PRMT table;
 // requires eqc == 0 (match >= mismatch).
-template <int G, int T, bool PK, int BITS = 2>
+template <int G, int T, bool PK, int BITS = 2, bool IMMG = false>
 __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : OVL_DP_MINB)) overlap_dp_kernel(
     const uint32_t* __restrict__ packed, int row_words, const int32_t* __restrict__ len,
     const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b, int64_t P, int lut_rows,
@@ -264,8 +275,8 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : OVL_DP_MINB)) overla
 #if OVL_DP_PREPACK
     const uint32_t gu2 = prm.gu2, gl2 = prm.gl2, maxs2 = prm.maxs2;
 #else
-    const uint32_t gu2 = PK ? pack2(prm.gu) : (uint32_t)prm.gu;
-    const uint32_t gl2 = PK ? pack2(prm.gl) : (uint32_t)prm.gl;
+    const uint32_t gu2 = IMMG ? kGapNever2 : PK ? pack2(prm.gu) : (uint32_t)prm.gu;
+    const uint32_t gl2 = IMMG ? kGapNever2 : PK ? pack2(prm.gl) : (uint32_t)prm.gl;
     const uint32_t maxs2 = PK ? (uint32_t)prm.maxs * 0x10001u : (uint32_t)prm.maxs;
 #endif
     const uint32_t one = prm.one;
@@ -308,11 +319,11 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : OVL_DP_MINB)) overla
                         asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a1) : "r"(ne), "r"((uint32_t)prm.nec), "r"(diag));
                     } else {
                         uint32_t dc = prmt(lu.x, lu.y, sel[c]);
-                        a1 = fma_add(dc, one, diag);
+                        a1 = IMMG ? dc + diag : fma_add(dc, one, diag);     // IMMG: two register sources either way
                     }
                     if (dp_form2(c)) {
-                        uint32_t a2 = fma_add(up[c], one, gu2);
-                        uint32_t a3 = fma_add(left, one, gl2);
+                        uint32_t a2 = IMMG ? up[c] + gu2 : fma_add(up[c], one, gu2);
+                        uint32_t a3 = IMMG ? left + gl2 : fma_add(left, one, gl2);
                         g = __vimin3_u16x2(a1, a2, a3);
                     } else {
                         uint32_t t1 = __viaddmin_u16x2(up[c], gu2, a1);

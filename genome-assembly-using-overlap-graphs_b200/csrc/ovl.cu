@@ -17,6 +17,7 @@
 #include "align.cuh"
 #include "check.cuh"
 #include "simulate.cuh"
+#include "trim.cuh"
 
 using namespace ovl;
 
@@ -537,8 +538,11 @@ bool dp_params(int64_t match, int64_t mismatch, int64_t indel, int64_t N, int64_
         if (mag >= (1ll << 30)) return false;
     }
     if (eqc >= (1ll << 30) || nec >= (1ll << 30)) return false;
+    const int64_t cmax_out = g <= 0 ? beta + std::max<int64_t>(maxs, 0) * N + std::max<int64_t>(-base, 0) * mn : 0;
+    const bool never_out = g <= 0 && (maxs - g) > cmax_out && (-g) > cmax_out;
     out->eqc = (int32_t)eqc; out->nec = (int32_t)nec; out->maxs = (int32_t)maxs; out->beta = (int32_t)beta;
     out->gu = (int32_t)gu; out->gl = (int32_t)gl; out->one = 1u;
+    out->cmax = (int32_t)std::min<int64_t>(cmax_out, INT32_MAX); out->gaps_never_win = never_out ? 1 : 0;
     if (packed) {
         out->gu2 = ((uint32_t)gu & 0xffffu) * 0x10001u;
         out->gl2 = ((uint32_t)gl & 0xffffu) * 0x10001u;
@@ -576,7 +580,7 @@ bool dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_t indel, in
     return false;
 }
 
-template <int G, int T, bool PK, int BITS = 2>
+template <int G, int T, bool PK, int BITS = 2, bool IMMG = false>
 int launch_dp(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int32_t* len, const int32_t* pair_a, const int32_t* pair_b,
               int64_t P, int32_t max_len, const DpParams& prm, int32_t* score, int32_t* end, const DpEdgeOut& eo, cudaStream_t st) {
     constexpr int PAIRS = PK ? 2 : 1;
@@ -589,16 +593,19 @@ int launch_dp(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int
                 + (size_t)GROUPS_PER_CTA * lut_rows * sizeof(uint2)                       // per-row score tables
                 + (kDpThreads / 32) * sizeof(uint64_t);                                   // one mbarrier per warp
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(overlap_dp_kernel<G, T, PK, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(overlap_dp_kernel<G, T, PK, BITS, IMMG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(OVL_E_CUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));
     }
-    overlap_dp_kernel<G, T, PK, BITS><<<(unsigned)grid, kDpThreads, smem, st>>>(packed, row_words, len, pair_a, pair_b, P, lut_rows, prm, score, end, eo);
+    overlap_dp_kernel<G, T, PK, BITS, IMMG><<<(unsigned)grid, kDpThreads, smem, st>>>(packed, row_words, len, pair_a, pair_b, P, lut_rows, prm, score, end, eo);
     LAUNCH_CHECK("overlap_dp_kernel");
     return OVL_OK;
 }
 
 #define DP_CASE(G_, T_, PK_) \
     if (plan.G == G_ && plan.T == T_) return launch_dp<G_, T_, PK_>(ctx, packed, row_words, len, pair_a, pair_b, P, max_len, plan.prm, score, end, eo, st);
+#define DP_CASE_IMM(G_, T_) \
+    if (plan.G == G_ && plan.T == T_) return launch_dp<G_, T_, true, 2, true>(ctx, packed, row_words, len, pair_a, pair_b, P, max_len, plan.prm, score, end, eo, st);
+#define DP_CASES_IMM_T(T_) DP_CASE_IMM(1, T_) DP_CASE_IMM(2, T_) DP_CASE_IMM(4, T_) DP_CASE_IMM(8, T_) DP_CASE_IMM(16, T_) DP_CASE_IMM(32, T_)
 #define DP_CASE8(G_, T_) \
     if (plan.G == G_ && plan.T == T_) return launch_dp<G_, T_, true, 8>(ctx, packed, row_words, len, pair_a, pair_b, P, max_len, plan.prm, score, end, eo, st);
 #define DP_CASES8_T(T_) DP_CASE8(1, T_) DP_CASE8(2, T_) DP_CASE8(4, T_) DP_CASE8(8, T_) DP_CASE8(16, T_) DP_CASE8(32, T_)
@@ -678,6 +685,12 @@ static int dp_dispatch(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, 
                     who, (long long)match, (long long)mismatch, (long long)indel, max_len, mode, group_lanes, cols_per_lane);
     cudaStream_t st = (cudaStream_t)stream;
     if (plan.mode == 1) {
+        // no gap can ever win (the default call site): the instantiation with immediate gap costs
+        static const bool imm_ok = !(getenv("OVL_DP_IMM_GAPS") && atoi(getenv("OVL_DP_IMM_GAPS")) == 0);
+        if (imm_ok && plan.prm.gaps_never_win && plan.prm.cmax <= (int32_t)kGapNever - 1 && plan.prm.cmax + (int64_t)kGapNever <= 65535) {
+            DP_CASES_IMM_T(19) DP_CASES_IMM_T(25) DP_CASES_IMM_T(32) DP_CASES_IMM_T(38)
+            DP_CASE_IMM(16, 76) DP_CASE_IMM(32, 76)
+        }
         DP_CASES_T(19, true) DP_CASES_T(25, true) DP_CASES_T(32, true) DP_CASES_T(38, true)
         DP_CASE(16, 76, true) DP_CASE(32, 76, true)
     } else {
@@ -995,6 +1008,49 @@ int ovl_simulate_reads(ovl_ctx* ctx, const uint8_t* genome, int64_t genome_len, 
     return OVL_OK;
 }
 
+// ---------------------------------------------------------------- cycle-removal pre-pass
+size_t ovl_trim_workspace_bytes(int64_t n_nodes) {
+    if (n_nodes < 1) n_nodes = 1;
+    return align256((size_t)n_nodes * 4) + 512;
+}
+
+int ovl_trim_sinks(ovl_ctx* ctx, const int32_t* src, const int32_t* dst, int64_t E, int64_t n_nodes, int32_t* state, void* workspace,
+                   size_t workspace_bytes, int32_t* h_rounds, void* stream) {
+    ON_CTX_DEVICE(ctx);
+    if (!ctx || !state || !workspace || (E > 0 && (!src || !dst))) return fail(OVL_E_ARG, "ovl_trim_sinks: null argument");
+    if (n_nodes < 0 || E < 0) return fail(OVL_E_ARG, "ovl_trim_sinks: negative size");
+    if (workspace_bytes < ovl_trim_workspace_bytes(n_nodes)) return fail(OVL_E_ARG, "ovl_trim_sinks: workspace too small");
+    if (h_rounds) *h_rounds = 0;
+    if (n_nodes == 0) return OVL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    int32_t* last_change = (int32_t*)ws;
+    int32_t* outdeg = (int32_t*)(ws + 256);
+    CUDA_TRY(cudaMemsetAsync(ws, 0, 256 + (size_t)n_nodes * 4, st));
+    if (E > 0) {
+        trim_outdeg_kernel<<<grid_for(E, 256), 256, 0, st>>>(src, E, outdeg);
+        LAUNCH_CHECK("trim_outdeg_kernel");
+    }
+    trim_init_kernel<<<grid_for(n_nodes, 256), 256, 0, st>>>(n_nodes, outdeg, state);
+    LAUNCH_CHECK("trim_init_kernel");
+    // peel in batches of rounds; stop when a whole batch passed without any node dying
+    int32_t round = 1;
+    const int kBatch = 32;
+    while (E > 0) {
+        for (int i = 0; i < kBatch; ++i, ++round) {
+            trim_round_kernel<<<grid_for(E, 256), 256, 0, st>>>(src, dst, E, outdeg, state, round, last_change);
+            LAUNCH_CHECK("trim_round_kernel");
+        }
+        int32_t last = 0;
+        CUDA_TRY(cudaMemcpyAsync(&last, last_change, sizeof(last), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (last < round) break;                        // nobody died in the batch's last round: the peeling has stopped
+        if (round > n_nodes + kBatch) return fail(OVL_E_CUDA, "ovl_trim_sinks: peeling did not converge");
+    }
+    if (h_rounds) *h_rounds = round - 1;
+    return OVL_OK;
+}
+
 // ---------------------------------------------------------------- edge-list fingerprint
 int ovl_edge_list_hash(ovl_ctx* ctx, const int32_t* edges, int64_t E, int64_t first_row, uint64_t* accum, void* stream) {
     ON_CTX_DEVICE(ctx);
@@ -1060,6 +1116,11 @@ int ovl_int_peak_probe(ovl_ctx* ctx, int32_t kind, int32_t iters, double* h_gops
         case 17: return run_probe<17>(ctx, iters, h_gops, h_ms);
         case 18: return run_probe<18>(ctx, iters, h_gops, h_ms);
         case 20: return run_probe<20>(ctx, iters, h_gops, h_ms);
+        case 21: return run_probe<21>(ctx, iters, h_gops, h_ms);
+        case 22: return run_probe<22>(ctx, iters, h_gops, h_ms);
+        case 23: return run_probe<23>(ctx, iters, h_gops, h_ms);
+        case 24: return run_probe<24>(ctx, iters, h_gops, h_ms);
+        case 25: return run_probe<25>(ctx, iters, h_gops, h_ms);
         default: return fail(OVL_E_ARG, "ovl_int_peak_probe: unknown kind %d", kind);
     }
 }

@@ -94,6 +94,20 @@ __global__ void __launch_bounds__(kProbeThreads) int_probe_kernel(uint32_t* out,
                     v[c] = __vimin3_u16x2(v[c], w[c], x[c]);
                 } else if (KIND == 20) {    // VIADDMNMX.U16x2 alone (the kernel's fused add+min)
                     v[c] = __viaddmin_u16x2(v[c], b0, w[c]);
+                } else if (KIND == 21) {    // VIADDMNMX.U16x2 with an IMMEDIATE addend: two register sources instead of three
+                    v[c] = __viaddmin_u16x2(v[c], 0x70007000u, w[c]);
+                } else if (KIND == 22) {    // form-1 column with immediate gap costs: PRMT, IMAD.IADD, 2x VIADDMNMX(imm)
+                    uint32_t dc;
+                    asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(dc) : "r"(x[c]), "r"(y[c]), "r"(v[c]));
+                    uint32_t a1 = dc + z[c];
+                    uint32_t t1 = __viaddmin_u16x2(w[c], 0x70007000u, a1);
+                    v[c] = __viaddmin_u16x2(v[c], 0x70007000u, t1);
+                } else if (KIND == 23) {    // IMAD with an immediate multiplier (two register sources)
+                    asm volatile("mad.lo.u32 %0, %0, 3, %1;" : "+r"(v[c]) : "r"(w[c]));
+                } else if (KIND == 24) {    // PRMT with a repeated source (two distinct registers)
+                    asm volatile("prmt.b32 %0, %0, %0, %1;" : "+r"(v[c]) : "r"(w[c]));
+                } else if (KIND == 25) {    // LOP3 with an immediate (two register sources)
+                    asm volatile("lop3.b32 %0, %0, %1, 0x0f0f0f0f, 0x96;" : "+r"(v[c]) : "r"(w[c]));
                 } else if (KIND == 5) {     // PRMT
                     asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(v[c]) : "r"(w[c]), "r"(b0));
                 } else {                    // LOP3
@@ -110,7 +124,7 @@ __global__ void __launch_bounds__(kProbeThreads) int_probe_kernel(uint32_t* out,
 
 inline int probe_ops_per_iter(int kind) {
     if (kind == 10) return 5;
-    if (kind == 4 || kind == 9 || kind == 11 || kind == 16) return 4;
+    if (kind == 4 || kind == 9 || kind == 11 || kind == 16 || kind == 22) return 4;
     if (kind == 15) return 3;
     return (kind == 7 || kind == 8 || kind == 12 || kind == 13 || kind == 14) ? 2 : 1;
 }

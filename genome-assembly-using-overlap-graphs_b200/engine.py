@@ -777,6 +777,21 @@ class OverlapEngine:
         nat.check(nat.lib.ovl_filter_fill(self._ctx, _ptr(edges), _ptr(keep_off), E, int(min_weight), _ptr(out), st))
         return out[:kept * 4].view(kept, 4)
 
+    # ------------------------------------------------------------------ cycle-removal pre-pass
+    def trim_sinks(self, src, dst, n_nodes: int):
+        """Peel sinks off a directed graph (edge list src[e] -> dst[e]) until none is left (csrc/trim.cuh).
+        Returns (keep bool[n_nodes], rounds): keep[v] is False for the nodes that cannot reach a cycle."""
+        E = int(len(src))
+        d_src = self._to_device(np.ascontiguousarray(src, dtype=np.int32), torch.int32) if E else None
+        d_dst = self._to_device(np.ascontiguousarray(dst, dtype=np.int32), torch.int32) if E else None
+        state = torch.zeros(max(n_nodes, 1), dtype=torch.int32, device=self.device)
+        ws_bytes = int(nat.lib.ovl_trim_workspace_bytes(n_nodes))
+        ws = self._empty(ws_bytes, torch.uint8)
+        rounds = ctypes.c_int32(0)
+        nat.check(nat.lib.ovl_trim_sinks(self._ctx, _ptr(d_src), _ptr(d_dst), E, int(n_nodes), _ptr(state), _ptr(ws), ws_bytes,
+                                         ctypes.byref(rounds), self._stream()))
+        return (state[:n_nodes] == 0).cpu().numpy(), int(rounds.value)
+
     # ------------------------------------------------------------------ read simulator
     def simulate_reads(self, genome, n_reads: int, read_len: int, error_prob: float, seed: int):
         """Seeded read simulation ON THE DEVICE (generateErrorFreeReads.py:22-52 + generateErrorProneReads.py:4-45
@@ -990,6 +1005,7 @@ def reference_module(name: str):
             from . import overlapGraphs as dropin
             from . import aligners as dropin_al
             mod.construct_overlap_graph_nx_k = dropin.construct_overlap_graph_nx_k
+            mod.remove_cycles_from_graph = dropin.remove_cycles_from_graph      # looked up at call time, :171
             mod.overlap_alignment = dropin_al.overlap_alignment
     _REF_MODULES[name] = mod
     return mod

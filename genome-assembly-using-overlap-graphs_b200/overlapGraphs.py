@@ -233,6 +233,46 @@ def construct_string_graph(reads):
     return graph
 
 
+def remove_cycles_from_graph(overlap_graph):
+    """Drop-in for overlapGraphs.py:106-130: remove the weakest edge of the cycle nx.find_cycle reports until
+    the graph is a DAG -- the same edges, removed in the same order, as the reference.
+
+    A device pre-pass (ovl_trim_sinks) first peels off every node that cannot reach a cycle.  Such a node is
+    never on a reported cycle, and a depth-first search that enters one only backtracks out of it, so the
+    search on the surviving nodes (same node order, same adjacency order) reports the same cycles.  The
+    reference restarts nx.find_cycle from scratch after every removal; here each restart walks the survivors
+    only, and a graph without any cycle costs no search at all."""
+    G = overlap_graph
+    nodes = list(G.nodes)
+    n = len(nodes)
+    if n == 0 or G.number_of_edges() == 0:
+        return G
+    idx = {v: i for i, v in enumerate(nodes)}
+    edges = list(G.edges)                                    # (source order, adjacency order)
+    src = np.fromiter((idx[u] for u, _ in edges), dtype=np.int32, count=len(edges))
+    dst = np.fromiter((idx[v] for _, v in edges), dtype=np.int32, count=len(edges))
+    loops = src == dst
+    keep, _ = _engine.get_engine().trim_sinks(src[~loops], dst[~loops], n)
+    keep[src[loops]] = True                                  # a self loop is a cycle of its own
+    if loops.any():
+        # nodes that reach a self loop must stay too: fall back to the plain search on the whole graph
+        keep[:] = True
+    if not keep.any():
+        return G                                             # already a DAG
+    H = nx.DiGraph()
+    H.add_nodes_from(v for v, k in zip(nodes, keep.tolist()) if k)
+    H.add_edges_from((u, v) for (u, v), a, b in zip(edges, keep[src].tolist(), keep[dst].tolist()) if a and b)
+    while True:
+        try:
+            cycle = nx.find_cycle(H, orientation='original')
+        except nx.NetworkXNoCycle:
+            break
+        u, v, _w = min(((u, v, G[u][v]["weight"]) for u, v, _ in cycle), key=lambda x: x[2])   # overlapGraphs.py:126
+        G.remove_edge(u, v)
+        H.remove_edge(u, v)
+    return G
+
+
 def __getattr__(name):
     if name.startswith("__") and name.endswith("__"):
         raise AttributeError(name)

@@ -308,6 +308,18 @@ int ovl_simulate_reads(ovl_ctx *ctx, const uint8_t *genome, int64_t genome_len, 
                        int32_t read_len, uint32_t error_thr, uint64_t seed, int64_t *offsets,
                        uint8_t *ascii, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Pre-pass for the weakest-edge cycle removal (overlapGraphs.py:106-130): peel sinks off the directed graph
+ * given as an edge list (src[e] -> dst[e], node ids < n_nodes, no self loops) until none is left.
+ * state[v] (int32[n_nodes], out) = 0 if v survives -- it reaches a cycle or lies on one -- else the
+ * round (>= 1) in which it became a sink.  Peeled nodes cannot be on any cycle nx.find_cycle reports and
+ * leaving them out does not change which cycle it reports, so the host loop runs on the survivors only
+ * and removes the same edges in the same order.  Synchronises the stream (the number of rounds is
+ * data dependent); *h_rounds (host, optional) receives the rounds launched. */
+size_t ovl_trim_workspace_bytes(int64_t n_nodes);
+int ovl_trim_sinks(ovl_ctx *ctx, const int32_t *src, const int32_t *dst, int64_t E, int64_t n_nodes,
+                   int32_t *state, void *workspace, size_t workspace_bytes, int32_t *h_rounds,
+                   void *stream);
+
 /* Order-sensitive fingerprint of an edge list: adds, into *accum (device u64, zeroed by the caller),
  * the sum over rows of mix(first_row + i, row i) mod 2^64.  Shards hashed with their global row
  * offset add up to the fingerprint of the whole list; any misplaced or reordered row changes it.
@@ -322,7 +334,9 @@ int ovl_edge_list_hash(ovl_ctx *ctx, const int32_t *edges, int64_t E, int64_t fi
  * 8 VIMNMX3 + IMAD with all-distinct register operands, 9 one form-1 DP column per chain,
  * 10 one form-2 DP column per chain, 11 a 2 ALU + 2 IMAD column, 12-16 pipe-pairing experiments,
  * 17 __vminu2 (2-input packed min: compiles to VIMNMX3.U16x2 with a repeated operand), 18 VIMNMX3.U16x2,
- * 20 VIADDMNMX.U16x2.
+ * 20 VIADDMNMX.U16x2, 21 VIADDMNMX.U16x2 with an immediate addend (two register sources), 22 a form-1 column
+ * with immediate gap costs, 23 IMAD with an immediate multiplier, 24 PRMT with a repeated source, 25 LOP3 with
+ * an immediate.
  * Synchronises the device.  h_gops receives giga lane-instructions per second. */
 int ovl_int_peak_probe(ovl_ctx *ctx, int32_t kind, int32_t iters, double *h_gops, double *h_ms);
 

@@ -247,6 +247,21 @@ def construct_string_graph(reads: Sequence[str]):
     return g
 
 
+def remove_cycles_from_graph(G):
+    """Restates overlapGraphs.py:106-130 literally (NetworkX calls and all); returns the removed edges in order."""
+    import networkx as nx
+    removed = []
+    while True:
+        try:
+            cycle = nx.find_cycle(G, orientation='original')
+        except nx.NetworkXNoCycle:
+            break
+        u, v, _w = min(((u, v, G[u][v]["weight"]) for u, v, _ in cycle), key=lambda x: x[2])
+        G.remove_edge(u, v)
+        removed.append((u, v))
+    return removed
+
+
 def to_networkx(nodes, edges):
     import networkx as nx
     g = nx.DiGraph()

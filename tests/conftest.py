@@ -52,6 +52,12 @@ def golden_allpairs():
 
 
 @pytest.fixture(scope="session")
+def golden_cycles():
+    with open(os.path.join(GOLDEN, "cycles.json")) as fh:
+        return json.load(fh)["cases"]
+
+
+@pytest.fixture(scope="session")
 def golden_local():
     with open(os.path.join(GOLDEN, "local.json")) as fh:
         return json.load(fh)

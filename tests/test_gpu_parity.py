@@ -761,3 +761,41 @@ def test_device_read_simulator_equals_numpy_mirror(eng, n, l, p, G):
             pa, pb = eng.fill_pairs(cand)
             wa, wb = orc.candidate_pairs(reads, 5)
             assert np.array_equal(pa.cpu().numpy(), wa) and np.array_equal(pb.cpu().numpy(), wb)
+
+
+def test_cycle_removal_with_device_prepass_golden(golden_graphs, golden_cycles, eng):
+    """overlapGraphs.remove_cycles_from_graph (device sink-peeling pre-pass + find_cycle on the survivors) removes the
+    edges the live reference removed, in the same order, on every golden graph -- and leaves the same DAG."""
+    import networkx as nx
+    g = load_pkg("overlapGraphs")
+    by_name = {c["name"]: c for c in golden_graphs}
+    checked = 0
+    for cyc in golden_cycles:
+        c = by_name[cyc["name"]]
+        G, _ = g.construct_overlap_graph_nx_k(c["reads"], k=c["k"])
+        idx = {v: i for i, v in enumerate(G.nodes)}
+        removed = []
+        orig = G.remove_edge
+        G.remove_edge = lambda u, v, _o=orig, _r=removed, _i=idx: (_r.append([_i[u], _i[v]]), _o(u, v))[1]
+        out = g.remove_cycles_from_graph(G)
+        del G.remove_edge
+        assert out is G
+        assert removed == cyc["removed"], cyc["name"]
+        assert G.number_of_edges() == cyc["edges_left"] and nx.is_directed_acyclic_graph(G)
+        checked += len(removed)
+    assert checked > 1500
+    # the pre-pass itself: survivors == nodes that can reach a cycle (brute force with NetworkX)
+    rng = random.Random(2)
+    for n, m in ((1, 0), (30, 40), (200, 260), (400, 1200)):
+        Gd = nx.gnm_random_graph(n, m, seed=n, directed=True)
+        src = np.array([u for u, v in Gd.edges], dtype=np.int32)
+        dst = np.array([v for u, v in Gd.edges], dtype=np.int32)
+        keep, rounds = eng.trim_sinks(src, dst, n)
+        on_cycle = set()
+        for comp in nx.strongly_connected_components(Gd):
+            if len(comp) > 1:
+                on_cycle |= comp
+        reach = set(on_cycle)
+        for v in on_cycle:
+            reach |= nx.ancestors(Gd, v)
+        assert set(np.nonzero(keep)[0].tolist()) == reach, (n, m)

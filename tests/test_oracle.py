@@ -119,3 +119,26 @@ def test_oracle_vs_live_reference_random():
         G2 = orc.to_networkx(nodes, edges)
         assert list(G.edges(data=True)) == list(G2.edges(data=True))
         assert [list(G.pred[n]) for n in G.nodes] == [list(G2.pred[n]) for n in G2.nodes]
+
+
+def test_oracle_cycle_removal_matches_live_reference_fixture():
+    """oracle.remove_cycles_from_graph (the literal restatement of overlapGraphs.py:106-130) on the golden graphs
+    reproduces the removed-edge sequences recorded from the live reference (tests/golden/make_golden_cycles.py)."""
+    import json
+    import os
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "graphs.json")) as fh:
+        graphs = {c["name"]: c for c in json.load(fh)["cases"]}
+    with open(os.path.join(GOLDEN, "cycles.json")) as fh:
+        cycles = json.load(fh)["cases"]
+    total = 0
+    for cyc in cycles:
+        c = graphs[cyc["name"]]
+        nodes, edges, _ = orc.construct_overlap_graph(c["reads"], c["k"])
+        G = orc.to_networkx(nodes, edges)
+        idx = {v: i for i, v in enumerate(nodes)}
+        removed = [[idx[u], idx[v]] for u, v in orc.remove_cycles_from_graph(G)]
+        assert removed == cyc["removed"], cyc["name"]
+        assert G.number_of_edges() == cyc["edges_left"]
+        total += len(removed)
+    assert total > 1500

@@ -74,7 +74,8 @@ def test_forwarding_module_is_patched_with_the_drop_ins(monkeypatch):
     assert ref.construct_overlap_graph_nx_k is og.construct_overlap_graph_nx_k
     assert ref.overlap_alignment is al.overlap_alignment
     # symbols outside the accelerated path resolve through the drop-in module
-    assert og.remove_cycles_from_graph is ref.remove_cycles_from_graph
+    assert ref.remove_cycles_from_graph is og.remove_cycles_from_graph
+    assert og.create_contig is ref.create_contig
     assert og.assemble_contigs_using_overlap_graphs is ref.assemble_contigs_using_overlap_graphs
     # dunder probes never reach the forwarding, and the import stubs do not outlive the module load
     assert not hasattr(og, "__wrapped__")
@@ -89,4 +90,4 @@ def test_no_forwarding_without_opt_in(monkeypatch):
     og = load_pkg("overlapGraphs")
     assert eng.reference_module("overlapGraphs") is None
     with pytest.raises(AttributeError):
-        og.remove_cycles_from_graph
+        og.create_contig

@@ -75,7 +75,8 @@ def main():
     names = {0: "iadd3", 1: "imad", 2: "vimnmx_s32", 3: "viaddmnmx_s16x2", 4: "dp_mix", 5: "prmt", 6: "lop3",
                  7: "lop3_imad_pair", 8: "vimnmx3_imad_distinct_regs", 9: "dp_form1_column", 10: "dp_form2_column", 11: "alu2_fma2_column", 12: "prmt+viaddmnmx", 13: "viaddmnmx+imad", 14: "prmt+imad",
                  15: "2viaddmnmx+imad", 16: "form1_iadd_on_alu", 17: "vminu2_as_vimnmx3_u16x2", 18: "vimnmx3_u16x2",
-                 20: "viaddmnmx_u16x2"}
+                 20: "viaddmnmx_u16x2", 21: "viaddmnmx_u16x2_imm", 22: "dp_form1_column_imm_gaps", 23: "imad_imm",
+                 24: "prmt_2regs", 25: "lop3_imm"}
     probe = {}
     for kind, nm in names.items():
         g, ms = ctypes.c_double(), ctypes.c_double()
