@@ -92,6 +92,10 @@ constexpr int kDpThreads = OVL_DP_THREADS;
 #ifndef OVL_DP_MINB
 #define OVL_DP_MINB 3          // resident CTAs per SM the register allocator must allow (168 regs; measured best)
 #endif
+#ifndef OVL_DP_MINB_IMM38
+#define OVL_DP_MINB_IMM38 4    // the immediate-gap instantiation with 38 columns fits 127 registers without spilling: 4 CTAs per SM
+                               // (measured 10.11 vs 9.84 TCUPS with 3; 32 columns x 32 lanes is best with 3, 5 spills)
+#endif
 #ifndef OVL_DP_F2_NUM
 #define OVL_DP_F2_NUM 1        // columns using form 2 (FMA-heavy): NUM out of every DEN
 #endif
@@ -173,7 +177,7 @@ __host__ __device__ inline int dp_lut_rows(int max_len) {
 // XOR + min(.,1) + multiply-add (LOP3, VIMNMX.U16x2, IMAD) instead of the 4-entry PRMT table;
 // requires eqc == 0 (match >= mismatch).
 template <int G, int T, bool PK, int BITS = 2, bool IMMG = false>
-__global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : OVL_DP_MINB)) overlap_dp_kernel(
+__global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? OVL_DP_MINB_IMM38 : OVL_DP_MINB)) overlap_dp_kernel(
     const uint32_t* __restrict__ packed, int row_words, const int32_t* __restrict__ len,
     const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b, int64_t P, int lut_rows,
     DpParams prm, int32_t* __restrict__ score_out, int32_t* __restrict__ end_out, DpEdgeOut eo) {

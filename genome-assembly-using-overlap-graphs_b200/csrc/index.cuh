@@ -285,23 +285,29 @@ __device__ __forceinline__ int64_t join_cut(int64_t p_begin, int64_t P, int i) {
     return p_begin + P / kTotalsCuts * i + P % kTotalsCuts * i / kTotalsCuts;
 }
 
+// this rank's slice of the pair list, computed once (the 64-bit divisions are not repeated per CTA)
+struct JoinSlice {
+    int64_t p_begin, p_end;
+    float inv_step;          // 1 / (pairs per cut), 0 when the slice has fewer pairs than cuts
+};
+__global__ void join_slice_kernel(const int64_t* __restrict__ pair_off, int64_t U, int rank, int world, JoinSlice* __restrict__ out) {
+    const int64_t total = pair_off[U];
+    JoinSlice s;
+    s.p_begin = total / world * rank + total % world * rank / world;              // == total * rank / world, no overflow
+    s.p_end = total / world * (rank + 1) + total % world * (rank + 1) / world;
+    const int64_t step = (s.p_end - s.p_begin) / kTotalsCuts;
+    s.inv_step = step > 0 ? 1.0f / (float)step : 0.0f;
+    *out = s;
+}
+
 // One thread per source read: the thread whose pair range [pair_off[a], pair_off[a+1]) contains a cut
 // writes that cut's pair index and edge offset -- no search.  Thread 0 writes the scalars and the cuts
-// that sit at the very end of the list.  (The 64-bit divisions are done once per CTA.)
+// that sit at the very end of the list.
 __global__ void __launch_bounds__(256) join_finalize_kernel(JoinEdgeIndex jx, const int32_t* __restrict__ copies, int64_t U,
                                                             const int32_t* __restrict__ bad, const int64_t* __restrict__ n_indexed,
-                                                            int rank, int world, int64_t* __restrict__ totals) {
-    __shared__ int64_t s_slice[2];
-    __shared__ float s_inv_step;
-    if (threadIdx.x == 0) {
-        const int64_t total = jx.pair_off[U];
-        s_slice[0] = total / world * rank + total % world * rank / world;              // == total * rank / world, no overflow
-        s_slice[1] = total / world * (rank + 1) + total % world * (rank + 1) / world;
-        const int64_t step = (s_slice[1] - s_slice[0]) / kTotalsCuts;
-        s_inv_step = step > 0 ? 1.0f / (float)step : 0.0f;
-    }
-    __syncthreads();
-    const int64_t p_begin = s_slice[0], p_end = s_slice[1];
+                                                            const JoinSlice* __restrict__ slice, int64_t* __restrict__ totals) {
+    const int64_t p_begin = slice->p_begin, p_end = slice->p_end;
+    const float inv_step = slice->inv_step;
     const int64_t P = p_end - p_begin;
     const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (a == 0) {
@@ -322,7 +328,7 @@ __global__ void __launch_bounds__(256) join_finalize_kernel(JoinEdgeIndex jx, co
     const int64_t lo_p = jx.pair_off[a], hi_p = jx.pair_off[a + 1];
     if (hi_p <= lo_p || hi_p <= p_begin || lo_p > p_end) return;
     // first cut that is >= lo_p: start from the proportional guess and correct
-    int i = (int)fminf((float)kTotalsCuts, fmaxf(0.0f, (float)(lo_p - p_begin) * s_inv_step));
+    int i = (int)fminf((float)kTotalsCuts, fmaxf(0.0f, (float)(lo_p - p_begin) * inv_step));
     while (i > 0 && join_cut(p_begin, P, i - 1) >= lo_p) --i;
     while (i <= kTotalsCuts && join_cut(p_begin, P, i) < lo_p) ++i;
     for (; i <= kTotalsCuts; ++i) {
@@ -402,16 +408,16 @@ __global__ void __launch_bounds__(256) join_fill_group_kernel(const int64_t* __r
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int64_t q = p + LANES * j - p_begin;
-            pair_a[q] = a;
-            pair_b[q] = b[j];
+            __stcs(pair_a + q, a);                      // streaming: the GBs of pairs must not evict the index from L2
+            __stcs(pair_b + q, b[j]);
         }
     }
     for (; p < to; p += LANES) {
         int32_t r = (int32_t)(p - first);
         if (sr >= 0 && r >= sr) r += 1;
         int64_t q = p - p_begin;
-        pair_a[q] = a;
-        pair_b[q] = (int32_t)bucket[r];
+        __stcs(pair_a + q, a);
+        __stcs(pair_b + q, (int32_t)bucket[r]);
     }
 }
 

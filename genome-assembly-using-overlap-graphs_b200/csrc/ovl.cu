@@ -25,6 +25,7 @@ struct ovl_ctx {
     int device;
     int sm_count;
     uint32_t* probe_sink;
+    void* scratch;               // 256 bytes of device memory for tiny hand-offs between kernels of one call
     long long launches;          // kernels launched through this context (bench bookkeeping)
 };
 
@@ -93,6 +94,7 @@ int ovl_ctx_create(int device, ovl_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->probe_sink = nullptr;
+    c->scratch = nullptr;
     c->launches = 0;
     *out = c;
     return OVL_OK;
@@ -102,6 +104,7 @@ int ovl_ctx_destroy(ovl_ctx* ctx) {
     if (!ctx) return OVL_OK;
     ON_CTX_DEVICE(ctx);
     if (ctx->probe_sink) cudaFree(ctx->probe_sink);
+    if (ctx->scratch) cudaFree(ctx->scratch);
     delete ctx;
     return OVL_OK;
 }
@@ -324,7 +327,11 @@ int ovl_join_finalize(ovl_ctx* ctx, const int64_t* pair_off, const int64_t* edge
     if (edge_base && (!bucket_lo || !self_rank || !cum || !copies)) return fail(OVL_E_ARG, "ovl_join_finalize: edge_base given without the join index");
     if (world < 1 || rank < 0 || rank >= world) return fail(OVL_E_ARG, "ovl_join_finalize: rank %d outside world %d", rank, world);
     JoinEdgeIndex jx{pair_off, edge_base, bucket_lo, self_rank, cum, 0, 0};
-    join_finalize_kernel<<<grid_for(std::max<int64_t>(U, 1), 256), 256, 0, (cudaStream_t)stream>>>(jx, copies, U, bad_count, n_indexed, rank, world, totals);
+    if (!ctx->scratch) CUDA_TRY(cudaMalloc(&ctx->scratch, 256));
+    JoinSlice* slice = (JoinSlice*)ctx->scratch;
+    join_slice_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(pair_off, U, rank, world, slice);
+    LAUNCH_CHECK("join_slice_kernel");
+    join_finalize_kernel<<<grid_for(std::max<int64_t>(U, 1), 256), 256, 0, (cudaStream_t)stream>>>(jx, copies, U, bad_count, n_indexed, slice, totals);
     LAUNCH_CHECK("join_finalize_kernel");
     return OVL_OK;
 }
@@ -341,7 +348,8 @@ int ovl_join_fill(ovl_ctx* ctx, const int64_t* pair_off, int64_t a_begin, int64_
     static const int force_lanes = getenv("OVL_FILL_LANES") ? atoi(getenv("OVL_FILL_LANES")) : -1;
 #define FILL_GROUP(L) join_fill_group_kernel<L><<<grid_for(nA * L, 256), 256, 0, st>>>(pair_off, nA, a_begin, bucket_lo, self_rank, sorted_uid, p_begin, p_count, pair_a, pair_b)
     const int lanes = force_lanes >= 0 ? force_lanes
-                    : total_hint >= 48 * nA ? 32 : total_hint >= 12 * nA ? 8 : total_hint >= 3 * nA ? 4 : total_hint * 8 >= nA ? 1 : 0;
+                    : total_hint >= 16 * nA ? 32 : total_hint >= 3 * nA ? 4 : total_hint * 8 >= nA ? 1 : 0;     // measured at 8 M reads: a whole warp per
+                                                                                                       // source wins down to ~16 candidates
     if (lanes == 32) FILL_GROUP(32);
     else if (lanes == 8) FILL_GROUP(8);
     else if (lanes == 4) FILL_GROUP(4);
@@ -384,7 +392,8 @@ int ovl_candidates_layout(int64_t U, int32_t max_len, int32_t k, int32_t n_segme
     out->sorted_key = take((size_t)n * 8);
     out->sorted_uid = take((size_t)n * 4);
     out->table = take((((size_t)1 << out->table_bits) + 1) * 4);
-    out->pos_of = take((size_t)n * 4);
+    out->pos_of = 0;                 // not built by the one-call job: a read's own slot is searched for only when its
+                                     // prefix and suffix keys coincide (rare), which saves U scattered 4-byte stores
     out->bucket_lo = take((size_t)n * 4);
     out->self_rank = take((size_t)n * 4);
     out->pair_off = take((size_t)(n + 1) * 8);
@@ -417,7 +426,7 @@ int ovl_candidates_build(ovl_ctx* ctx, const uint8_t* ascii, const int64_t* offs
     uint64_t* skey = (uint64_t*)(base + lay->sorted_key);
     uint32_t* suid = (uint32_t*)(base + lay->sorted_uid);
     int32_t* table = (int32_t*)(base + lay->table);
-    int32_t* pos_of = (int32_t*)(base + lay->pos_of);
+    int32_t* pos_of = nullptr;
     int32_t* lo = (int32_t*)(base + lay->bucket_lo);
     int32_t* sr = (int32_t*)(base + lay->self_rank);
     int64_t* pair_off = (int64_t*)(base + lay->pair_off);

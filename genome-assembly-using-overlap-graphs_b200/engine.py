@@ -372,8 +372,7 @@ class OverlapEngine:
         index = KmerIndex(k, view(lay.prefix_key, n, torch.int64), view(lay.suffix_key, n, torch.int64),
                           view(lay.sorted_key, n, torch.int64), view(lay.sorted_uid, n, torch.int32),
                           view(lay.n_indexed, 1, torch.int64), int(lay.key_bits),
-                          view(lay.table, (1 << lay.table_bits) + 1, torch.int32), int(lay.table_bits),
-                          view(lay.pos_of, n, torch.int32))
+                          view(lay.table, (1 << lay.table_bits) + 1, torch.int32), int(lay.table_bits), None)
         has = copies is not None
         done.synchronize()                                            # the one host sync of the job
         t = self._totals.tolist()

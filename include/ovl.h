@@ -166,7 +166,7 @@ int ovl_all_pairs_fill(ovl_ctx *ctx, int64_t U, int64_t a_begin, int64_t p_begin
  * totals -- a dozen kernels launched back to back on `stream`, all arrays carved out of one
  * caller-owned arena.  ovl_candidates_layout fills the byte offsets (and the sizes it chose);
  * arena must be 256-byte aligned and lay->total_bytes long.  After the call (and a wait on the
- * stream) `totals` holds the block described at ovl_join_finalize; the caller then sizes the pair
+ * stream) `totals` holds the block described at ovl_join_finalize (pos_of is not built: lay->pos_of is 0); the caller then sizes the pair
  * list and calls ovl_join_fill / ovl_overlap_dp_edges[_join] on the arrays inside the arena. */
 typedef struct ovl_cand_layout {
     size_t packed, len, bad, n_indexed, prefix_key, suffix_key, sorted_key, sorted_uid, table, pos_of,

@@ -567,9 +567,7 @@ def test_one_call_job_keys_index_table_and_pairs(eng, k):
     skeys = want_pk[valid][order]
     assert np.array_equal(idx.sorted_uid[:n_idx].cpu().numpy().view(np.uint32), uids.astype(np.uint32))
     assert np.array_equal(idx.sorted_key[:n_idx].cpu().numpy().view(np.uint64), skeys)
-    # every indexed read knows its own sorted position
-    pos_of = idx.pos_of[:U].cpu().numpy()
-    assert np.array_equal(pos_of[uids], np.arange(n_idx))
+    assert idx.pos_of is None            # the one-call job does not build it (the granular ovl_index_build can)
     # the bucket table: first sorted position whose key prefix is >= t
     shift = idx.key_bits - idx.table_bits
     table = idx.table.cpu().numpy()
@@ -593,6 +591,9 @@ def test_one_call_job_keys_index_table_and_pairs(eng, k):
     gi = eng.kmer_index(rs, k)
     ga, gb, _ = eng.candidate_pairs(rs, gi, k)
     assert torch.equal(ga, pa) and torch.equal(gb, pb)
+    # every indexed read knows its own sorted position
+    pos_of = gi.pos_of[:U].cpu().numpy()
+    assert np.array_equal(pos_of[uids], np.arange(n_idx))
 
 
 def test_one_call_job_suffix_key_straddles_groups_and_warps(eng):
