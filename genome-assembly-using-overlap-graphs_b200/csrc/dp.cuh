@@ -326,6 +326,8 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
                         a1 = IMMG ? dc + diag : fma_add(dc, one, diag);     // IMMG: two register sources either way
                     }
                     if (dp_form2(c)) {
+                        // IMMG: x + immediate (ptxas emits VIADD).  Forcing these two adds onto the FMA pipe as
+                        // IMAD x, one, imm was measured SLOWER (9.80 vs 10.11 TCUPS), at every form mix.
                         uint32_t a2 = IMMG ? up[c] + gu2 : fma_add(up[c], one, gu2);
                         uint32_t a3 = IMMG ? left + gl2 : fma_add(left, one, gl2);
                         g = __vimin3_u16x2(a1, a2, a3);
