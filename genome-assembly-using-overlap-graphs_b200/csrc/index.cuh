@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint64
                                                                     int64_t* __restrict__ n_out) {
     constexpr int ND_MAX = 1 << kSortMaxDigit;
     constexpr int DPT = ND_MAX / kSortThreads;                    // digits per thread in the CTA scan (4)
-    __shared__ uint16_t wcnt[kSortWarps][ND_MAX];                 // per-warp digit counts, then per-warp local bases
+    static_assert(kSortWarps == 8, "the eight per-warp counters of a digit are one 16-byte shared-memory vector");
+    __shared__ __align__(16) uint16_t wcnt[ND_MAX][kSortWarps];   // [digit][warp]: per-warp digit counts, then per-warp local bases
     __shared__ int32_t delta[ND_MAX];                             // global position - local position, per digit
     __shared__ uint64_t keys_s[kSortChunk];
     __shared__ uint32_t uid_s[kSortChunk];
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint64
         *n_out = (int64_t)hist_scanned[(int64_t)nd * C];           // grand total of the scan = reads with len >= k
     if (base >= n) return;
     const int wib = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < kSortWarps * ND_MAX / 2; i += kSortThreads) reinterpret_cast<uint32_t*>(&wcnt[0][0])[i] = 0u;
+    for (int i = threadIdx.x; i < nd; i += kSortThreads) *reinterpret_cast<uint4*>(&wcnt[i][0]) = make_uint4(0u, 0u, 0u, 0u);
     uint64_t key[kSortRounds];
     uint32_t uid[kSortRounds];
     int rank[kSortRounds];             // rank among the warp's earlier elements with the same digit, or -1 (dead)
@@ -111,31 +112,41 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint64
         if (FIRST && live) live = len[idx] >= k;
         rank[r] = live ? 0 : -1;
     }
+    // ranks inside each round first (eight independent matches) ...
+    int within[kSortRounds], group[kSortRounds];
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        const unsigned d = rank[r] >= 0 ? ((unsigned)(key[r] >> shift) & mask) : (unsigned)nd + lane_id();   // dead lanes match nobody
+        const unsigned peers = __match_any_sync(kFull, d);
+        within[r] = __popc(peers & lanemask_lt());
+        group[r] = __popc(peers);
+    }
     __syncthreads();
+    // ... then the running per-digit counts of the warp, round after round
 #pragma unroll
     for (int r = 0; r < kSortRounds; ++r) {
         const bool live = rank[r] >= 0;
-        const unsigned d = live ? ((unsigned)(key[r] >> shift) & mask) : (unsigned)nd + lane_id();   // dead lanes match nobody
-        const unsigned peers = __match_any_sync(kFull, d);
-        const int within = __popc(peers & lanemask_lt());
-        if (live) rank[r] = (int)wcnt[wib][d] + within;
+        const unsigned d = (unsigned)(key[r] >> shift) & mask;
+        if (live) rank[r] = (int)wcnt[d][wib] + within[r];
         __syncwarp();
-        if (live && within == 0) wcnt[wib][d] = (uint16_t)(wcnt[wib][d] + __popc(peers));
+        if (live && within[r] == 0) wcnt[d][wib] = (uint16_t)(rank[r] + group[r]);
         __syncwarp();
     }
     __syncthreads();
-    // CTA scan over (digit, warp): local sorted position of every warp's first element of every digit
+    // CTA scan over (digit, warp): local sorted position of every warp's first element of every digit.
+    // The eight counters of a digit are one 16-byte vector: one load and one store per digit.
     {
         int32_t cnt[DPT];
         int32_t mine = 0;
+        uint4 vec[DPT];
 #pragma unroll
         for (int x = 0; x < DPT; ++x) {
             const int d = threadIdx.x * DPT + x;
-            int32_t c = 0;
-            if (d < nd)
-                for (int w = 0; w < kSortWarps; ++w) c += wcnt[w][d];
-            cnt[x] = c;
-            mine += c;
+            vec[x] = d < nd ? *reinterpret_cast<const uint4*>(&wcnt[d][0]) : make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t w01 = vec[x].x, w23 = vec[x].y, w45 = vec[x].z, w67 = vec[x].w;
+            cnt[x] = (int32_t)((w01 & 0xffffu) + (w01 >> 16) + (w23 & 0xffffu) + (w23 >> 16) +
+                               (w45 & 0xffffu) + (w45 >> 16) + (w67 & 0xffffu) + (w67 >> 16));
+            mine += cnt[x];
         }
         int32_t inc = mine;
 #pragma unroll
@@ -157,12 +168,14 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint64
             const int d = threadIdx.x * DPT + x;
             if (d < nd) {
                 delta[d] = hist_scanned[(int64_t)d * C + blockIdx.x] - lstart;
-                int32_t run = lstart;
-                for (int w = 0; w < kSortWarps; ++w) {
-                    int32_t c = wcnt[w][d];
-                    wcnt[w][d] = (uint16_t)run;
-                    run += c;
-                }
+                // exclusive prefix over the eight warps, starting at the digit's local start
+                uint32_t c[8] = {vec[x].x & 0xffffu, vec[x].x >> 16, vec[x].y & 0xffffu, vec[x].y >> 16,
+                                 vec[x].z & 0xffffu, vec[x].z >> 16, vec[x].w & 0xffffu, vec[x].w >> 16};
+                uint32_t run = (uint32_t)lstart, b[8];
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { b[w] = run; run += c[w]; }
+                *reinterpret_cast<uint4*>(&wcnt[d][0]) = make_uint4(b[0] | (b[1] << 16), b[2] | (b[3] << 16),
+                                                                    b[4] | (b[5] << 16), b[6] | (b[7] << 16));
                 lstart += cnt[x];
             }
         }
@@ -172,7 +185,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint64
     for (int r = 0; r < kSortRounds; ++r) {
         if (rank[r] < 0) continue;
         const unsigned d = (unsigned)(key[r] >> shift) & mask;
-        const int lp = (int)wcnt[wib][d] + rank[r];
+        const int lp = (int)wcnt[d][wib] + rank[r];
         keys_s[lp] = key[r];
         uid_s[lp] = uid[r];
     }
@@ -207,12 +220,15 @@ __global__ void __launch_bounds__(256) bucket_table_kernel(const uint64_t* __res
 struct SortedCopies {
     const uint32_t* sorted_uid;
     const int32_t* copies;
-    const int32_t* sorted_copies;
     const int64_t* n_ptr;
     __device__ __forceinline__ int64_t operator()(int64_t i) const {
-        if (i >= *n_ptr) return 0;
-        return sorted_copies != nullptr ? (int64_t)sorted_copies[i] : (int64_t)copies[sorted_uid[i]];
+        return i < *n_ptr ? (int64_t)copies[sorted_uid[i]] : 0;
     }
+};
+// the same from the array the last sort pass wrote (zero past the end of the index: the caller cleared it)
+struct SortedCopiesArray {
+    const int32_t* sorted_copies;
+    __device__ __forceinline__ int64_t operator()(int64_t i) const { return (int64_t)sorted_copies[i]; }
 };
 
 // One thread per source read a (overlapGraphs.py:43-52): bucket of suffix_key[a] in the sorted prefix

@@ -229,6 +229,7 @@ int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len
     uint64_t* tmp_key = (uint64_t*)ws;            ws += align256((size_t)U * sizeof(uint64_t));
     uint32_t* tmp_uid = (uint32_t*)ws;
 
+    if (sorted_copies) CUDA_TRY(cudaMemsetAsync(sorted_copies, 0, (size_t)U * sizeof(int32_t), st));   // zero past the end of the index
     const int passes = sort_passes(key_bits);
     const int D = sort_digit_bits(key_bits);
     int nl = 0;
@@ -300,7 +301,10 @@ int ovl_join_count(ovl_ctx* ctx, const uint64_t* suffix_key, const uint64_t* pre
     int nl = 0;
     if (copies) {
         // copies along the sorted index, scanned: the copy mass of any bucket range is a difference of two entries
-        CUDA_TRY((exclusive_scan<SortedCopies, int64_t>(SortedCopies{sorted_uid, copies, sorted_copies, n_indexed}, cum, U, sums, st, &nl)));
+        if (sorted_copies)
+            CUDA_TRY((exclusive_scan<SortedCopiesArray, int64_t>(SortedCopiesArray{sorted_copies}, cum, U, sums, st, &nl)));
+        else
+            CUDA_TRY((exclusive_scan<SortedCopies, int64_t>(SortedCopies{sorted_uid, copies, n_indexed}, cum, U, sums, st, &nl)));
     }
     if (U > 0) {
         join_count_kernel<<<grid_for(U, 256), 256, 0, st>>>(suffix_key, prefix_key, len, k, U, sorted_key, sorted_uid, n_indexed, table,

@@ -98,8 +98,8 @@ int ovl_pack_reads_keys(ovl_ctx *ctx, const uint8_t *ascii, const int64_t *offse
  *           size this library picks for (U, key_bits).
  *   pos_of  int32[U]: sorted position of every indexed read (its own slot in its bucket).
  *   copies / sorted_copies (both or neither): int32[U] multiplicity of every read in, the same along
- *           the sorted index out (sorted_copies[i] = copies[sorted_uid[i]]) -- what ovl_join_count
- *           scans when reads have copies. */
+ *           the sorted index out (sorted_copies[i] = copies[sorted_uid[i]], 0 for i >= *n_indexed) -- what
+ *           ovl_join_count scans when reads have copies. */
 size_t ovl_index_workspace_bytes(int64_t U);
 int32_t ovl_index_table_bits(int64_t U, int32_t key_bits);
 /* key_bits: number of significant key bits to sort on (2k + segment-tag bits); 0 means 2k. */

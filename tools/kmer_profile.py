@@ -85,13 +85,13 @@ def k0():
 
 def k2():
     nat.check(nat.lib.ovl_index_build(ctx, P(lay.prefix_key), P(lay.len), U, k, lay.key_bits, P(lay.sorted_key), P(lay.sorted_uid),
-                                      P(lay.n_indexed), P(lay.table), lay.table_bits, P(lay.pos_of), None, None, P(lay.scratch),
+                                      P(lay.n_indexed), P(lay.table), lay.table_bits, None, None, None, P(lay.scratch),
                                       lay.scratch_bytes, st()))
 
 
 def k3c():
     nat.check(nat.lib.ovl_join_count(ctx, P(lay.suffix_key), P(lay.prefix_key), P(lay.len), k, U, P(lay.sorted_key), P(lay.sorted_uid),
-                                     P(lay.n_indexed), P(lay.table), lay.table_bits, lay.key_bits, P(lay.pos_of), None, None, None,
+                                     P(lay.n_indexed), P(lay.table), lay.table_bits, lay.key_bits, None, None, None, None,
                                      P(lay.bucket_lo), P(lay.self_rank), P(lay.pair_off), None, P(lay.scratch), lay.scratch_bytes, st()))
     nat.check(nat.lib.ovl_join_finalize(ctx, P(lay.pair_off), None, None, None, None, None, U, P(lay.bad), P(lay.n_indexed), 0, 1,
                                         ctypes.c_void_p(totals.data_ptr()), st()))
