@@ -66,7 +66,10 @@ struct DpParams {
 // at twice the rate of the three-register form on this GPU (probe kinds 20 / 21).  Same recurrence,
 // same instruction count, same results.  Requires cmax < kGapNever (so that it still never wins) and
 // cmax + kGapNever <= 65535 (no carry between the halves): cmax <= 0x6fff.
-constexpr uint32_t kGapNever = 0x7000u;
+#ifndef OVL_DP_GAPNEVER
+#define OVL_DP_GAPNEVER 0x7000u
+#endif
+constexpr uint32_t kGapNever = OVL_DP_GAPNEVER;
 constexpr uint32_t kGapNever2 = kGapNever * 0x10001u;
 
 // optional fused edge expansion in the DP epilogue (all null: plain score/end output)
@@ -142,6 +145,41 @@ __device__ __forceinline__ uint32_t read_symbol(const uint32_t* row, int i) {
 __device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; }
 __device__ __forceinline__ constexpr bool dp_form2(int c) {
     return OVL_DP_F2_NUM > 0 && (c * OVL_DP_F2_NUM) % OVL_DP_F2_DEN < OVL_DP_F2_NUM;
+}
+// Column form by position.  With OVL_DP_PATTERN (decimal digits, most significant first, repeated over the columns):
+//   1  PRMT, add, VIADDMNMX(up), VIADDMNMX(left)
+//   2  PRMT, 3 adds, VIMNMX3
+//   3  PRMT, add, up+g on the FMA pipe, two-input packed min, VIADDMNMX(left)
+//   4  as 3 with the up+g add left to ptxas
+//   5  PRMT, add, VIADDMNMX(up), left+g on the FMA pipe, two-input packed min
+//   6  PRMT, add, VIADDMNMX(up), left+g, fp16x2 min      (6-8 need every value < 0x7c00: OVL_DP_GAPNEVER=0x3e00)
+//   7  PRMT, 3 adds, two fp16x2 mins
+//   8  PRMT, add, up+g, fp16x2 min, VIADDMNMX(left)
+// The two-input packed min (VIMNMX3.U16x2 with a repeated source) issues at twice the rate of the
+// three-source DPX forms (probe kind 17).
+#ifdef OVL_DP_PATTERN
+__device__ __forceinline__ constexpr int dp_form(int c) {
+    int nd = 0;
+    for (long long v = OVL_DP_PATTERN; v > 0; v /= 10) ++nd;
+    long long v = OVL_DP_PATTERN;
+    for (int skip = nd - 1 - c % nd; skip > 0; --skip) v /= 10;
+    return (int)(v % 10);
+}
+#else
+__device__ __forceinline__ constexpr int dp_form(int c) { return dp_form2(c) ? 2 : 1; }
+#endif
+// min of two packed halves that are both below 0x7c00, as an fp16x2 min: the bit patterns of non-negative finite
+// halves order like the integers they spell (no .ftz: subnormal patterns are kept), SASS HMNMX2
+__device__ __forceinline__ uint32_t hmin2_bits(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("min.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+// a + c on the FMA pipe in every instantiation (a * one + c, `one` a runtime 1)
+__device__ __forceinline__ uint32_t fma_add_always(uint32_t a, uint32_t one, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(c));
+    return d;
 }
 // (There is no cheaper 2-input packed min to build a third form from: __vminu2 compiles to
 // VIMNMX3.U16x2 with a repeated operand on sm_100a -- probe kind 17.)
@@ -325,12 +363,28 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
                         uint32_t dc = prmt(lu.x, lu.y, sel[c]);
                         a1 = IMMG ? dc + diag : fma_add(dc, one, diag);     // IMMG: two register sources either way
                     }
-                    if (dp_form2(c)) {
+                    if (dp_form(c) == 2) {
                         // IMMG: x + immediate (ptxas emits VIADD).  Forcing these two adds onto the FMA pipe as
                         // IMAD x, one, imm was measured SLOWER (9.80 vs 10.11 TCUPS), at every form mix.
                         uint32_t a2 = IMMG ? up[c] + gu2 : fma_add(up[c], one, gu2);
                         uint32_t a3 = IMMG ? left + gl2 : fma_add(left, one, gl2);
                         g = __vimin3_u16x2(a1, a2, a3);
+                    } else if (dp_form(c) == 3 || dp_form(c) == 4) {
+                        uint32_t a2 = dp_form(c) == 3 ? fma_add_always(up[c], one, gu2) : up[c] + gu2;
+                        uint32_t m1 = __vminu2(a1, a2);
+                        g = __viaddmin_u16x2(left, gl2, m1);
+                    } else if (dp_form(c) == 6) {
+                        uint32_t t1 = __viaddmin_u16x2(up[c], gu2, a1);
+                        g = hmin2_bits(t1, left + gl2);
+                    } else if (dp_form(c) == 7) {
+                        g = hmin2_bits(hmin2_bits(a1, up[c] + gu2), left + gl2);
+                    } else if (dp_form(c) == 8) {
+                        uint32_t m1 = hmin2_bits(a1, up[c] + gu2);
+                        g = __viaddmin_u16x2(left, gl2, m1);
+                    } else if (dp_form(c) == 5) {
+                        uint32_t t1 = __viaddmin_u16x2(up[c], gu2, a1);
+                        uint32_t a3 = fma_add_always(left, one, gl2);
+                        g = __vminu2(t1, a3);
                     } else {
                         uint32_t t1 = __viaddmin_u16x2(up[c], gu2, a1);
                         g = __viaddmin_u16x2(left, gl2, t1);

@@ -1134,6 +1134,11 @@ int ovl_int_peak_probe(ovl_ctx* ctx, int32_t kind, int32_t iters, double* h_gops
         case 23: return run_probe<23>(ctx, iters, h_gops, h_ms);
         case 24: return run_probe<24>(ctx, iters, h_gops, h_ms);
         case 25: return run_probe<25>(ctx, iters, h_gops, h_ms);
+        case 26: return run_probe<26>(ctx, iters, h_gops, h_ms);
+        case 27: return run_probe<27>(ctx, iters, h_gops, h_ms);
+        case 28: return run_probe<28>(ctx, iters, h_gops, h_ms);
+        case 29: return run_probe<29>(ctx, iters, h_gops, h_ms);
+        case 30: return run_probe<30>(ctx, iters, h_gops, h_ms);
         default: return fail(OVL_E_ARG, "ovl_int_peak_probe: unknown kind %d", kind);
     }
 }

@@ -108,6 +108,20 @@ __global__ void __launch_bounds__(kProbeThreads) int_probe_kernel(uint32_t* out,
                     asm volatile("prmt.b32 %0, %0, %0, %1;" : "+r"(v[c]) : "r"(w[c]));
                 } else if (KIND == 25) {    // LOP3 with an immediate (two register sources)
                     asm volatile("lop3.b32 %0, %0, %1, 0x0f0f0f0f, 0x96;" : "+r"(v[c]) : "r"(w[c]));
+                } else if (KIND == 26) {    // fp16x2 min alone (HMNMX2): which pipe, what rate?
+                    asm volatile("min.f16x2 %0, %0, %1;" : "+r"(v[c]) : "r"(w[c]));
+                } else if (KIND == 27) {    // HMNMX2 + LOP3 on independent chains
+                    asm volatile("min.f16x2 %0, %0, %1;" : "+r"(v[c]) : "r"(x[c]));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(w[c]) : "r"(a0), "r"(b0));
+                } else if (KIND == 28) {    // HMNMX2 + IMAD on independent chains
+                    asm volatile("min.f16x2 %0, %0, %1;" : "+r"(v[c]) : "r"(x[c]));
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(w[c]) : "r"(one), "r"(b0));
+                } else if (KIND == 29) {    // HMNMX2 + VIADDMNMX.U16x2 on independent chains
+                    asm volatile("min.f16x2 %0, %0, %1;" : "+r"(v[c]) : "r"(x[c]));
+                    w[c] = __viaddmin_u16x2(w[c], 0x3e003e00u, z[c]);
+                } else if (KIND == 30) {    // HMNMX2 + PRMT on independent chains
+                    asm volatile("min.f16x2 %0, %0, %1;" : "+r"(v[c]) : "r"(x[c]));
+                    asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(w[c]) : "r"(y[c]), "r"(z[c]));
                 } else if (KIND == 5) {     // PRMT
                     asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(v[c]) : "r"(w[c]), "r"(b0));
                 } else {                    // LOP3
@@ -126,7 +140,7 @@ inline int probe_ops_per_iter(int kind) {
     if (kind == 10) return 5;
     if (kind == 4 || kind == 9 || kind == 11 || kind == 16 || kind == 22) return 4;
     if (kind == 15) return 3;
-    return (kind == 7 || kind == 8 || kind == 12 || kind == 13 || kind == 14) ? 2 : 1;
+    return (kind == 7 || kind == 8 || kind == 12 || kind == 13 || kind == 14 || (kind >= 27 && kind <= 30)) ? 2 : 1;
 }
 
 }  // namespace ovl

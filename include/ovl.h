@@ -336,7 +336,7 @@ int ovl_edge_list_hash(ovl_ctx *ctx, const int32_t *edges, int64_t E, int64_t fi
  * 17 __vminu2 (2-input packed min: compiles to VIMNMX3.U16x2 with a repeated operand), 18 VIMNMX3.U16x2,
  * 20 VIADDMNMX.U16x2, 21 VIADDMNMX.U16x2 with an immediate addend (two register sources), 22 a form-1 column
  * with immediate gap costs, 23 IMAD with an immediate multiplier, 24 PRMT with a repeated source, 25 LOP3 with
- * an immediate.
+ * an immediate, 26 HMNMX2 (fp16x2 min), 27-30 HMNMX2 next to LOP3 / IMAD / VIADDMNMX.U16x2 / PRMT.
  * Synchronises the device.  h_gops receives giga lane-instructions per second. */
 int ovl_int_peak_probe(ovl_ctx *ctx, int32_t kind, int32_t iters, double *h_gops, double *h_ms);
 

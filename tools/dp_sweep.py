@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--modes", default="1,2")
     ap.add_argument("--only", default="", help="LANESxCOLS, e.g. 4x38")
     ap.add_argument("--no-probe", action="store_true")
+    ap.add_argument("--probe-only", action="store_true")
     args = ap.parse_args()
     import torch
     synth = importlib.import_module(PKG + ".synth")
@@ -44,7 +45,7 @@ def main():
     print(json.dumps({"lib": nat.LIB_PATH, "workload": args.workload, "pairs": P, "cells": cells,
                       "max_len": rs.max_len, "plan": eng.dp_plan(rs.max_len, 10, -1, args.indel)}), flush=True)
     ref = None
-    for mode in [int(x) for x in args.modes.split(",")]:
+    for mode in ([] if args.probe_only else [int(x) for x in args.modes.split(",")]):
         for lanes in (1, 2, 4, 8, 16, 32):
             for cols in ((19, 25, 32, 38) if mode == 1 else (32,)):
                 if lanes * cols < rs.max_len or lanes * cols > 4 * max(rs.max_len, 38):
@@ -76,7 +77,8 @@ def main():
                  7: "lop3_imad_pair", 8: "vimnmx3_imad_distinct_regs", 9: "dp_form1_column", 10: "dp_form2_column", 11: "alu2_fma2_column", 12: "prmt+viaddmnmx", 13: "viaddmnmx+imad", 14: "prmt+imad",
                  15: "2viaddmnmx+imad", 16: "form1_iadd_on_alu", 17: "vminu2_as_vimnmx3_u16x2", 18: "vimnmx3_u16x2",
                  20: "viaddmnmx_u16x2", 21: "viaddmnmx_u16x2_imm", 22: "dp_form1_column_imm_gaps", 23: "imad_imm",
-                 24: "prmt_2regs", 25: "lop3_imm"}
+                 24: "prmt_2regs", 25: "lop3_imm", 26: "hmnmx2", 27: "hmnmx2+lop3", 28: "hmnmx2+imad",
+                 29: "hmnmx2+viaddmnmx", 30: "hmnmx2+prmt"}
     probe = {}
     for kind, nm in names.items():
         g, ms = ctypes.c_double(), ctypes.c_double()
