@@ -444,7 +444,9 @@ def measure(env, wl, steps, warmup, cpu_seconds, use_peer=True, with_cpu=True, s
             return eng.overlap_edges(h_bases, h_off, h_counts if wl.has_dups else None, k, shard, reuse_host_buffer=True)
         # every rank copies its slice over its own PCIe link into one shared, page-locked host buffer;
         # after the barrier rank 0 holds the complete ordered edge list in host memory
-        eng.overlap_edges(h_bases, h_off, h_counts if wl.has_dups else None, k, shard, host_sink=sink)
+        # the inputs cross PCIe once in total: rank r uploads its 1/world, one all-gather over NVLink completes them
+        eng.overlap_edges(h_bases, h_off, h_counts if wl.has_dups else None, k, shard, host_sink=sink,
+                          upload_group=dist.group.WORLD)
         dist.barrier()
         return sink.rows()
 
@@ -557,7 +559,8 @@ def measure(env, wl, steps, warmup, cpu_seconds, use_peer=True, with_cpu=True, s
                         "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                         "edge_list_hash_matches_device_path": e2e_ok,
                         "path": "engine.overlap_edges: pinned host reads in, host edge rows out, D2H overlapped with the DP"
-                                + ("; each rank writes its slice into one shared page-locked host buffer" if world > 1 else "")},
+                                + ("; the reads cross PCIe once in total (each rank uploads 1/N, one all-gather over NVLink); each rank "
+                                   "writes its slice into one shared page-locked host buffer" if world > 1 else "")},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         if numba is not None:
             line["cpu_baseline_numba"] = numba

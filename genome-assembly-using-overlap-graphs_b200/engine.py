@@ -142,14 +142,40 @@ class OverlapEngine:
             x = x.to(dtype)
         return x.to(self.device, non_blocking=True)
 
+    def _to_device_sharded(self, x, dtype, group, slack: int = 0) -> torch.Tensor:
+        """Host array that EVERY rank of `group` holds -> the same array on every rank's GPU, moving it over
+        PCIe only once in total: rank r uploads the r-th 1/world of it and one all-gather over NVLink
+        completes the copies.  (Each rank uploading everything costs world x the bytes on the host's
+        root complexes, which the ranks share.)  Small arrays take the plain path."""
+        import torch.distributed as dist
+        if isinstance(x, np.ndarray):
+            x = self._from_numpy(x)
+        world = dist.get_world_size(group) if group is not None else 1
+        n = int(x.shape[0])
+        if world == 1 or x.is_cuda or x.dtype != dtype or n * x.element_size() < (1 << 20):
+            out = torch.empty(n + slack, dtype=dtype, device=self.device)
+            out[:n].copy_(x.to(dtype) if x.dtype != dtype else x, non_blocking=True)
+            return out[:n] if slack == 0 else out
+        rank = dist.get_rank(group)
+        gran = max(1, 16 // x.element_size())
+        per = ((n + world - 1) // world + gran - 1) // gran * gran
+        out = torch.empty(world * per + slack, dtype=dtype, device=self.device)
+        lo = min(n, rank * per)
+        hi = min(n, lo + per)
+        if hi > lo:
+            out[lo:hi].copy_(x[lo:hi], non_blocking=True)
+        dist.all_gather_into_tensor(out[:world * per], out[rank * per:(rank + 1) * per], group=group)
+        return out[:n] if slack == 0 else out
+
     # ------------------------------------------------------------------ K0
     def upload_reads(self, bases, offsets, max_len: Optional[int] = None, code_bits: int = 2) -> ReadSet:
         """bases: uint8[sum len] ASCII, offsets: int64[U+1] (NumPy or CPU/GPU torch tensors)."""
         ascii_dev, off_dev, U, max_len = self._upload_ascii(bases, offsets, max_len)
         return self.pack_reads(ascii_dev, off_dev, U, max_len, code_bits)
 
-    def _upload_ascii(self, bases, offsets, max_len: Optional[int] = None):
-        """Host (or device) reads -> (ascii_dev with slack, off_dev, U, max_len)."""
+    def _upload_ascii(self, bases, offsets, max_len: Optional[int] = None, group=None):
+        """Host (or device) reads -> (ascii_dev with slack, off_dev, U, max_len).  With `group` (every rank
+        holds the same host arrays) each rank uploads its 1/world and an all-gather completes the copies."""
         off_host = None
         if isinstance(offsets, np.ndarray):
             off_host = offsets
@@ -163,6 +189,11 @@ class OverlapEngine:
                 off_host = offsets.cpu().numpy()
             max_len = int(np.max(off_host[1:] - off_host[:-1])) if U > 0 else 0
         total = int(bases.shape[0]) if U > 0 else 0
+        if group is not None and total:
+            src = self._from_numpy(bases) if isinstance(bases, np.ndarray) else bases
+            ascii_dev = self._to_device_sharded(src[:total], torch.uint8, group, slack=64)
+            off_dev = self._to_device_sharded(offsets, torch.int64, group)
+            return ascii_dev, off_dev, U, max_len
         ascii_dev = torch.empty(total + 64, dtype=torch.uint8, device=self.device)   # 32 B slack for K0
         if total:
             src = self._from_numpy(bases) if isinstance(bases, np.ndarray) else bases
@@ -453,16 +484,19 @@ class OverlapEngine:
             return np.zeros((0, 4), np.int32)
         main = torch.cuda.current_stream(self.device)
         st = self._stream()
-        # Chunk sizes shrink geometrically (1/2, 1/4, ... 1/64 of the slice, cut at the 64ths the job computed):
-        # every copy hides behind the next, larger-than-needed DP chunk and only the last 1/64 is exposed.
-        # chunk_pairs caps the chunk size (more, equal chunks first) for very long lists.
+        # Chunk schedule in 64ths of the slice (the cut points the job computed): 4, 8, 13, 13, 9, 6, 4, 3, 2, 1, 1.
+        # Small chunks first so the copy engine starts early, then chunks that shrink by ~2/3 per step: every copy
+        # hides behind the next DP chunk as long as copying a slice takes less than ~2/3 of computing it, and only
+        # the last 1/64 is exposed.  (Round 2 first used 1/2, 1/4, ... 1/64: fine while the copy costs < 1/2 of the
+        # DP -- one to four GPUs -- but with eight GPUs sharing the host's 92 GB/s the copy is 0.66 of the DP and a
+        # first chunk of 1/2 left 50 ms of it exposed.)  chunk_pairs caps the chunk size for very long lists.
         if P < min_chunked_pairs:
             cuts = [0, 64]
         else:
-            cuts = [0, 32, 48, 56, 60, 62, 63, 64]
-            while (cuts[1] - cuts[0]) * P // 64 > chunk_pairs and cuts[1] - cuts[0] > 1:
-                half = (cuts[1] - cuts[0]) // 2
-                cuts = [c for c in range(0, cuts[1], half)] + cuts[1:]
+            cuts = [0, 4, 12, 25, 38, 47, 53, 57, 60, 62, 63, 64]
+            per64 = max(1, P // 64)
+            step = max(1, chunk_pairs // per64)               # largest chunk, in 64ths
+            cuts = [c for lo, hi in zip(cuts[:-1], cuts[1:]) for c in range(lo, hi, step)] + [64]
         n_chunks = len(cuts) - 1
         bounds = [cand.cut_pairs[c] - cand.p_begin for c in cuts]
         e_bounds = [cand.cut_edges[c] - cand.e_begin for c in cuts]
@@ -876,10 +910,12 @@ class OverlapEngine:
                       match_score: int = 10, mismatch: int = -1, indel: int = INDEL_DEFAULT,
                       stats: Optional[dict] = None, to_host: bool = True, reuse_host_buffer: bool = False,
                       min_weight: Optional[int] = None, pairs=None, segments=None, n_segments: int = 1,
-                      host_sink=None, code_bits: int = 2):
+                      host_sink=None, code_bits: int = 2, upload_group=None):
         """HOST buffers in, HOST edge rows out: unique reads (ASCII bytes + offsets) and their
         multiplicities -> int32[E, 4] (node_a, node_b, weight, end_position) in the reference's
-        insertion order.  This is the call the drop-in graph builder makes."""
+        insertion order.  This is the call the drop-in graph builder makes.
+        upload_group: a torch.distributed group whose ranks all make this call with the SAME host arrays
+        (the sharded builder): the inputs then cross PCIe once in total instead of once per rank."""
         if k < 0:
             raise AssertionError("k-mer length must be non-negative")      # overlapGraphs.py:17
         copies = node_off = None
@@ -888,11 +924,15 @@ class OverlapEngine:
             if counts_np.size and int(counts_np.max()) > 1:
                 no = np.zeros(counts_np.shape[0] + 1, dtype=np.int64)
                 np.cumsum(counts_np, out=no[1:])
-                copies = self._to_device(counts_np, torch.int32)
-                node_off = self._to_device(no, torch.int64)
+                if upload_group is not None and counts_np.dtype == np.int32:
+                    copies = self._to_device_sharded(counts_np, torch.int32, upload_group)
+                    node_off = self._to_device_sharded(no, torch.int64, upload_group)
+                else:
+                    copies = self._to_device(counts_np, torch.int32)
+                    node_off = self._to_device(no, torch.int64)
         if pairs is None and self.composite_ok(k, code_bits):
             # the common call: K0-K3 as one job, one host sync, then fill + DP (+ D2H overlapped with the DP)
-            ascii_dev, off_dev, U, max_len = self._upload_ascii(bases, offsets)
+            ascii_dev, off_dev, U, max_len = self._upload_ascii(bases, offsets, group=upload_group)
             seg_dev = self._to_device(segments, torch.int32) if segments is not None else None
             cand = self.build_candidates(ascii_dev, off_dev, U, max_len, k, copies, node_off, shard, seg_dev, n_segments)
             pa, pb = self.fill_pairs(cand)

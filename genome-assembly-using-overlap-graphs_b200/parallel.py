@@ -49,6 +49,32 @@ def gather_edges(edges: torch.Tensor, dst: int = 0, group=None) -> Optional[torc
     return None
 
 
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_cpus(device_index: int):
+    """(numa node, CPUs of that node) the GPU hangs off, from sysfs; None when the platform does not say."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        return (node, cpus) if cpus else None
+    except Exception:
+        return None
+
+
 class SharedEdgeSink:
     """Host-side landing zone for the edge rows of all ranks of ONE node: a POSIX shared-memory
     segment that every rank maps and page-locks (cudaHostRegister), so each GPU copies its slice
@@ -60,7 +86,12 @@ class SharedEdgeSink:
     CPU tensor slice this rank must fill.  After a barrier, `rows()` on rank 0 is the whole list.
     """
 
-    def __init__(self, group=None, cuda: bool = True, initial_rows: int = 1 << 20):
+    def __init__(self, group=None, cuda: bool = True, initial_rows: int = 1 << 20, numa_local: bool = True):
+        # numa_local: before the segment is page-locked every rank first-touches ITS share of it from a CPU of the
+        # NUMA node its GPU hangs off, so the rank's device->host copies land in memory behind its own PCIe root
+        # instead of crossing the socket interconnect to wherever rank 0's registration would have faulted the pages in
+        self.numa_local = numa_local
+        self.numa_node = None
         self.group = group
         self.cuda = cuda and torch.cuda.is_available()
         self.rank = dist.get_rank(group)
@@ -107,6 +138,9 @@ class SharedEdgeSink:
                 pass
         arr = np.ndarray((rows, 4), dtype=np.int32, buffer=self.shm.buf)
         self.tensor = torch.from_numpy(arr)
+        if self.cuda and self.numa_local:
+            self._first_touch(arr, rows)
+            dist.barrier(group=self.group)
         if self.cuda:
             # page-lock the mapping in every process, one rank at a time: concurrent registration of
             # the same not-yet-populated segment fails with cudaErrorOperatingSystem (measured)
@@ -120,6 +154,26 @@ class SharedEdgeSink:
                 dist.barrier(group=self.group)
         self.capacity = rows
         dist.barrier(group=self.group)
+
+    def _first_touch(self, arr, rows: int):
+        """Fault in rows [rank, rank+1) * rows / world (the pair-range shards produce nearly equal edge counts)
+        from a CPU next to this rank's GPU.  Pages of a fresh POSIX segment are placed on the node of the CPU that
+        first writes them; the later cudaHostRegister pins them where they are."""
+        import os
+        where = gpu_numa_cpus(torch.cuda.current_device())
+        lo, hi = rows * self.rank // self.world, rows * (self.rank + 1) // self.world
+        old = None
+        try:
+            if where is not None:
+                old = os.sched_getaffinity(0)
+                cpus = where[1] & old
+                if cpus:
+                    os.sched_setaffinity(0, cpus)
+                    self.numa_node = where[0]
+            arr[lo:hi] = 0
+        finally:
+            if old is not None:
+                os.sched_setaffinity(0, old)
 
     def __call__(self, n_local: int, e_begin: Optional[int] = None, total: Optional[int] = None) -> torch.Tensor:
         """The slice this rank must fill.  With (e_begin, total) -- the global row offset of the rank's slice

@@ -103,6 +103,16 @@ def _worker(rank, world, port, q):
         if rank == 0:
             report["sink_equal"] = bool(np.array_equal(sink.rows(), whole.cpu().numpy()))
             report["sink_hash_equal"] = (eng.edge_hash_host(sink.rows()) & 0xFFFFFFFFFFFFFFFF) == (whole_hash & 0xFFFFFFFFFFFFFFFF)
+        dist.barrier()
+        # (4) the same with the inputs uploaded once in total (each rank 1/world + an all-gather over NVLink)
+        sink.rows()[:] = 0
+        dist.barrier()
+        eng.overlap_edges(ub, uo, counts.astype(np.int32), k, (rank, world), host_sink=sink, upload_group=dist.group.WORLD)
+        dist.barrier()
+        if rank == 0:
+            report["sharded_upload_equal"] = bool(np.array_equal(sink.rows(), whole.cpu().numpy()))
+        d_whole = eng._to_device_sharded(ub, torch.uint8, dist.group.WORLD, slack=64)
+        report["sharded_upload_bytes_equal"] = bool(np.array_equal(d_whole[:len(ub)].cpu().numpy(), ub))
         sink.close()
         report["edges"] = E
         report["ok"] = True
@@ -138,5 +148,7 @@ def test_two_gpu_exchange_paths_equal_single_gpu():
     assert r0["gather_equal"] and r0["gather_hash_equal"]
     assert r0["peer_equal"]
     assert r0["sink_equal"] and r0["sink_hash_equal"]
+    assert r0["sharded_upload_equal"]
+    assert all(reports[r]["sharded_upload_bytes_equal"] for r in range(world))
     for p in procs:
         assert p.exitcode == 0

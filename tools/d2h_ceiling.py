@@ -1,7 +1,8 @@
 """Aggregate device->host bandwidth of N ranks copying at once (what bounds the N-GPU e2e leg: all edge rows must
 land in host memory).  torchrun --nproc-per-node N tools/d2h_ceiling.py
   (a) every rank into its own cudaHostAlloc buffer; (b) every rank into its slice of ONE shared, page-locked segment
-  (parallel.SharedEdgeSink -- the e2e path)."""
+  (parallel.SharedEdgeSink -- the e2e path), faulted in by rank 0's registration; (c) the same with every rank's share
+  first-touched from a CPU of its GPU's NUMA node."""
 import importlib
 import json
 import os
@@ -42,11 +43,16 @@ def timed(dst, reps=3):
 
 out = {"ranks": world, "bytes_per_rank": rows * 16}
 out["own_pinned_buffers_gbs"] = timed(own)
+out["gpu_numa"] = par.gpu_numa_cpus(lr)[0] if par.gpu_numa_cpus(lr) else None
 if world > 1:
-    sink = par.SharedEdgeSink(initial_rows=rows * world)
-    mine = sink(rows, rank * rows, rows * world)
-    out["shared_segment_gbs"] = timed(mine)
-    sink.close()
+    nodes = [None] * world
+    dist.all_gather_object(nodes, out["gpu_numa"])
+    out["gpu_numa"] = nodes
+    for numa in (False, True):
+        sink = par.SharedEdgeSink(initial_rows=rows * world, numa_local=numa)
+        mine = sink(rows, rank * rows, rows * world)
+        out["shared_segment_numa_local_gbs" if numa else "shared_segment_gbs"] = timed(mine)
+        sink.close()
 if rank == 0:
     print(json.dumps(out), flush=True)
 if world > 1:
