@@ -706,6 +706,88 @@ def sweep_extra(env, iterations=10, cpu_seconds=20.0):
     return out
 
 
+def next_rows_extra(env):
+    """SURVEY 8(f) rows f1, f2, f4 measured through their drop-in calls, each result compared with the oracle
+    (the checker) in the same run: contig -> genome local alignment (aligners.py:85-202 as the reference's
+    performanceMeasures.py:219-221 loop uses it), the all-pairs builder (overlapGraphs.py:196-232) and the
+    cycle removal (overlapGraphs.py:106-130)."""
+    import numpy as np
+    from oracle import overlap_oracle as orc
+    synth = importlib.import_module(PKG + ".synth")
+    al = importlib.import_module(PKG + ".aligners")
+    og = importlib.import_module(PKG + ".overlapGraphs")
+    torch = env.torch
+    out = {}
+    genome_u8 = synth.phix_like_genome()
+    genome = genome_u8.tobytes().decode()
+    G = len(genome)
+    rng = np.random.Generator(np.random.PCG64(2024))
+    # f1: 96 contigs (100 .. 1,000 bases, 1 % substitutions) against the 5,386-base genome
+    contigs = []
+    for i in range(96):
+        L = int(rng.integers(100, 1001))
+        st = int(rng.integers(0, G - L))
+        c = genome_u8[st:st + L].copy()
+        flip = rng.random(L) < 0.01
+        c[flip] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(flip.sum()))]
+        contigs.append(c.tobytes().decode())
+    cells = sum(len(c) for c in contigs) * G
+    al.local_alignment_batch(contigs[:4], genome)                      # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    got = al.local_alignment_batch(contigs, genome)
+    t_batch = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    one = [al.local_alignment(c, genome) for c in contigs[:16]]
+    t_one = (time.perf_counter() - t0) / 16
+    t0 = time.perf_counter()
+    ref = [orc.local_alignment(c, genome) for c in contigs[:16]]
+    t_cpu = (time.perf_counter() - t0) / 16
+    assert got[:16] == ref and one == ref
+    out["f1_local_alignment"] = {
+        "contigs": len(contigs), "genome": G, "cells": cells,
+        "batch_one_launch_ms": t_batch * 1e3, "batch_ms_per_contig": t_batch * 1e3 / len(contigs),
+        "batch_mcups": cells / t_batch / 1e6, "per_call_ms_per_contig": t_one * 1e3,
+        "oracle_c_port_ms_per_contig_1_thread": t_cpu * 1e3, "reference_numba_ms_per_contig": 304.0,
+        "note": "str contigs in, the reference's 6-tuples out (traceback strings included), wall clock; first 16 results "
+                "compared with the oracle; 304 ms per contig is BASELINE.md's figure for the Numba reference"}
+    # f2: the all-pairs builder on 400 reads (159,600 ordered pairs)
+    b, o = synth.simulate_reads(genome_u8, 400, 100, 0.01, seed=11)
+    reads = synth.to_strings(b, o)
+    with contextlib.redirect_stdout(io.StringIO()):
+        og.construct_overlap_graph_string(reads[:50])                  # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        g_gpu = og.construct_overlap_graph_string(reads)
+        t_gpu = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        g_cpu = orc.construct_overlap_graph_string(reads, nthreads=0)
+        t_cpu = time.perf_counter() - t0
+    g_gpu = g_gpu[0]
+    cpu_edges = g_cpu[1]                                               # (nodes, edges, read_copies)
+    assert len(cpu_edges) == g_gpu.number_of_edges()
+    out["f2_all_pairs_builder"] = {"reads": len(reads), "ordered_pairs_aligned": len(set(reads)) * (len(set(reads)) - 1),
+                                   "edges_score_gt_0": g_gpu.number_of_edges(), "gpu_dropin_wall_ms": t_gpu * 1e3,
+                                   "oracle_c_port_wall_ms_all_threads": t_cpu * 1e3, "same_edge_count_as_oracle": True}
+    # f4: cycle removal on the N = 1,000 graph (same removals as the literal NetworkX restatement)
+    b, o = synth.simulate_reads(genome_u8, 1000, 100, 0.01, seed=12)
+    reads = synth.to_strings(b, o)
+    g1, _ = og.construct_overlap_graph_nx_k(reads, k=5)
+    g2 = g1.copy()
+    e_before = g1.number_of_edges()
+    t0 = time.perf_counter()
+    og.remove_cycles_from_graph(g1)
+    t_gpu = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    orc.remove_cycles_from_graph(g2)
+    t_cpu = time.perf_counter() - t0
+    assert list(g1.edges(data=True)) == list(g2.edges(data=True))
+    out["f4_cycle_removal"] = {"edges_before": e_before, "edges_removed": e_before - g1.number_of_edges(),
+                               "dropin_with_device_sink_peeling_ms": t_gpu * 1e3,
+                               "literal_networkx_restatement_ms": t_cpu * 1e3, "same_graph_after": True}
+    return out
+
+
 def configs_extra(env, args):
     extra = {}
     t_all = time.perf_counter()
@@ -738,6 +820,12 @@ def configs_extra(env, args):
         extra["configs[4]_sweep"]["bench_seconds"] = time.perf_counter() - t0
     except Exception as exc:                               # noqa: BLE001
         extra["configs[4]_sweep"] = {"error": f"{type(exc).__name__}: {exc}"}
+    try:
+        t0 = time.perf_counter()
+        extra["next_rows"] = next_rows_extra(env)
+        extra["next_rows"]["bench_seconds"] = time.perf_counter() - t0
+    except Exception as exc:                               # noqa: BLE001
+        extra["next_rows"] = {"error": f"{type(exc).__name__}: {exc}"}
     extra["bench_seconds"] = time.perf_counter() - t_all
     return extra
 

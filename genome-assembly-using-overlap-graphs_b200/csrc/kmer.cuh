@@ -26,6 +26,10 @@ constexpr uint64_t kInvalidKey = ~0ull;
 // Requires: ascii base 16-byte aligned and >= 32 bytes of slack after the last read.
 constexpr int kPackThreads = 256;
 constexpr int kPackPieces = (kPackThreads * 64 + 32 + 16) / 16 + 2;      // 16-byte pieces a CTA's span can touch
+constexpr int kPackIters = (kPackPieces + 3 + kPackThreads - 1) / kPackThreads;      // rounds of the conversion loop (5)
+#ifndef OVL_PACK_MINB
+#define OVL_PACK_MINB 8                  // resident CTAs per SM: measured at 8 M reads 455 us (8, two spilled words) / 465 (6) / 496 (5) / 555 (4); the loop without the preloads: 475
+#endif
 
 // 4 ASCII bytes -> their 2-bit codes gathered in byte 3 of the result; `bad` collects c ^ (the letter each code stands for)
 __device__ __forceinline__ uint32_t codes4(uint32_t c, uint32_t& bad) {
@@ -37,7 +41,7 @@ __device__ __forceinline__ uint32_t codes4(uint32_t c, uint32_t& bad) {
 }
 
 template <bool KEYS>
-__global__ void __launch_bounds__(kPackThreads, 8) pack_reads_kernel(const uint8_t* __restrict__ ascii,
+__global__ void __launch_bounds__(kPackThreads, OVL_PACK_MINB) pack_reads_kernel(const uint8_t* __restrict__ ascii,
                                                                   const int64_t* __restrict__ offsets,
                                                                   int64_t U, int row_words,
                                                                   uint32_t* __restrict__ packed,
@@ -75,22 +79,31 @@ __global__ void __launch_bounds__(kPackThreads, 8) pack_reads_kernel(const uint8
     const int64_t span_base = s_span[0];
     const int n_pieces = (int)((s_span[1] - span_base + 15) >> 4);
     uint32_t bad = 0;
-    for (int p = threadIdx.x; p < n_pieces + 3; p += kPackThreads) {
+    // all of the thread's 16-byte loads are issued before the first conversion (memory-level parallelism: a CTA's
+    // span is at most kPackPieces pieces = kPackIters rounds)
+    uint4 v[kPackIters];
+#pragma unroll
+    for (int it = 0; it < kPackIters; ++it) {
+        const int p = it * kPackThreads + threadIdx.x;
+        v[it] = p < n_pieces ? __ldg(reinterpret_cast<const uint4*>(ascii + span_base + 16 * (int64_t)p)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int it = 0; it < kPackIters; ++it) {
+        const int p = it * kPackThreads + threadIdx.x;
+        if (p >= n_pieces + 3) break;
         uint32_t w = 0;
         if (p < n_pieces) {
             const int64_t g = span_base + 16 * (int64_t)p;
-            uint4 v = __ldg(reinterpret_cast<const uint4*>(ascii + g));
+            uint32_t x[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
             if (g + 16 > total_bytes) {              // the slack after the last read is not input: treat it as 'A'
-                uint32_t x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     int64_t nv = total_bytes - (g + 4 * i);
                     uint32_t keep = nv >= 4 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << (8 * (int)nv)) - 1u));
                     x[i] = (x[i] & keep) | (0x41414141u & ~keep);
                 }
-                v = make_uint4(x[0], x[1], x[2], x[3]);
             }
-            const uint32_t m0 = codes4(v.x, bad), m1 = codes4(v.y, bad), m2 = codes4(v.z, bad), m3 = codes4(v.w, bad);
+            const uint32_t m0 = codes4(x[0], bad), m1 = codes4(x[1], bad), m2 = codes4(x[2], bad), m3 = codes4(x[3], bad);
             w = __byte_perm(__byte_perm(m0, m1, 0x0073), __byte_perm(m2, m3, 0x0073), 0x5410);
         }
         bits[p] = w;                                 // three zero words of padding after the stream

@@ -331,11 +331,7 @@ int ovl_join_finalize(ovl_ctx* ctx, const int64_t* pair_off, const int64_t* edge
     if (edge_base && (!bucket_lo || !self_rank || !cum || !copies)) return fail(OVL_E_ARG, "ovl_join_finalize: edge_base given without the join index");
     if (world < 1 || rank < 0 || rank >= world) return fail(OVL_E_ARG, "ovl_join_finalize: rank %d outside world %d", rank, world);
     JoinEdgeIndex jx{pair_off, edge_base, bucket_lo, self_rank, cum, 0, 0};
-    if (!ctx->scratch) CUDA_TRY(cudaMalloc(&ctx->scratch, 256));
-    JoinSlice* slice = (JoinSlice*)ctx->scratch;
-    join_slice_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(pair_off, U, rank, world, slice);
-    LAUNCH_CHECK("join_slice_kernel");
-    join_finalize_kernel<<<grid_for(std::max<int64_t>(U, 1), 256), 256, 0, (cudaStream_t)stream>>>(jx, copies, U, bad_count, n_indexed, slice, totals);
+    join_finalize_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(jx, copies, U, bad_count, n_indexed, rank, world, totals);
     LAUNCH_CHECK("join_finalize_kernel");
     return OVL_OK;
 }
