@@ -117,6 +117,12 @@ constexpr int kDpThreads = OVL_DP_THREADS;
 #endif
 
 constexpr int kDpKUnroll = OVL_DP_KUNROLL;
+#ifndef OVL_DP_ROWVAR
+#define OVL_DP_ROWVAR 0        // 1: keep the lane's row index in a register instead of deriving it from the step counter
+#endif
+#ifndef OVL_DP_BULK
+#define OVL_DP_BULK 0          // packed 2-bit instantiations: prologue / epilogue on aligned base windows and packed keys (below)
+#endif
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t d;
@@ -136,6 +142,26 @@ __device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t one, uint32_t c
 }
 __device__ __forceinline__ uint32_t base_code(const uint32_t* row, int i) {
     return (row[i >> 4] >> ((i & 15) * 2)) & 3u;
+}
+// T consecutive 2-bit bases of a packed row, starting at base `first`, re-aligned so that base c of the window sits
+// at bits 2 (c % 16) of w[c / 16]: one funnel shift per word; after that every per-base extraction shifts by a
+// compile-time amount.  Words past the end of the row are read from its last word (their bases only ever feed
+// padded DP cells, which nothing reads).
+template <int T>
+__device__ __forceinline__ void base_window(const uint32_t* row, int row_words, int first, uint32_t (&w)[(2 * T + 31) / 32]) {
+    constexpr int NW = (2 * T + 31) / 32;
+    const int i0 = first >> 4;
+    const int sh = (first & 15) * 2;
+    uint32_t a[NW + 1];
+#pragma unroll
+    for (int i = 0; i <= NW; ++i) a[i] = row[min(i0 + i, row_words - 1)];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) w[i] = __funnelshift_r(a[i], a[i + 1], sh);
+}
+// ((w >> s) & 3) << up, with compile-time s and up
+__device__ __forceinline__ uint32_t base_field(uint32_t w, int s, int up) {
+    const uint32_t mask = 3u << up;
+    return s >= up ? (w >> (s - up)) & mask : (w << (up - s)) & mask;
 }
 // BITS = 2: 2-bit packed rows (16 bases per word); BITS = 8: byte rows (any alphabet)
 template <int BITS>
@@ -281,7 +307,25 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
 
     // ---- per-row tables: lut.x / lut.y = bytes {cost of s[i] vs code 0..3} for pair 0 / 1
     uint2* lut = smem_lut + (size_t)gib * lut_rows;
-    {
+    constexpr bool BULK = OVL_DP_BULK && PK && BITS == 2;
+    constexpr int NW = (2 * T + 31) / 32;
+    if (BULK) {
+        // lane r builds rows [rT, rT + T): the two query reads' bases come out of two aligned windows with
+        // compile-time shifts (the row-strided version spent ~20 instructions per row on variable shifts)
+        const uint32_t nec4 = (uint32_t)prm.nec * 0x01010101u;
+        const uint32_t flip = (uint32_t)(prm.eqc ^ prm.nec);
+        uint32_t sa[NW], sb[NW];
+        base_window<T>(srow[0], row_words, r * T, sa);
+        base_window<T>(srow[PAIRS - 1], row_words, r * T, sb);
+#pragma unroll
+        for (int c = 0; c < T; ++c) {
+            const int i = r * T + c;
+            const int sft = 2 * (c & 15);
+            const uint32_t xa = nec4 ^ (flip << base_field(sa[c >> 4], sft, 3));      // byte ca of the table = eqc
+            const uint32_t xb = nec4 ^ (flip << base_field(sb[c >> 4], sft, 3));
+            lut[i] = make_uint2(xa, xb);         // unconditional: the table has G*T rows (launch_dp); rows >= nmax are never read
+        }
+    } else {
         const uint32_t nec4 = (uint32_t)prm.nec * 0x01010101u;
         const uint32_t flip = (uint32_t)(prm.eqc ^ prm.nec);
         for (int i = r; i < nmax; i += G) {
@@ -302,17 +346,30 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
 #else
     const uint32_t beta2 = PK ? pack2(prm.beta) : (uint32_t)prm.beta;
 #endif
+    if (BULK) {
+        uint32_t wa[NW], wb[NW];
+        base_window<T>(trow[0], row_words, r * T, wa);
+        base_window<T>(trow[PAIRS - 1], row_words, r * T, wb);
 #pragma unroll
-    for (int c = 0; c < T; ++c) {
-        int j = min(r * T + c, max_col);
-        uint32_t ca = read_symbol<BITS>(trow[0], j);
-        if (PK) {
-            uint32_t cb = read_symbol<BITS>(trow[PAIRS - 1], j);
-            sel[c] = BITS == 8 ? (ca | (cb << 16)) : (ca | 0x80u | ((4u + cb) << 8) | 0x8000u);
-        } else {
-            sel[c] = ca;
+        for (int c = 0; c < T; ++c) {
+            const int sft = 2 * (c & 15);
+            // ca | 0x80 | ((4 + cb) << 8) | 0x8000
+            sel[c] = base_field(wa[c >> 4], sft, 0) | base_field(wb[c >> 4], sft, 8) | 0x8480u;
+            up[c] = beta2;
         }
-        up[c] = beta2;
+    } else {
+#pragma unroll
+        for (int c = 0; c < T; ++c) {
+            int j = min(r * T + c, max_col);
+            uint32_t ca = read_symbol<BITS>(trow[0], j);
+            if (PK) {
+                uint32_t cb = read_symbol<BITS>(trow[PAIRS - 1], j);
+                sel[c] = BITS == 8 ? (ca | (cb << 16)) : (ca | 0x80u | ((4u + cb) << 8) | 0x8000u);
+            } else {
+                sel[c] = ca;
+            }
+            up[c] = beta2;
+        }
     }
 #if OVL_DP_PREPACK
     const uint32_t gu2 = prm.gu2, gl2 = prm.gl2, maxs2 = prm.maxs2;
@@ -341,9 +398,17 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
     uint32_t col0 = beta2;       // lane 0: C[i][0] = beta + i*maxs
     const int steps = __reduce_max_sync(kFull, nmax) + G - 1;      // warp-uniform trip count
 
+#if OVL_DP_ROWVAR
+    int irow = -r;
+    const int fold_row = (PK && nshort < nmax) ? nshort - 1 : INT_MIN;
+#endif
 #pragma unroll kDpKUnroll
     for (int k = 0; k < steps; ++k) {
+#if OVL_DP_ROWVAR
+        const int i = irow++;                              // 0-based row of s handled this step
+#else
         const int i = k - r;                               // 0-based row of s handled this step
+#endif
         uint32_t recv = __shfl_up_sync(kFull, out, 1, G);
         col0 += maxs2;                                     // lane 0 at step k: C[k+1][0]
         if (r == 0) recv = col0;
@@ -403,7 +468,11 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
             diag_in = recv;
             // a pair shorter than its partner reaches its last row inside the loop: fold my columns
             // into its running (first) minimum now, its half keeps computing an ignored padded DP
+#if OVL_DP_ROWVAR
+            if (PK && i == fold_row) {
+#else
             if (PK && i + 1 == nshort && nshort < nmax) {
+#endif
 #pragma unroll
                 for (int c = 0; c < T; ++c) {
                     int j = r * T + c + 1;
@@ -417,11 +486,24 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
 #pragma unroll
     for (int h = 0; h < PAIRS; ++h) {
         if (n[h] == nmax && nmax > 0) {
+            if (BULK) {
+                // first minimum over my columns inside t as ONE running min of (value << 8 | column): the smallest
+                // value wins, then the smallest column; then against what I hold (lane 0: the j = 0 cell)
+                const int nv = m[h] - r * T;                 // columns c < nv have j = rT + c + 1 <= m
+                int key = INT_MAX;
 #pragma unroll
-            for (int c = 0; c < T; ++c) {
-                int j = r * T + c + 1;
-                int v = PK ? (int)(h == 0 ? (up[c] & 0xffffu) : (up[c] >> 16)) : (int)up[c];
-                if (j <= m[h] && v < bestv[h]) { bestv[h] = v; bestj[h] = j; }
+                for (int c = 0; c < T; ++c) {
+                    const int kc = (int)(h == 0 ? (up[c] & 0xffffu) : (up[c] >> 16)) * 256 + c;
+                    if (c < nv) key = min(key, kc);
+                }
+                if (key != INT_MAX && (key >> 8) < bestv[h]) { bestv[h] = key >> 8; bestj[h] = r * T + (key & 0xff) + 1; }
+            } else {
+#pragma unroll
+                for (int c = 0; c < T; ++c) {
+                    int j = r * T + c + 1;
+                    int v = PK ? (int)(h == 0 ? (up[c] & 0xffffu) : (up[c] >> 16)) : (int)up[c];
+                    if (j <= m[h] && v < bestv[h]) { bestv[h] = v; bestj[h] = j; }
+                }
             }
         } else if (PK) {
             bestv[h] = bests;
