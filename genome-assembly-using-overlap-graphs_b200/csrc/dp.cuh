@@ -117,12 +117,18 @@ constexpr int kDpThreads = OVL_DP_THREADS;
 #endif
 
 constexpr int kDpKUnroll = OVL_DP_KUNROLL;
-#ifndef OVL_DP_ROWVAR
-#define OVL_DP_ROWVAR 0        // 1: keep the lane's row index in a register instead of deriving it from the step counter
-#endif
 #ifndef OVL_DP_BULK
-#define OVL_DP_BULK 0          // packed 2-bit instantiations: prologue / epilogue on aligned base windows and packed keys (below)
+#define OVL_DP_BULK 1          // packed 2-bit instantiations of at most OVL_DP_BULK_MAX_COLS columns: prologue / epilogue on
+#endif                         // aligned base windows and packed keys, row index kept in a register (dp_bulk() below)
+#ifndef OVL_DP_BULK_MAX_COLS
+#define OVL_DP_BULK_MAX_COLS 256
 #endif
+// Which instantiations take the bulk prologue / epilogue.  Measured (kernel alone, profiles/r2v_dp_bulk_prologue.jsonl):
+// 4 x 38 at l = 150: 10.11 -> 10.66 TCUPS (the prologue and epilogue were 7 % of the executed instructions there);
+// 32 x 32 at l = 1,000, where they are amortised over 1,031 rows: 10.48 -> 10.35, so the long instantiations keep the
+// row-strided code.
+template <int G, int T, bool PK, int BITS>
+__host__ __device__ constexpr bool dp_bulk() { return OVL_DP_BULK && PK && BITS == 2 && G * T <= OVL_DP_BULK_MAX_COLS; }
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t d;
@@ -307,7 +313,7 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
 
     // ---- per-row tables: lut.x / lut.y = bytes {cost of s[i] vs code 0..3} for pair 0 / 1
     uint2* lut = smem_lut + (size_t)gib * lut_rows;
-    constexpr bool BULK = OVL_DP_BULK && PK && BITS == 2;
+    constexpr bool BULK = dp_bulk<G, T, PK, BITS>();
     constexpr int NW = (2 * T + 31) / 32;
     if (BULK) {
         // lane r builds rows [rT, rT + T): the two query reads' bases come out of two aligned windows with
@@ -398,17 +404,13 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
     uint32_t col0 = beta2;       // lane 0: C[i][0] = beta + i*maxs
     const int steps = __reduce_max_sync(kFull, nmax) + G - 1;      // warp-uniform trip count
 
-#if OVL_DP_ROWVAR
+    // BULK: the lane's row index lives in a register (one add per step) instead of being re-derived from the step
+    // counter and the thread index (S2R, LOP3, IADD3 per step under the 128-register cap)
     int irow = -r;
-    const int fold_row = (PK && nshort < nmax) ? nshort - 1 : INT_MIN;
-#endif
+    const int fold_row = (PK && nshort < nmax) ? nshort - 1 : INT_MIN;     // the step at which the shorter pair ends
 #pragma unroll kDpKUnroll
     for (int k = 0; k < steps; ++k) {
-#if OVL_DP_ROWVAR
-        const int i = irow++;                              // 0-based row of s handled this step
-#else
-        const int i = k - r;                               // 0-based row of s handled this step
-#endif
+        const int i = BULK ? irow++ : k - r;               // 0-based row of s handled this step
         uint32_t recv = __shfl_up_sync(kFull, out, 1, G);
         col0 += maxs2;                                     // lane 0 at step k: C[k+1][0]
         if (r == 0) recv = col0;
@@ -468,11 +470,7 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
             diag_in = recv;
             // a pair shorter than its partner reaches its last row inside the loop: fold my columns
             // into its running (first) minimum now, its half keeps computing an ignored padded DP
-#if OVL_DP_ROWVAR
-            if (PK && i == fold_row) {
-#else
-            if (PK && i + 1 == nshort && nshort < nmax) {
-#endif
+            if (PK && (BULK ? i == fold_row : (i + 1 == nshort && nshort < nmax))) {
 #pragma unroll
                 for (int c = 0; c < T; ++c) {
                     int j = r * T + c + 1;

@@ -598,7 +598,7 @@ int launch_dp(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, const int
     int64_t grid = (groups + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA;
     if (grid > 0x7fffffffll) return fail(OVL_E_ARG, "ovl_overlap_dp: too many pairs for one launch (%lld)", (long long)P);
     // the bulk prologue of the packed 2-bit kernels writes table rows [0, G*T) without a bound check
-    int lut_rows = dp_lut_rows((OVL_DP_BULK && PK && BITS == 2) ? std::max(max_len, G * T) : max_len);
+    int lut_rows = dp_lut_rows(dp_bulk<G, T, PK, BITS>() ? std::max(max_len, G * T) : max_len);
     size_t smem = (size_t)GROUPS_PER_CTA * 2 * PAIRS * row_words * sizeof(uint32_t)       // TMA-staged read rows
                 + (size_t)GROUPS_PER_CTA * lut_rows * sizeof(uint2)                       // per-row score tables
                 + (kDpThreads / 32) * sizeof(uint64_t);                                   // one mbarrier per warp

@@ -1,11 +1,11 @@
 #!/bin/bash
-# full GPU suite on the default library, then DP kernel A/B: named variants vs the default build
+# DP kernel A/B: the full GPU suite under the FIRST named variant library, then the kernel alone for every variant and the default build
 set -u
 TAG=${1:-run15}
 shift
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1
-echo "pytest rc=$?"; tail -4 gpurun_out/${TAG}_pytest.log
+OVL_B200_LIB=build/variants/libovl_$1.so python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_$1.log 2>&1
+echo "pytest ($1) rc=$?"; tail -4 gpurun_out/${TAG}_pytest_$1.log
 for v in "$@" default; do
   echo "variant $v" >> gpurun_out/${TAG}_dp_variants.jsonl
   if [ "$v" = default ]; then unset OVL_B200_LIB; else export OVL_B200_LIB=build/variants/libovl_$v.so; fi
