@@ -200,6 +200,15 @@ __device__ __forceinline__ constexpr int dp_form(int c) {
 #else
 __device__ __forceinline__ constexpr int dp_form(int c) { return dp_form2(c) ? 2 : 1; }
 #endif
+// the short (bulk) instantiations run 2 form-2 columns in 5 (10.72 vs 10.66 TCUPS at 4 x 38 with 1 in 3); the long ones 1 in 3
+template <bool BULK_>
+__device__ __forceinline__ constexpr int dp_form_of(int c) {
+#if defined(OVL_DP_PATTERN) || defined(OVL_DP_F2_FIXED)
+    return dp_form(c);
+#else
+    return BULK_ ? ((c * 2) % 5 < 2 ? 2 : 1) : dp_form(c);
+#endif
+}
 // min of two packed halves that are both below 0x7c00, as an fp16x2 min: the bit patterns of non-negative finite
 // halves order like the integers they spell (no .ftz: subnormal patterns are kept), SASS HMNMX2
 __device__ __forceinline__ uint32_t hmin2_bits(uint32_t a, uint32_t b) {
@@ -430,25 +439,25 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
                         uint32_t dc = prmt(lu.x, lu.y, sel[c]);
                         a1 = IMMG ? dc + diag : fma_add(dc, one, diag);     // IMMG: two register sources either way
                     }
-                    if (dp_form(c) == 2) {
+                    if (dp_form_of<BULK>(c) == 2) {
                         // IMMG: x + immediate (ptxas emits VIADD).  Forcing these two adds onto the FMA pipe as
                         // IMAD x, one, imm was measured SLOWER (9.80 vs 10.11 TCUPS), at every form mix.
                         uint32_t a2 = IMMG ? up[c] + gu2 : fma_add(up[c], one, gu2);
                         uint32_t a3 = IMMG ? left + gl2 : fma_add(left, one, gl2);
                         g = __vimin3_u16x2(a1, a2, a3);
-                    } else if (dp_form(c) == 3 || dp_form(c) == 4) {
-                        uint32_t a2 = dp_form(c) == 3 ? fma_add_always(up[c], one, gu2) : up[c] + gu2;
+                    } else if (dp_form_of<BULK>(c) == 3 || dp_form_of<BULK>(c) == 4) {
+                        uint32_t a2 = dp_form_of<BULK>(c) == 3 ? fma_add_always(up[c], one, gu2) : up[c] + gu2;
                         uint32_t m1 = __vminu2(a1, a2);
                         g = __viaddmin_u16x2(left, gl2, m1);
-                    } else if (dp_form(c) == 6) {
+                    } else if (dp_form_of<BULK>(c) == 6) {
                         uint32_t t1 = __viaddmin_u16x2(up[c], gu2, a1);
                         g = hmin2_bits(t1, left + gl2);
-                    } else if (dp_form(c) == 7) {
+                    } else if (dp_form_of<BULK>(c) == 7) {
                         g = hmin2_bits(hmin2_bits(a1, up[c] + gu2), left + gl2);
-                    } else if (dp_form(c) == 8) {
+                    } else if (dp_form_of<BULK>(c) == 8) {
                         uint32_t m1 = hmin2_bits(a1, up[c] + gu2);
                         g = __viaddmin_u16x2(left, gl2, m1);
-                    } else if (dp_form(c) == 5) {
+                    } else if (dp_form_of<BULK>(c) == 5) {
                         uint32_t t1 = __viaddmin_u16x2(up[c], gu2, a1);
                         uint32_t a3 = fma_add_always(left, one, gl2);
                         g = __vminu2(t1, a3);
