@@ -40,6 +40,7 @@
 // A 32-bit variant (one pair per group, s32 DPX ops, compare+select for dc) covers scoring
 // schemes or read lengths whose range does not fit 16 bits.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "joinidx.cuh"
 
@@ -73,6 +74,26 @@ constexpr uint32_t kGapNever = OVL_DP_GAPNEVER;
 constexpr uint32_t kGapNever2 = kGapNever * 0x10001u;
 
 // optional fused edge expansion in the DP epilogue (all null: plain score/end output)
+// OVL_DP_STREAM_HINTS=1 accesses the pair list (read once) and the edge rows (written once) with the streaming
+// (evict-first) hints.  Measured: no effect on the kernel's DRAM traffic (35.0 GB read per launch at the 1 M-read
+// workload either way, profiles/r2y_dp_traffic.csv), so it stays off.
+#ifndef OVL_DP_STREAM_HINTS
+#define OVL_DP_STREAM_HINTS 0
+#endif
+__device__ __forceinline__ int32_t ld_pair(const int32_t* p) {
+#if OVL_DP_STREAM_HINTS
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+__device__ __forceinline__ void st_edge(int4* p, int4 v) {
+#if OVL_DP_STREAM_HINTS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 struct DpEdgeOut {
     int4* edges;                 // int32[E][4] rows, or null
     const int32_t* copies;       // multiplicity per unique read, or null when every read occurs once
@@ -120,6 +141,12 @@ constexpr int kDpKUnroll = OVL_DP_KUNROLL;
 #ifndef OVL_DP_BULK
 #define OVL_DP_BULK 1          // packed 2-bit instantiations of at most OVL_DP_BULK_MAX_COLS columns: prologue / epilogue on
 #endif                         // aligned base windows and packed keys, row index kept in a register (dp_bulk() below)
+#ifndef OVL_DP_PHASES
+#define OVL_DP_PHASES 0        // 1: bulk instantiations split the row loop into ramp-up / steady / ramp-down phases
+#endif
+#ifndef OVL_DP_ROWVAR_ALL
+#define OVL_DP_ROWVAR_ALL 1    // the register row index in the long instantiations too (32 x 32: 10.49 -> 10.58 TCUPS)
+#endif
 #ifndef OVL_DP_BULK_MAX_COLS
 #define OVL_DP_BULK_MAX_COLS 256
 #endif
@@ -294,7 +321,7 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
         for (int idx = lane; idx < NROWS; idx += 32) {
             int64_t p = warp_p0 + idx / 2;                  // rows come in (s, t) order per pair
             int32_t uid = 0;
-            if (p < P) uid = (idx & 1) ? pair_b[p] : pair_a[p];
+            if (p < P) uid = (idx & 1) ? ld_pair(pair_b + p) : ld_pair(pair_a + p);
             tma_load_1d(smem_u32(warp_rows + (size_t)idx * row_words), packed + (size_t)uid * row_words, row_bytes, bar);
         }
     }
@@ -307,7 +334,7 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
     for (int h = 0; h < PAIRS; ++h) {
         int64_t p = p0 + h;
         bool live = p < P;
-        int32_t a = live ? pair_a[p] : 0, b = live ? pair_b[p] : 0;
+        int32_t a = live ? ld_pair(pair_a + p) : 0, b = live ? ld_pair(pair_b + p) : 0;
         n[h] = live ? len[a] : 0;
         m[h] = live ? len[b] : 0;
         srow[h] = grp_rows + (size_t)(2 * h) * row_words;
@@ -415,15 +442,18 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
 
     // BULK: the lane's row index lives in a register (one add per step) instead of being re-derived from the step
     // counter and the thread index (S2R, LOP3, IADD3 per step under the 128-register cap)
+    constexpr bool ROWV = BULK || OVL_DP_ROWVAR_ALL;
     int irow = -r;
     const int fold_row = (PK && nshort < nmax) ? nshort - 1 : INT_MIN;     // the step at which the shorter pair ends
-#pragma unroll kDpKUnroll
-    for (int k = 0; k < steps; ++k) {
-        const int i = BULK ? irow++ : k - r;               // 0-based row of s handled this step
+    // One wavefront step.  CHECKED: the lane may be outside its rows (ramp-up / ramp-down of the wavefront) and the
+    // shorter pair of the couple may end at this row.  Unchecked steps are the steady state, see the phases below.
+    auto step = [&](int k, auto checked_tag) {
+        constexpr bool CHECKED = decltype(checked_tag)::value;
+        const int i = ROWV ? irow++ : k - r;               // 0-based row of s handled this step
         uint32_t recv = __shfl_up_sync(kFull, out, 1, G);
         col0 += maxs2;                                     // lane 0 at step k: C[k+1][0]
         if (r == 0) recv = col0;
-        if ((unsigned)i < (unsigned)nmax) {               // 0 <= i < nmax in one compare
+        if (!CHECKED || (unsigned)i < (unsigned)nmax) {   // 0 <= i < nmax in one compare
             uint32_t left = recv, diag = diag_in;
             uint2 lu;
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lu.x), "=r"(lu.y) : "r"(lut_addr + 8u * (unsigned)i));
@@ -479,7 +509,7 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
             diag_in = recv;
             // a pair shorter than its partner reaches its last row inside the loop: fold my columns
             // into its running (first) minimum now, its half keeps computing an ignored padded DP
-            if (PK && (BULK ? i == fold_row : (i + 1 == nshort && nshort < nmax))) {
+            if (CHECKED && PK && (ROWV ? i == fold_row : (i + 1 == nshort && nshort < nmax))) {
 #pragma unroll
                 for (int c = 0; c < T; ++c) {
                     int j = r * T + c + 1;
@@ -488,6 +518,21 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
                 }
             }
         }
+    };
+    if (BULK && OVL_DP_PHASES) {
+        // Three phases with warp-uniform bounds.  For G - 1 <= k < (shortest read of the warp) - 1 every lane is inside
+        // its rows (0 <= k - r < n) and no pair ends (that needs k - r == n - 1, k >= n - 1), so the steady state runs
+        // without the range check, the fold check and the reconvergence bracket around them: 3 ALU instructions and 4
+        // control instructions fewer per step.  The few steps before and after take the checked path.
+        int k = 0;
+        const int k_lo = min(G - 1, steps);
+        for (; k < k_lo; ++k) step(k, std::true_type{});
+        const int k_hi = max(k_lo, min(steps, __reduce_min_sync(kFull, nshort) - 1));
+        for (; k < k_hi; ++k) step(k, std::false_type{});
+        for (; k < steps; ++k) step(k, std::true_type{});
+    } else {
+#pragma unroll kDpKUnroll
+        for (int k = 0; k < steps; ++k) step(k, std::true_type{});
     }
     // the pair(s) with n == nmax: after the loop every lane still holds its columns of the last row
 #pragma unroll
@@ -535,15 +580,15 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
                 end_out[p] = bestj[h];
             } else {
                 // fused K6 (overlapGraphs.py:55-60): emit the pair's copy_a x copy_b edge rows directly
-                const int32_t a = pair_a[p], b = pair_b[p];
+                const int32_t a = ld_pair(pair_a + p), b = ld_pair(pair_b + p);
                 if (eo.copies == nullptr) {
-                    eo.edges[p] = make_int4(a, b, score, bestj[h]);
+                    st_edge(eo.edges + p, make_int4(a, b, score, bestj[h]));
                 } else {
                     const int32_t ca = eo.copies[a], cb = eo.copies[b];
                     const int32_t na = (int32_t)eo.node_off[a], nb = (int32_t)eo.node_off[b];
                     int4* dst = dp_edge_dst(eo, p, a);
                     for (int32_t ia = 0; ia < ca; ++ia)
-                        for (int32_t ib = 0; ib < cb; ++ib) *dst++ = make_int4(na + ia, nb + ib, score, bestj[h]);
+                        for (int32_t ib = 0; ib < cb; ++ib) st_edge(dst++, make_int4(na + ia, nb + ib, score, bestj[h]));
                 }
             }
         }
