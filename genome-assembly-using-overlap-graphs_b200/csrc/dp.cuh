@@ -267,9 +267,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+#ifndef OVL_DP_TMA_EVICT_LAST
+#define OVL_DP_TMA_EVICT_LAST 0   // 1: the bulk copies of packed read rows carry an L2 evict_last policy (the rows are re-read by every pair)
+#endif
 __device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+#if OVL_DP_TMA_EVICT_LAST
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+#else
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
+#endif
 }
 
 // rows of the per-couple LUT array, padded so that consecutive couples start 8 banks apart
