@@ -81,6 +81,23 @@ def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
 
+def d2h_chunk_cuts(P: int, chunk_pairs: int = 1 << 62, min_chunked_pairs: int = 1_000_000):
+    """Chunk schedule of the device->host copy that runs behind the DP, as cut points in 64ths of the slice (the
+    cut points the K0-K3 job computed): 4, 8, 13, 13, 9, 6, 4, 3, 2, 1, 1.
+
+    Small chunks first so the copy engine starts early, then chunks that shrink by ~2/3 per step: every copy hides
+    behind the next DP chunk as long as copying a slice takes less than ~2/3 of computing it, and only the last 1/64
+    is exposed.  (Round 2 first used 1/2, 1/4, ... 1/64: fine while the copy costs < 1/2 of the DP -- one to four
+    GPUs -- but with eight GPUs sharing the host's 92 GB/s the copy is 0.66 of the DP and a first chunk of 1/2 left
+    50 ms of it exposed.)  chunk_pairs caps the chunk size for very long lists; short lists are not chunked."""
+    if P < min_chunked_pairs:
+        return [0, 64]
+    cuts = [0, 4, 12, 25, 38, 47, 53, 57, 60, 62, 63, 64]
+    per64 = max(1, P // 64)
+    step = max(1, chunk_pairs // per64)               # largest chunk, in 64ths
+    return [c for lo, hi in zip(cuts[:-1], cuts[1:]) for c in range(lo, hi, step)] + [64]
+
+
 class OverlapEngine:
     def __init__(self, device: Optional[int] = None):
         if not torch.cuda.is_available():
@@ -484,19 +501,7 @@ class OverlapEngine:
             return np.zeros((0, 4), np.int32)
         main = torch.cuda.current_stream(self.device)
         st = self._stream()
-        # Chunk schedule in 64ths of the slice (the cut points the job computed): 4, 8, 13, 13, 9, 6, 4, 3, 2, 1, 1.
-        # Small chunks first so the copy engine starts early, then chunks that shrink by ~2/3 per step: every copy
-        # hides behind the next DP chunk as long as copying a slice takes less than ~2/3 of computing it, and only
-        # the last 1/64 is exposed.  (Round 2 first used 1/2, 1/4, ... 1/64: fine while the copy costs < 1/2 of the
-        # DP -- one to four GPUs -- but with eight GPUs sharing the host's 92 GB/s the copy is 0.66 of the DP and a
-        # first chunk of 1/2 left 50 ms of it exposed.)  chunk_pairs caps the chunk size for very long lists.
-        if P < min_chunked_pairs:
-            cuts = [0, 64]
-        else:
-            cuts = [0, 4, 12, 25, 38, 47, 53, 57, 60, 62, 63, 64]
-            per64 = max(1, P // 64)
-            step = max(1, chunk_pairs // per64)               # largest chunk, in 64ths
-            cuts = [c for lo, hi in zip(cuts[:-1], cuts[1:]) for c in range(lo, hi, step)] + [64]
+        cuts = d2h_chunk_cuts(P, chunk_pairs, min_chunked_pairs)
         n_chunks = len(cuts) - 1
         bounds = [cand.cut_pairs[c] - cand.p_begin for c in cuts]
         e_bounds = [cand.cut_edges[c] - cand.e_begin for c in cuts]

@@ -97,3 +97,31 @@ def test_synth_generator_is_seeded_and_truncates():
     for r in reads:
         d[r] = d.get(r, 0) + 1
     assert synth.to_strings(ub, uo) == list(d.keys()) and counts.tolist() == list(d.values())
+
+
+def test_d2h_chunk_schedule_hides_the_copy():
+    """The copy of the edge rows runs behind the DP chunk by chunk (engine.d2h_chunk_cuts): the cuts must tile the
+    slice, and for a copy that costs up to 2/3 of the DP only ~1/64 of it may stay exposed."""
+    eng = load_pkg("engine")
+    assert eng.d2h_chunk_cuts(10) == [0, 64]                                   # short lists: one chunk
+    cuts = eng.d2h_chunk_cuts(10 ** 9)
+    assert cuts[0] == 0 and cuts[-1] == 64 and all(a < b for a, b in zip(cuts, cuts[1:]))
+    capped = eng.d2h_chunk_cuts(64_000_000, chunk_pairs=2_000_000)             # at most 2/64 of the slice per chunk
+    assert capped[0] == 0 and capped[-1] == 64 and max(b - a for a, b in zip(capped, capped[1:])) <= 2
+    assert set(cuts) <= set(capped) | set(range(65))
+
+    def finish(cuts, c):                       # DP produces 64 units in 64 time units; copying a unit costs c
+        t_copy = 0.0
+        for a, b in zip(cuts, cuts[1:]):
+            t_copy = max(t_copy, float(b)) + c * (b - a)      # a chunk's copy starts when it is computed and the engine is free
+        return t_copy
+
+    for c in (0.1, 0.3, 0.5, 0.66):
+        assert finish(cuts, c) <= 64 * 1.012 + c, (c, finish(cuts, c))
+    assert finish([0, 32, 48, 56, 60, 62, 63, 64], 0.66) > 64 * 1.15               # the first schedule of round 2 at 8 GPUs
+
+
+def test_numa_cpulist_parser():
+    par = load_pkg("parallel")
+    assert par._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert par._parse_cpulist("") == set()
