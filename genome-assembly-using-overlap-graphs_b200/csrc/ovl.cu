@@ -509,6 +509,9 @@ struct DpPlan {
     DpParams prm;
 };
 
+#ifndef OVL_DP_EXP_2X76
+#define OVL_DP_EXP_2X76 0
+#endif
 const int kPackedT[] = {19, 25, 32, 38, 76};   // 76 columns per lane only with 16 or 32 lanes (reads > 1,216 bases)
 const int kScalarT[] = {32};
 const int kLanes[] = {1, 2, 4, 8, 16, 32};
@@ -576,7 +579,11 @@ bool dp_plan(int32_t max_len, int64_t match, int64_t mismatch, int64_t indel, in
                 int G = kLanes[gi], T = Ts[ti];
                 if (forceG && G != forceG) continue;
                 if (forceT && T != forceT) continue;
+#if OVL_DP_EXP_2X76
+                if (T == 76 && G < 16 && !(forceG == 2 && forceT == 76)) continue;      // experiment: 2 lanes x 76 columns when forced
+#else
                 if (T == 76 && G < 16) continue;
+#endif
                 if ((int64_t)G * T < N) continue;
                 DpParams prm;
                 if (!dp_params(match, mismatch, indel, N, (int64_t)G * T, m == 1, &prm)) continue;
@@ -700,6 +707,9 @@ static int dp_dispatch(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, 
         if (imm_ok && plan.prm.gaps_never_win && plan.prm.cmax <= (int32_t)kGapNever - 1 && plan.prm.cmax + (int64_t)kGapNever <= 65535) {
             DP_CASES_IMM_T(19) DP_CASES_IMM_T(25) DP_CASES_IMM_T(32) DP_CASES_IMM_T(38)
             DP_CASE_IMM(16, 76) DP_CASE_IMM(32, 76)
+#if OVL_DP_EXP_2X76
+            DP_CASE_IMM(2, 76)
+#endif
         }
         DP_CASES_T(19, true) DP_CASES_T(25, true) DP_CASES_T(32, true) DP_CASES_T(38, true)
         DP_CASE(16, 76, true) DP_CASE(32, 76, true)

@@ -47,10 +47,10 @@ def main():
     ref = None
     for mode in ([] if args.probe_only else [int(x) for x in args.modes.split(",")]):
         for lanes in (1, 2, 4, 8, 16, 32):
-            for cols in ((19, 25, 32, 38) if mode == 1 else (32,)):
+            for cols in ((19, 25, 32, 38, 76) if mode == 1 else (32,)):
                 if lanes * cols < rs.max_len or lanes * cols > 4 * max(rs.max_len, 38):
                     continue
-                if args.only and args.only != f"{lanes}x{cols}":
+                if args.only and f"{lanes}x{cols}" not in args.only.split(","):
                     continue
                 try:
                     s, e = eng.overlap_scores(rs, pa, pb, 10, -1, args.indel, mode=mode, lanes=lanes, cols=cols)
