@@ -62,6 +62,22 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint64_t*
     for (int d = threadIdx.x; d < nd; d += kSortThreads) hist[(int64_t)d * C + blockIdx.x] = cnt[d];
 }
 
+// One CTA per digit: in-place exclusive scan of the digit's per-CTA counts hist[d * C .. d * C + C) and the digit's
+// total.  Together with the scan of the (at most 1,024) digit totals that every scatter CTA does for itself this
+// replaces the three-kernel scan over the whole [digit][cta] array: one launch between histogram and scatter.
+__global__ void __launch_bounds__(kScanThreads) sort_digit_scan_kernel(int32_t* __restrict__ hist, int64_t C,
+                                                                       int32_t* __restrict__ digit_total) {
+    __shared__ int32_t sm[kScanThreads / 32 + 1];
+    __shared__ int32_t tile[scan_smem_elems<int32_t>()];
+    int32_t* mine = hist + (int64_t)blockIdx.x * C;
+    const LoadArray<int32_t> f{mine};
+    const StoreArray<int32_t> store{mine};
+    int32_t carry = 0;
+    for (int64_t start = 0; start < C; start += scan_tile<int32_t>())
+        carry += scan_one_tile<LoadArray<int32_t>, StoreArray<int32_t>, int32_t>(f, store, start, C, carry, tile, sm);
+    if (threadIdx.x == 0) digit_total[blockIdx.x] = carry;
+}
+
 // Stable scatter of the CTA's chunk to the scanned offsets.  Warp w owns elements [256 w, 256 w + 256) of the
 // chunk and ranks them among themselves (8 rounds of __match_any_sync); the CTA scans the per-warp digit
 // counts into CTA-local sorted positions, the elements are staged in shared memory in that order, and
@@ -77,6 +93,8 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint64
                                                                     const int64_t* __restrict__ n_ptr, int64_t n_static,
                                                                     int shift, int digit_bits, int64_t C,
                                                                     const int32_t* __restrict__ hist_scanned,
+                                                                    const int32_t* __restrict__ digit_total,
+                                                                    int32_t* __restrict__ table_out,
                                                                     uint64_t* __restrict__ keys_out,
                                                                     uint32_t* __restrict__ uid_out,
                                                                     int32_t* __restrict__ pos_of,
@@ -91,12 +109,11 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint64
     __shared__ uint64_t keys_s[kSortChunk];
     __shared__ uint32_t uid_s[kSortChunk];
     __shared__ int32_t warp_sums[kSortWarps + 1];
+    __shared__ int32_t warp_tot[kSortWarps + 1];                  // the same block scan over the digit totals
     const int nd = 1 << digit_bits;
     const unsigned mask = (unsigned)nd - 1u;
     const int64_t n = FIRST ? n_static : *n_ptr;
     const int64_t base = (int64_t)blockIdx.x * kSortChunk;
-    if (FIRST && n_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
-        *n_out = (int64_t)hist_scanned[(int64_t)nd * C];           // grand total of the scan = reads with len >= k
     if (base >= n) return;
     const int wib = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < nd; i += kSortThreads) *reinterpret_cast<uint4*>(&wcnt[i][0]) = make_uint4(0u, 0u, 0u, 0u);
@@ -138,36 +155,51 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint64
     {
         int32_t cnt[DPT];
         int32_t mine = 0;
+        int32_t tot[DPT];                      // global totals of my digits (hist_scanned is scanned per digit only)
+        int32_t tmine = 0;
         uint4 vec[DPT];
 #pragma unroll
         for (int x = 0; x < DPT; ++x) {
             const int d = threadIdx.x * DPT + x;
+            tot[x] = d < nd ? digit_total[d] : 0;
+            tmine += tot[x];
             vec[x] = d < nd ? *reinterpret_cast<const uint4*>(&wcnt[d][0]) : make_uint4(0u, 0u, 0u, 0u);
             const uint32_t w01 = vec[x].x, w23 = vec[x].y, w45 = vec[x].z, w67 = vec[x].w;
             cnt[x] = (int32_t)((w01 & 0xffffu) + (w01 >> 16) + (w23 & 0xffffu) + (w23 >> 16) +
                                (w45 & 0xffffu) + (w45 >> 16) + (w67 & 0xffffu) + (w67 >> 16));
             mine += cnt[x];
         }
-        int32_t inc = mine;
+        int32_t inc = mine, tinc = tmine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int32_t v = __shfl_up_sync(kFull, inc, o);
-            if ((int)lane_id() >= o) inc += v;
+            int32_t tv = __shfl_up_sync(kFull, tinc, o);
+            if ((int)lane_id() >= o) { inc += v; tinc += tv; }
         }
-        if (lane_id() == 31) warp_sums[wib] = inc;
+        if (lane_id() == 31) { warp_sums[wib] = inc; warp_tot[wib] = tinc; }
         __syncthreads();
         if (threadIdx.x == 0) {
-            int32_t run = 0;
-            for (int w = 0; w < kSortWarps; ++w) { int32_t t = warp_sums[w]; warp_sums[w] = run; run += t; }
+            int32_t run = 0, trun = 0;
+            for (int w = 0; w < kSortWarps; ++w) {
+                int32_t t = warp_sums[w]; warp_sums[w] = run; run += t;
+                int32_t tt = warp_tot[w]; warp_tot[w] = trun; trun += tt;
+            }
             warp_sums[kSortWarps] = run;                           // live elements of the CTA
+            warp_tot[kSortWarps] = trun;                           // live elements of the whole input
+            if (FIRST && n_out != nullptr && blockIdx.x == 0) *n_out = (int64_t)trun;      // reads with len >= k
+            if (table_out != nullptr && blockIdx.x == 0) table_out[nd] = trun;
         }
         __syncthreads();
         int32_t lstart = inc - mine + warp_sums[wib];
+        int32_t gbase = tinc - tmine + warp_tot[wib];              // first sorted position of my first digit
 #pragma unroll
         for (int x = 0; x < DPT; ++x) {
             const int d = threadIdx.x * DPT + x;
             if (d < nd) {
-                delta[d] = hist_scanned[(int64_t)d * C + blockIdx.x] - lstart;
+                // one pass over the whole key: the digit's first position IS the bucket table entry
+                if (table_out != nullptr && blockIdx.x == 0) table_out[d] = gbase;
+                delta[d] = gbase + hist_scanned[(int64_t)d * C + blockIdx.x] - lstart;
+                gbase += tot[x];
                 // exclusive prefix over the eight warps, starting at the digit's local start
                 uint32_t c[8] = {vec[x].x & 0xffffu, vec[x].x >> 16, vec[x].y & 0xffffu, vec[x].y >> 16,
                                  vec[x].z & 0xffffu, vec[x].z >> 16, vec[x].w & 0xffffu, vec[x].w >> 16};

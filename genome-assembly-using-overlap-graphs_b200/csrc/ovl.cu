@@ -182,12 +182,17 @@ int ovl_kmer_hashes(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, con
 static inline int64_t sort_warps(int64_t U) { return (U + kSortChunk - 1) / kSortChunk; }
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// the digit totals of one sort pass (or the tile sums of a generic scan, whichever is larger)
+static inline size_t index_sums_bytes(int64_t hn) {
+    return align256(std::max(scan_workspace_bytes(hn, sizeof(int32_t)), (((size_t)1 << kSortMaxDigit) + 1) * sizeof(int32_t)));
+}
+
 size_t ovl_index_workspace_bytes(int64_t U) {
     if (U < 1) U = 1;
     int64_t W = sort_warps(U);
     int64_t hn = ((int64_t)1 << kSortMaxDigit) * W;
     size_t hist = align256((size_t)(hn + 1) * sizeof(int32_t));
-    size_t sums = align256(scan_workspace_bytes(hn, sizeof(int32_t)));
+    size_t sums = index_sums_bytes(hn);
     size_t keys = align256((size_t)U * sizeof(uint64_t));
     size_t uids = align256((size_t)U * sizeof(uint32_t));
     return hist + sums + keys + uids + 256;
@@ -225,7 +230,7 @@ int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len
     int64_t hn_max = ((int64_t)1 << kSortMaxDigit) * W;
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     int32_t* hist = (int32_t*)ws;                 ws += align256((size_t)(hn_max + 1) * sizeof(int32_t));
-    void* sums = ws;                              ws += align256(scan_workspace_bytes(hn_max, sizeof(int32_t)));
+    int32_t* digit_total = (int32_t*)ws;          ws += index_sums_bytes(hn_max);
     uint64_t* tmp_key = (uint64_t*)ws;            ws += align256((size_t)U * sizeof(uint64_t));
     uint32_t* tmp_uid = (uint32_t*)ws;
 
@@ -243,8 +248,9 @@ int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len
     for (int p = 0; p < passes; ++p) {
         int shift = D * p;
         int bits = std::min(D, key_bits - shift);
-        int64_t hn = ((int64_t)1 << bits) * W;
         const bool last_pass = p == passes - 1;
+        // a single pass over the whole key with a table as wide as the key: the scatter writes the table itself
+        int32_t* table_direct = (table && passes == 1 && table_bits == key_bits) ? table : nullptr;
         int32_t* pos_out = last_pass ? pos_of : nullptr;
         int32_t* sc_out = last_pass ? sorted_copies : nullptr;
         if (p == 0) {
@@ -253,13 +259,14 @@ int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len
             sort_hist_kernel<false><<<grid, kSortThreads, 0, st>>>(src_key, len, k, n_indexed, 0, shift, bits, W, hist);
         }
         LAUNCH_CHECK("sort_hist_kernel");
-        CUDA_TRY((exclusive_scan<LoadArray<int32_t>, int32_t>(LoadArray<int32_t>{hist}, hist, hn, sums, st, &nl)));
+        sort_digit_scan_kernel<<<1u << bits, kScanThreads, 0, st>>>(hist, W, digit_total);
+        LAUNCH_CHECK("sort_digit_scan_kernel");
         if (p == 0) {
-            sort_scatter_kernel<true><<<grid, kSortThreads, 0, st>>>(src_key, nullptr, len, k, nullptr, U, shift, bits, W, hist,
-                                                                     kbuf[dst], ubuf[dst], pos_out, copies, sc_out, n_indexed);
+            sort_scatter_kernel<true><<<grid, kSortThreads, 0, st>>>(src_key, nullptr, len, k, nullptr, U, shift, bits, W, hist, digit_total,
+                                                                     table_direct, kbuf[dst], ubuf[dst], pos_out, copies, sc_out, n_indexed);
         } else {
-            sort_scatter_kernel<false><<<grid, kSortThreads, 0, st>>>(src_key, src_uid, len, k, n_indexed, 0, shift, bits, W, hist,
-                                                                      kbuf[dst], ubuf[dst], pos_out, copies, sc_out, nullptr);
+            sort_scatter_kernel<false><<<grid, kSortThreads, 0, st>>>(src_key, src_uid, len, k, n_indexed, 0, shift, bits, W, hist, digit_total,
+                                                                      table_direct, kbuf[dst], ubuf[dst], pos_out, copies, sc_out, nullptr);
         }
         LAUNCH_CHECK("sort_scatter_kernel");
         src_key = kbuf[dst];
@@ -267,7 +274,7 @@ int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len
         dst ^= 1;
     }
     ctx->launches += nl;
-    if (table) {
+    if (table && !(passes == 1 && table_bits == key_bits)) {
         bucket_table_kernel<<<grid_for(U + 1, 256), 256, 0, st>>>(sorted_key, n_indexed, key_bits - table_bits, table_bits, table);
         LAUNCH_CHECK("bucket_table_kernel");
     }
