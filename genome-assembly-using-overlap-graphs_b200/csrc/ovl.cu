@@ -178,7 +178,7 @@ int ovl_kmer_hashes(ovl_ctx* ctx, const uint32_t* packed, int32_t row_words, con
 }
 
 // ---------------------------------------------------------------- K2
-// workspace: [hist int32 2^D*C + 1][scan sums][tmp keys u64 U][tmp uids u32 U]     (C = CTAs of 2,048 elements)
+// workspace: [hist int32 2^D*C + 1][scan sums][tmp keys u64 U][tmp uids u32 U]     (C = CTAs of kSortChunk = 4,096 elements)
 static inline int64_t sort_warps(int64_t U) { return (U + kSortChunk - 1) / kSortChunk; }
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -235,6 +235,14 @@ int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len
     uint32_t* tmp_uid = (uint32_t*)ws;
 
     if (sorted_copies) CUDA_TRY(cudaMemsetAsync(sorted_copies, 0, (size_t)U * sizeof(int32_t), st));   // zero past the end of the index
+    if (kSortStageBytes + 24 * 1024 > 48 * 1024) {      // the kernel also has ~22 KB of static shared memory
+        static bool attr_set = false;               // per process: the attribute belongs to the function, not the context
+        if (!attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(sort_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortStageBytes));
+            CUDA_TRY(cudaFuncSetAttribute(sort_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortStageBytes));
+            attr_set = true;
+        }
+    }
     const int passes = sort_passes(key_bits);
     const int D = sort_digit_bits(key_bits);
     int nl = 0;
@@ -242,7 +250,7 @@ int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len
     uint64_t* kbuf[2] = {sorted_key, tmp_key};
     uint32_t* ubuf[2] = {sorted_uid, tmp_uid};
     int dst = (passes & 1) ? 0 : 1;
-    unsigned grid = (unsigned)W;                        // one CTA per 2,048-element chunk
+    unsigned grid = (unsigned)W;                        // one CTA per kSortChunk-element chunk
     const uint64_t* src_key = prefix_key;
     const uint32_t* src_uid = nullptr;
     for (int p = 0; p < passes; ++p) {
@@ -262,10 +270,10 @@ int ovl_index_build(ovl_ctx* ctx, const uint64_t* prefix_key, const int32_t* len
         sort_digit_scan_kernel<<<1u << bits, kScanThreads, 0, st>>>(hist, W, digit_total);
         LAUNCH_CHECK("sort_digit_scan_kernel");
         if (p == 0) {
-            sort_scatter_kernel<true><<<grid, kSortThreads, 0, st>>>(src_key, nullptr, len, k, nullptr, U, shift, bits, W, hist, digit_total,
+            sort_scatter_kernel<true><<<grid, kSortThreads, kSortStageBytes, st>>>(src_key, nullptr, len, k, nullptr, U, shift, bits, W, hist, digit_total,
                                                                      table_direct, kbuf[dst], ubuf[dst], pos_out, copies, sc_out, n_indexed);
         } else {
-            sort_scatter_kernel<false><<<grid, kSortThreads, 0, st>>>(src_key, src_uid, len, k, n_indexed, 0, shift, bits, W, hist, digit_total,
+            sort_scatter_kernel<false><<<grid, kSortThreads, kSortStageBytes, st>>>(src_key, src_uid, len, k, n_indexed, 0, shift, bits, W, hist, digit_total,
                                                                       table_direct, kbuf[dst], ubuf[dst], pos_out, copies, sc_out, nullptr);
         }
         LAUNCH_CHECK("sort_scatter_kernel");
