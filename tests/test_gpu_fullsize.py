@@ -211,3 +211,29 @@ def test_config3_long_reads_full_size():
             rows = eng.overlap_edges_fused(rs, pa, pb)
             assert torch.equal(rows, torch.stack((pa, pb, s, e), dim=1))
         del pa, pb, idx
+
+
+@pytest.mark.parametrize("k", [5, 6])
+def test_index_beyond_one_scan_tile_of_sort_ctas(k):
+    """17 M short reads: more sort CTAs (4,151 of 4,096 elements) than one tile of the per-digit scan holds, with a
+    single-pass index whose bucket table comes straight from the digit totals (k = 5) and a two-pass one (k = 6).
+    Checked against torch's stable sort of the same keys: sorted keys, uid order inside equal keys, bucket table."""
+    import torch
+    eng = load_pkg("engine").get_engine()
+    dev = eng.device
+    U, L = 17_000_000, 12
+    g = torch.Generator(device=dev).manual_seed(99 + k)
+    letters = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    ascii_dev = torch.empty(U * L + 64, dtype=torch.uint8, device=dev)
+    ascii_dev[:U * L] = letters[torch.randint(0, 4, (U * L,), device=dev, generator=g)]
+    off_dev = torch.arange(U + 1, dtype=torch.int64, device=dev) * L
+    rs = eng.pack_reads(ascii_dev, off_dev, U, L)
+    idx = eng.kmer_index(rs, k)
+    n = int(idx.n_indexed.item())
+    assert n == U
+    want_key, want_uid = torch.sort(idx.prefix_key[:U], stable=True)          # keys < 2^12: the int64 view orders like uint64
+    assert torch.equal(idx.sorted_key[:U], want_key)
+    assert torch.equal(idx.sorted_uid[:U].to(torch.int64), want_uid)
+    assert idx.table is not None and idx.table_bits == 2 * k
+    t = torch.arange((1 << idx.table_bits) + 1, device=dev, dtype=torch.int64)
+    assert torch.equal(idx.table.to(torch.int64), torch.searchsorted(want_key, t))
