@@ -3,6 +3,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// -DOVL_BOUNDS_CHECKS=1 compiles index checks into the kernels (every shared-memory table access and scattered global
+// store the index of which is computed from data): a violated check traps, which fails the launch and with it the
+// test that made it.  compute-sanitizer is closed on the GPU pool, so the GPU suite is also run once against a library
+// built this way (tools/gpu_round23.sh, profiles/r3k_pytest_gpu_bounds_checked.log).
+#ifndef OVL_BOUNDS_CHECKS
+#define OVL_BOUNDS_CHECKS 0
+#endif
+#if OVL_BOUNDS_CHECKS
+#define OVL_CHECK(cond) do { if (!(cond)) __trap(); } while (0)
+#else
+#define OVL_CHECK(cond) do { } while (0)
+#endif
+
 namespace ovl {
 
 constexpr int kWarp = 32;

@@ -186,6 +186,7 @@ __device__ __forceinline__ void base_window(const uint32_t* row, int row_words, 
     const int i0 = first >> 4;
     const int sh = (first & 15) * 2;
     uint32_t a[NW + 1];
+    OVL_CHECK(first >= 0 && row_words >= 1);
 #pragma unroll
     for (int i = 0; i <= NW; ++i) a[i] = row[min(i0 + i, row_words - 1)];
 #pragma unroll
@@ -375,6 +376,7 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
             const int sft = 2 * (c & 15);
             const uint32_t xa = nec4 ^ (flip << base_field(sa[c >> 4], sft, 3));      // byte ca of the table = eqc
             const uint32_t xb = nec4 ^ (flip << base_field(sb[c >> 4], sft, 3));
+            OVL_CHECK(i >= 0 && i < lut_rows);
             lut[i] = make_uint2(xa, xb);         // unconditional: the table has G*T rows (launch_dp); rows >= nmax are never read
         }
     } else {
@@ -383,6 +385,7 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
         for (int i = r; i < nmax; i += G) {
             uint32_t ca = read_symbol<BITS>(srow[0], min(i, max_col));
             uint32_t cb = read_symbol<BITS>(srow[PAIRS - 1], min(i, max_col));
+            OVL_CHECK(i < lut_rows);
             if (BITS == 8)      lut[i] = make_uint2(PK ? (ca | (cb << 16)) : ca, 0u);     // the two query symbols
             else                lut[i] = PK ? make_uint2(nec4 ^ (flip << (8 * ca)), nec4 ^ (flip << (8 * cb))) : make_uint2(ca, 0u);
         }
@@ -466,6 +469,7 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
         if (!CHECKED || (unsigned)i < (unsigned)nmax) {   // 0 <= i < nmax in one compare
             uint32_t left = recv, diag = diag_in;
             uint2 lu;
+            OVL_CHECK(i >= 0 && i < lut_rows);
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lu.x), "=r"(lu.y) : "r"(lut_addr + 8u * (unsigned)i));
 #pragma unroll
             for (int c = 0; c < T; ++c) {
@@ -585,6 +589,7 @@ __global__ void __launch_bounds__(kDpThreads, (T > 38 ? 2 : (IMMG && T == 38) ? 
         int64_t p = p0 + h;
         if (r == 0 && p < P) {
             const int32_t score = prm.beta + n[h] * prm.maxs - bestv[h];
+            OVL_CHECK(p >= 0 && p < P);
             if (eo.edges == nullptr) {
                 score_out[p] = score;
                 end_out[p] = bestj[h];

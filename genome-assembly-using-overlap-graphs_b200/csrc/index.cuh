@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint64
         if (rank[r] < 0) continue;
         const unsigned d = (unsigned)(key[r] >> shift) & mask;
         const int lp = (int)wcnt[d][wib] + rank[r];
+        OVL_CHECK(lp >= 0 && lp < warp_sums[kSortWarps] && lp < kSortChunk);
         keys_s[lp] = key[r];
         uid_s[lp] = uid[r];
     }
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint64
         const uint64_t kk = keys_s[j];
         const uint32_t uu = uid_s[j];
         const int pos = delta[(unsigned)(kk >> shift) & mask] + j;
+        OVL_CHECK(pos >= 0 && pos < warp_tot[kSortWarps]);
         keys_out[pos] = kk;
         uid_out[pos] = uu;
         if (pos_of != nullptr) pos_of[uu] = pos;
@@ -294,6 +296,7 @@ __global__ void __launch_bounds__(256) join_count_kernel(const uint64_t* __restr
             const uint64_t t = key >> shift;
             lo = table[t];
             hi = table[t + 1];
+            OVL_CHECK(lo >= 0 && lo <= hi && hi <= *n_indexed);
             if (shift != 0) {                           // the table narrowed the range: finish inside it
                 lo = lower_bound<uint64_t>(sorted_key, lo, hi, key);
                 hi = upper_bound<uint64_t>(sorted_key, lo, hi, key);
@@ -436,11 +439,13 @@ __global__ void __launch_bounds__(256) join_fill_group_kernel(const int64_t* __r
         for (int j = 0; j < 4; ++j) {
             int32_t r = (int32_t)(p + LANES * j - first);
             if (sr >= 0 && r >= sr) r += 1;
+            OVL_CHECK(r >= 0 && (int64_t)r <= last - first);        // the bucket holds the candidates and, at most, the read itself
             b[j] = (int32_t)bucket[r];
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int64_t q = p + LANES * j - p_begin;
+            OVL_CHECK(q >= 0 && q < p_count);
             __stcs(pair_a + q, a);                      // streaming: the GBs of pairs must not evict the index from L2
             __stcs(pair_b + q, b[j]);
         }
@@ -449,6 +454,7 @@ __global__ void __launch_bounds__(256) join_fill_group_kernel(const int64_t* __r
         int32_t r = (int32_t)(p - first);
         if (sr >= 0 && r >= sr) r += 1;
         int64_t q = p - p_begin;
+        OVL_CHECK(q >= 0 && q < p_count);
         __stcs(pair_a + q, a);
         __stcs(pair_b + q, (int32_t)bucket[r]);
     }

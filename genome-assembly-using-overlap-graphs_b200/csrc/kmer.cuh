@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(kPackThreads, OVL_PACK_MINB) pack_reads_kernel
             const uint32_t m0 = codes4(x[0], bad), m1 = codes4(x[1], bad), m2 = codes4(x[2], bad), m3 = codes4(x[3], bad);
             w = __byte_perm(__byte_perm(m0, m1, 0x0073), __byte_perm(m2, m3, 0x0073), 0x5410);
         }
+        OVL_CHECK(p >= 0 && p < kPackPieces + 3);
         bits[p] = w;                                 // three zero words of padding after the stream
     }
     if (bad) atomicAdd(bad_count, 1);
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(kPackThreads, OVL_PACK_MINB) pack_reads_kernel
             const int nv = nvalid - 16 * w;
             if (nv > 0) {
                 const int bit = bit0 + 32 * w;
+                OVL_CHECK(bit >= 0 && (bit >> 5) + 1 < kPackPieces + 3);
                 uint32_t x = __funnelshift_r(bits[bit >> 5], bits[(bit >> 5) + 1], bit & 31);
                 if (nv < 16) x &= (1u << (2 * nv)) - 1u;
                 o[w] = x;
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(kPackThreads, OVL_PACK_MINB) pack_reads_kernel
             if (len >= k) {
                 const int bit = 2 * (int)(o0 + len - k - span_base);      // >= 0: the span starts 32 bases before my slot
                 const int i = bit >> 5, sh = bit & 31;
+                OVL_CHECK(bit >= 0 && i + 2 < kPackPieces + 3);
                 const uint32_t a = bits[i], b = bits[i + 1], c = bits[i + 2];
                 sk = ((((uint64_t)__funnelshift_r(b, c, sh) << 32) | __funnelshift_r(a, b, sh)) & mask) | tag;
             }
