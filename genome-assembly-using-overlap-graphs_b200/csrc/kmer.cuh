@@ -27,6 +27,9 @@ constexpr uint64_t kInvalidKey = ~0ull;
 constexpr int kPackThreads = 256;
 constexpr int kPackPieces = (kPackThreads * 64 + 32 + 16) / 16 + 2;      // 16-byte pieces a CTA's span can touch
 constexpr int kPackIters = (kPackPieces + 3 + kPackThreads - 1) / kPackThreads;      // rounds of the conversion loop (5)
+#ifndef OVL_PACK_PRELOADS
+#define OVL_PACK_PRELOADS 4          // rounds of the conversion loop whose 16-byte load is issued up front (4: 32 registers, no spill, 435 us at 8 M reads; 5: two spilled words, 454 us; 3: 444 us)
+#endif
 #ifndef OVL_PACK_MINB
 #define OVL_PACK_MINB 8                  // resident CTAs per SM: measured at 8 M reads 455 us (8, two spilled words) / 465 (6) / 496 (5) / 555 (4); the loop without the preloads: 475
 #endif
@@ -81,9 +84,10 @@ __global__ void __launch_bounds__(kPackThreads, OVL_PACK_MINB) pack_reads_kernel
     uint32_t bad = 0;
     // all of the thread's 16-byte loads are issued before the first conversion (memory-level parallelism: a CTA's
     // span is at most kPackPieces pieces = kPackIters rounds)
-    uint4 v[kPackIters];
+    constexpr int kPre = OVL_PACK_PRELOADS < kPackIters ? OVL_PACK_PRELOADS : kPackIters;   // rounds whose load is issued up front
+    uint4 v[kPre];
 #pragma unroll
-    for (int it = 0; it < kPackIters; ++it) {
+    for (int it = 0; it < kPre; ++it) {
         const int p = it * kPackThreads + threadIdx.x;
         v[it] = p < n_pieces ? __ldg(reinterpret_cast<const uint4*>(ascii + span_base + 16 * (int64_t)p)) : make_uint4(0u, 0u, 0u, 0u);
     }
@@ -94,7 +98,8 @@ __global__ void __launch_bounds__(kPackThreads, OVL_PACK_MINB) pack_reads_kernel
         uint32_t w = 0;
         if (p < n_pieces) {
             const int64_t g = span_base + 16 * (int64_t)p;
-            uint32_t x[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+            const uint4 vv = it < kPre ? v[it < kPre ? it : 0] : __ldg(reinterpret_cast<const uint4*>(ascii + g));   // the last round holds at most 8 pieces
+            uint32_t x[4] = {vv.x, vv.y, vv.z, vv.w};
             if (g + 16 > total_bytes) {              // the slack after the last read is not input: treat it as 'A'
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
