@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) join_count_kernel(const uint64_t* __restr
                                                          const int32_t* __restrict__ pos_of,
                                                          const int32_t* __restrict__ copies, const int64_t* __restrict__ cum,
                                                          int32_t* __restrict__ lo_out, int32_t* __restrict__ self_rank,
-                                                         int64_t* __restrict__ cnt_single, I64x2* __restrict__ cnt_pair) {
+                                                         int32_t* __restrict__ cnt_single, I64x2* __restrict__ cnt_pair) {
     const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= U) return;
     int64_t cnt = 0, ecnt = 0;
@@ -308,11 +308,16 @@ __global__ void __launch_bounds__(256) join_count_kernel(const uint64_t* __restr
         }
         cnt = hi - lo;
         lo32 = (int32_t)lo;
-        bool self = prefix_key[a] == key;               // a sits in its own bucket
-        if (self) {
-            sr = pos_of != nullptr ? pos_of[a] - lo32 : (int32_t)(lower_bound<uint32_t>(sorted_uid, lo, hi, (uint32_t)a) - lo);
-            cnt -= 1;
+        bool self;                                      // a sits in its own bucket
+        if (pos_of != nullptr) {
+            const int64_t mine = pos_of[a];             // a's own sorted position: inside [lo, hi) iff its prefix equals its suffix
+            self = mine >= lo && mine < hi;
+            if (self) sr = (int32_t)(mine - lo);
+        } else {
+            self = prefix_key[a] == key;
+            if (self) sr = (int32_t)(lower_bound<uint32_t>(sorted_uid, lo, hi, (uint32_t)a) - lo);
         }
+        if (self) cnt -= 1;
         if (copies != nullptr) {
             const int64_t ca = copies[a];
             ecnt = ca * (cum[hi] - cum[lo] - (self ? ca : 0));
@@ -321,7 +326,7 @@ __global__ void __launch_bounds__(256) join_count_kernel(const uint64_t* __restr
     lo_out[a] = lo32;
     self_rank[a] = sr;
     if (cnt_pair != nullptr) cnt_pair[a] = I64x2{cnt, ecnt};
-    else cnt_single[a] = cnt;
+    else cnt_single[a] = (int32_t)cnt;          // a bucket holds fewer than 2^31 reads: 4-byte counts, scanned into 8-byte offsets
 }
 
 // Layout of the `totals` block join_finalize writes (int64 words), read by the host after one sync.

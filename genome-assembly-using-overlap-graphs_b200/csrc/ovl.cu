@@ -324,13 +324,13 @@ int ovl_join_count(ovl_ctx* ctx, const uint64_t* suffix_key, const uint64_t* pre
     if (U > 0) {
         join_count_kernel<<<grid_for(U, 256), 256, 0, st>>>(suffix_key, prefix_key, len, k, U, sorted_key, sorted_uid, n_indexed, table,
                                                              table ? key_bits - table_bits : 0, pos_of, copies, cum, bucket_lo, self_rank,
-                                                             copies ? nullptr : (int64_t*)cnt, copies ? (I64x2*)cnt : nullptr);
+                                                             copies ? nullptr : (int32_t*)cnt, copies ? (I64x2*)cnt : nullptr);
         LAUNCH_CHECK("join_count_kernel");
     }
     if (copies) {
         CUDA_TRY((exclusive_scan_to<LoadArray<I64x2>, StoreSplit, I64x2>(LoadArray<I64x2>{(const I64x2*)cnt}, StoreSplit{pair_off, edge_base}, U, sums, st, &nl)));
     } else {
-        CUDA_TRY((exclusive_scan<LoadArray<int64_t>, int64_t>(LoadArray<int64_t>{(const int64_t*)cnt}, pair_off, U, sums, st, &nl)));
+        CUDA_TRY((exclusive_scan<LoadArray<int32_t>, int64_t>(LoadArray<int32_t>{(const int32_t*)cnt}, pair_off, U, sums, st, &nl)));
     }
     ctx->launches += nl;
     return OVL_OK;
