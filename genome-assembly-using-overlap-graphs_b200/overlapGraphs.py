@@ -90,9 +90,26 @@ def _graph_from_rows(uniq, counts, edges):
     overlap_graph.add_nodes_from(names)
     if edges.shape[0]:
         cols = edges.T.tolist()               # Python ints, like the reference's edge attributes
-        overlap_graph.add_edges_from(
-            (names[u], names[v], {"weight": w, "end_position": e})
-            for u, v, w, e in zip(cols[0], cols[1], cols[2], cols[3]))
+        succ, pred = getattr(overlap_graph, "_succ", None), getattr(overlap_graph, "_pred", None)
+        if (isinstance(succ, dict) and isinstance(pred, dict) and overlap_graph.edge_attr_dict_factory is dict
+                and overlap_graph.adjlist_inner_dict_factory is dict):
+            # What add_edges_from builds edge by edge -- ONE attribute dict shared by _succ[u][v] and _pred[v][u], rows
+            # in insertion order -- without its per-edge membership tests and dict copies (a quarter of the wall time
+            # of a 3 M-edge graph).  Every (u, v) occurs once (reads are unique, copies are distinct nodes), so no
+            # edge is ever updated, and all nodes exist already.
+            srow = [succ[n] for n in names]
+            prow = [pred[n] for n in names]
+            for u, v, w, e in zip(cols[0], cols[1], cols[2], cols[3]):
+                d = {"weight": w, "end_position": e}
+                srow[u][names[v]] = d
+                prow[v][names[u]] = d
+            clear = getattr(nx, "_clear_cache", None)
+            if clear is not None:
+                clear(overlap_graph)
+        else:
+            overlap_graph.add_edges_from(
+                (names[u], names[v], {"weight": w, "end_position": e})
+                for u, v, w, e in zip(cols[0], cols[1], cols[2], cols[3]))
     return overlap_graph
 
 

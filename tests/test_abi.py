@@ -125,3 +125,35 @@ def test_numa_cpulist_parser():
     par = load_pkg("parallel")
     assert par._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
     assert par._parse_cpulist("") == set()
+
+
+def test_graph_from_rows_equals_networkx_edge_by_edge():
+    import numpy as np
+    """overlapGraphs._graph_from_rows fills the DiGraph's adjacency directly; the result must be indistinguishable from
+    add_node / add_edge in the reference's order (nodes, adjacency order, predecessor order, shared attribute dicts)."""
+    import networkx as nx
+    og = load_pkg("overlapGraphs")
+    rng = np.random.default_rng(5)
+    uniq = ["ACGT" * 3 + str(i) for i in range(40)]
+    counts = rng.integers(1, 4, len(uniq)).astype(np.int32)
+    n_nodes = int(counts.sum())
+    pairs = sorted({(int(a), int(b)) for a, b in rng.integers(0, n_nodes, (600, 2)) if a != b})
+    edges = np.array([(a, b, int(rng.integers(-5, 1500)), int(rng.integers(0, 150))) for a, b in pairs], dtype=np.int32)
+    got = og._graph_from_rows(uniq, counts, edges)
+    names = [f"{r}_{c}" for r, cnt in zip(uniq, counts.tolist()) for c in range(cnt)]
+    want = nx.DiGraph()
+    for n in names:
+        want.add_node(n)
+    for a, b, w, e in edges.tolist():
+        want.add_edge(names[a], names[b], weight=w, end_position=e)
+    assert list(got.nodes) == list(want.nodes)
+    assert list(got.edges(data=True)) == list(want.edges(data=True))
+    assert all(list(got.pred[n]) == list(want.pred[n]) for n in names)
+    assert got.number_of_edges() == len(pairs) and nx.is_isomorphic(got, want) is True
+    u, v = names[pairs[0][0]], names[pairs[0][1]]
+    assert got[u][v] is got.pred[v][u]                      # one dict per edge, as NetworkX keeps it
+    assert all(type(d["weight"]) is int and type(d["end_position"]) is int for _, _, d in got.edges(data=True))
+    got.remove_edge(u, v)                                   # the caller mutates the graph (overlapGraphs.py:117)
+    assert not got.has_edge(u, v) and u not in got.pred[v]
+    empty = og._graph_from_rows(uniq, counts, np.zeros((0, 4), np.int32))
+    assert list(empty.nodes) == names and empty.number_of_edges() == 0
